@@ -1,0 +1,79 @@
+/*
+ * sw_types.h — plain-C value types shared by the CUDA library (swgpu.h), the CPU oracle
+ * (oracle/) and the host adapters.  No torch / CUDA types appear here.
+ *
+ * Reference concepts mirrored (paths relative to /root/reference/schwarzwald):
+ *   sw_sampling        <-> names accepted by make_sampling_strategy_from_name,
+ *                          core/tiling/Sampling.h:774-791
+ *   sw_tiling          <-> TilingStrategy {Accurate, Fast}, core/process/Tiler.cpp:189-198
+ *   sw_params          <-> TilerMetaParameters, core/process/Tiler.h:64-75 (+ dataset bounds,
+ *                          Tiler.cpp:185-187) and the indexing thread count that
+ *                          TilingAlgorithmV3::estimate_start_node_level_in_octree depends on
+ *                          (core/tiling/TilingAlgorithms.cpp:1473-1535)
+ *   sw_node            <-> OctreeNodeIndex64 {index, levels}
+ *                          (core/datastructures/OctreeNodeIndex.h:118-579) plus the slice of the
+ *                          node-major point-id array that persist_points() would receive
+ *                          (core/io/PointsPersistence.h:23-31)
+ */
+#ifndef SW_TYPES_H
+#define SW_TYPES_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sw_sampling {
+  SW_RANDOM_GRID = 0,  /* RandomSortedGridSampling, Sampling.h:187-308 */
+  SW_GRID_CENTER = 1,  /* GridCenterSampling,       Sampling.h:314-416 */
+  SW_MIN_DISTANCE = 2, /* PoissonDiskSampling,      Sampling.h:421-471 */
+  SW_JITTERED = 3      /* JitteredSampling,         Sampling.h:598-759 */
+} sw_sampling;
+
+typedef enum sw_tiling {
+  SW_ACCURATE = 0, /* TilingAlgorithmV1, TilingAlgorithms.cpp:577-626 */
+  SW_FAST = 1      /* TilingAlgorithmV3, TilingAlgorithms.cpp:1207-1784 */
+} sw_tiling;
+
+/* node flags */
+#define SW_NODE_TAKE_ALL 1u      /* all points of the visit were taken (count <= max_points_per_node) */
+#define SW_NODE_TERMINAL 2u      /* tile_terminal_node: level >= max_level, stored unsampled */
+#define SW_NODE_RECONSTRUCTED 4u /* FAST finalize: re-sampled copy of the children's points */
+
+typedef struct sw_params {
+  int32_t sampling;             /* sw_sampling */
+  int32_t tiling;               /* sw_tiling */
+  float spacing_at_root;        /* TilerMetaParameters::spacing_at_root (float!) */
+  uint32_t max_depth;           /* TilerMetaParameters::max_depth; CLI effectively uses 100 */
+  uint64_t max_points_per_node; /* default 20000 */
+  double bounds_min[3];         /* cubic dataset bounds (AABB::makeCubic, math/AABB.h:50-61) */
+  double bounds_max[3];
+  uint32_t concurrency;         /* FAST: num_indexing_threads of the reference run being matched */
+  uint32_t reserved;
+} sw_params;
+
+typedef struct sw_node {
+  uint64_t index;  /* octants packed 3 bits per level, deepest level in the low bits */
+  uint32_t levels; /* 0 = root "r"; node level in the reference's sense is levels-1 */
+  uint32_t flags;
+  uint64_t first;  /* offset of the node's first point in the node-major id array */
+  uint64_t count;
+} sw_node;
+
+/* error codes shared by swgpu_* and swo_* */
+#define SW_OK 0
+#define SW_ERR_INVALID_ARGUMENT 1
+#define SW_ERR_CUDA 2
+#define SW_ERR_OUT_OF_MEMORY 3
+#define SW_ERR_JITTER_GRID_TOO_SMALL 4 /* Sampling.h:632-635 "Grids smaller than 16x16 ..." */
+#define SW_ERR_JITTER_NODE_TOO_SMALL 5 /* Sampling.h:641-653 grid_level >= 21 */
+#define SW_ERR_DEEP_REROOT 6           /* TilingAlgorithms.cpp:444-483 path, not supported */
+#define SW_ERR_EMPTY_NODE 7            /* TilingAlgorithms.cpp:253-259 */
+#define SW_ERR_STATE 8
+#define SW_ERR_TOO_FEW_POINTS 9        /* Parallel.h:181-186: fewer points than indexing threads */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,399 @@
+/*
+ * oracle/ref_driver.cpp — TEST INFRASTRUCTURE ONLY.
+ *
+ * Drives the reference's OWN hot-path code, compiled verbatim from /root/reference (never copied
+ * into this repository), behind the same C API shape as tiler_oracle.cpp (prefix swr_ instead of
+ * swo_).  Built by oracle/Makefile into oracle/_ref/libswref.so, only where /root/reference
+ * exists; the built library travels to the GPU box, the sources do not.
+ *
+ * Reference functions called (all from /root/reference/schwarzwald/core):
+ *   index_point<21>                         tiling/OctreeAlgorithms.h:145-175
+ *   partition_points_into_child_octants     tiling/OctreeAlgorithms.h:240-265
+ *   get_octant_bounds                       tiling/OctreeAlgorithms.cpp:3-18
+ *   get_bounds_from_morton_index<21>        tiling/OctreeAlgorithms.h:104-116
+ *   sample_points(SamplingStrategy&, ...)   tiling/Sampling.h:799-821 (all four strategies)
+ *   required_morton_index_depth             tiling/Sampling.cpp:29-62
+ *   expand_bits_by_3 / contract_bits_by_3   util/stuff.h:207-234
+ * TilingAlgorithms.cpp needs taskflow/boost::hana/cista, which are not in this image, so the
+ * control flow around these calls is the restatement in orchestrator.h.
+ */
+#include "orchestrator.h"
+
+#include "datastructures/PointBuffer.h"
+#include "tiling/Node.h"
+#include "tiling/OctreeAlgorithms.h"
+#include "tiling/Sampling.h"
+#include "util/stuff.h"
+
+#include <cstring>
+#include <memory>
+
+namespace {
+
+AABB
+to_aabb(const swo::Box& b)
+{
+  return AABB{ { b.min[0], b.min[1], b.min[2] }, { b.max[0], b.max[1], b.max[2] } };
+}
+
+swo::Box
+from_aabb(const AABB& a)
+{
+  swo::Box b;
+  b.min[0] = a.min.x;
+  b.min[1] = a.min.y;
+  b.min[2] = a.min.z;
+  b.max[0] = a.max.x;
+  b.max[1] = a.max.y;
+  b.max[2] = a.max.z;
+  return b;
+}
+
+SamplingStrategy
+make_strategy(int32_t sampling, size_t max_points)
+{
+  switch (sampling) {
+    case SW_RANDOM_GRID:
+      return RandomSortedGridSampling{ max_points };
+    case SW_GRID_CENTER:
+      return GridCenterSampling{ max_points };
+    case SW_MIN_DISTANCE:
+      return PoissonDiskSampling{ max_points };
+    case SW_JITTERED:
+      return JitteredSampling{ max_points };
+  }
+  throw swo::OracleError(SW_ERR_INVALID_ARGUMENT, "unknown sampling strategy");
+}
+
+struct RefPrims
+{
+  using Item = IndexedPoint64;
+
+  PointBuffer buffer; /* owns a copy of the positions; PointReference indexes into it */
+  SamplingStrategy strategy;
+  std::vector<PointBuffer::PointReference> refs;
+
+  RefPrims(const double* xyz, uint64_t n, int32_t sampling, size_t max_points)
+    : strategy(make_strategy(sampling, max_points))
+  {
+    std::vector<Vector3<double>> positions(n);
+    for (uint64_t i = 0; i < n; ++i)
+      positions[i] = { xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2] };
+    buffer = PointBuffer(n, std::move(positions));
+    refs.reserve(n);
+    for (auto it = buffer.begin(); it != buffer.end(); ++it)
+      refs.push_back(*it);
+  }
+
+  uint64_t key(const Item& i) const { return i.morton_index.get(); }
+  uint32_t id(const Item& i) const
+  {
+    return static_cast<uint32_t>(&i.point_reference.position() - buffer.positions().data());
+  }
+
+  void index_all(std::vector<Item>& out, const swo::Box& bounds)
+  {
+    const AABB b = to_aabb(bounds);
+    out.clear();
+    out.reserve(refs.size());
+    for (auto& r : refs)
+      out.push_back(index_point<21>(r, b, OutlierPointsBehaviour::ClampToBounds));
+  }
+
+  void index_ids(const std::vector<uint32_t>& ids, std::vector<Item>& out, const swo::Box& bounds)
+  {
+    const AABB b = to_aabb(bounds);
+    out.clear();
+    out.reserve(ids.size());
+    for (uint32_t id : ids)
+      out.push_back(index_point<21>(refs[id], b, OutlierPointsBehaviour::ClampToBounds));
+  }
+
+  swo::Box octant_bounds(uint8_t octant, const swo::Box& parent) const
+  {
+    return from_aabb(get_octant_bounds(octant, to_aabb(parent)));
+  }
+
+  std::array<size_t, 9> partition(const Item* begin, const Item* end, uint32_t level) const
+  {
+    const auto parts = partition_points_into_child_octants(begin, end, level);
+    std::array<size_t, 9> cuts{};
+    cuts[0] = 0;
+    for (int o = 0; o < 8; ++o)
+      cuts[o + 1] = static_cast<size_t>(parts[o].end() - begin);
+    return cuts;
+  }
+
+  int32_t required_depth(int32_t node_level, const swo::NodeStructure& root) const
+  {
+    octree::NodeStructure r;
+    r.bounds = to_aabb(root.bounds);
+    r.level = root.level;
+    r.max_spacing = root.max_spacing;
+    r.max_depth = root.max_depth;
+    r.morton_index = {};
+    r.name = "r";
+    return required_morton_index_depth(strategy, node_level, r);
+  }
+
+  size_t sample(Item* begin,
+                Item* end,
+                uint64_t node_key,
+                int32_t node_level,
+                const swo::Box& root_bounds,
+                float spacing_at_root,
+                swo::Behaviour behaviour)
+  {
+    try {
+      Item* pp = sample_points(strategy,
+                               begin,
+                               end,
+                               MortonIndex64{ node_key },
+                               node_level,
+                               to_aabb(root_bounds),
+                               spacing_at_root,
+                               behaviour == swo::AlwaysAdhereToMinSpacing
+                                 ? SamplingBehaviour::AlwaysAdhereToMinSpacing
+                                 : SamplingBehaviour::TakeAllWhenCountBelowMaxPoints);
+      return static_cast<size_t>(pp - begin);
+    } catch (const std::runtime_error& e) {
+      const std::string what = e.what();
+      if (what.find("smaller than 16x16") != std::string::npos)
+        throw swo::OracleError(SW_ERR_JITTER_GRID_TOO_SMALL, what);
+      if (what.find("too small to be sampled") != std::string::npos)
+        throw swo::OracleError(SW_ERR_JITTER_NODE_TOO_SMALL, what);
+      throw;
+    }
+  }
+};
+
+struct Handle
+{
+  std::vector<sw_node> nodes;
+  std::vector<uint32_t> ids;
+  std::vector<uint64_t> keys;
+  std::vector<uint32_t> order;
+  uint64_t duplicate_keys = 0;
+  int32_t start_level = -1;
+  std::string error;
+};
+
+swo::Box
+make_box(const double* bmin, const double* bmax)
+{
+  swo::Box b;
+  for (int a = 0; a < 3; ++a) {
+    b.min[a] = bmin[a];
+    b.max[a] = bmax[a];
+  }
+  return b;
+}
+
+} // namespace
+
+extern "C" {
+
+uint64_t
+swr_expand_bits_by_3(uint64_t v)
+{
+  return expand_bits_by_3(v);
+}
+
+uint64_t
+swr_contract_bits_by_3(uint64_t v)
+{
+  return contract_bits_by_3(v);
+}
+
+void
+swr_index_points(double* xyz, uint64_t n, const double* bmin, const double* bmax, uint64_t* keys)
+{
+  RefPrims p(xyz, n, SW_RANDOM_GRID, 1);
+  std::vector<IndexedPoint64> items;
+  p.index_all(items, make_box(bmin, bmax));
+  for (uint64_t i = 0; i < n; ++i) {
+    keys[i] = items[i].morton_index.get();
+    const auto& pos = p.buffer.positions()[i]; /* index_point clamps in place */
+    xyz[3 * i] = pos.x;
+    xyz[3 * i + 1] = pos.y;
+    xyz[3 * i + 2] = pos.z;
+  }
+}
+
+void
+swr_octant_bounds(uint8_t octant, const double* bmin, const double* bmax, double* out6)
+{
+  const swo::Box r = from_aabb(get_octant_bounds(octant, to_aabb(make_box(bmin, bmax))));
+  std::memcpy(out6, r.min, 3 * sizeof(double));
+  std::memcpy(out6 + 3, r.max, 3 * sizeof(double));
+}
+
+void
+swr_bounds_from_morton_index(uint64_t key, uint32_t depth, const double* bmin, const double* bmax, double* out6)
+{
+  const swo::Box r =
+    from_aabb(get_bounds_from_morton_index(MortonIndex64{ key }, to_aabb(make_box(bmin, bmax)), depth));
+  std::memcpy(out6, r.min, 3 * sizeof(double));
+  std::memcpy(out6 + 3, r.max, 3 * sizeof(double));
+}
+
+int32_t
+swr_required_morton_index_depth(int32_t sampling,
+                                int32_t node_level,
+                                const double* bmin,
+                                const double* bmax,
+                                float root_max_spacing)
+{
+  double dummy[3] = { 0, 0, 0 };
+  RefPrims p(dummy, 1, sampling, 1);
+  swo::NodeStructure root{};
+  root.bounds = make_box(bmin, bmax);
+  root.max_spacing = root_max_spacing;
+  root.level = -1;
+  return p.required_depth(node_level, root);
+}
+
+void
+swr_partition_child_octants(const uint64_t* keys, uint64_t n, uint32_t level, uint64_t* cuts9)
+{
+  std::vector<IndexedPoint64> items(n);
+  for (uint64_t i = 0; i < n; ++i)
+    items[i].morton_index = MortonIndex64{ keys[i] };
+  const auto parts = partition_points_into_child_octants(items.data(), items.data() + n, level);
+  cuts9[0] = 0;
+  for (int o = 0; o < 8; ++o)
+    cuts9[o + 1] = static_cast<uint64_t>(parts[o].end() - items.data());
+}
+
+int64_t
+swr_sample_points(int32_t sampling,
+                  const double* xyz,
+                  const uint64_t* keys,
+                  const uint32_t* ids,
+                  uint64_t n,
+                  uint64_t node_key,
+                  int32_t node_level,
+                  const double* bmin,
+                  const double* bmax,
+                  float spacing_at_root,
+                  int32_t behaviour,
+                  uint64_t max_points_per_node,
+                  uint64_t* keys_out,
+                  uint32_t* ids_out)
+{
+  try {
+    uint32_t max_id = 0;
+    for (uint64_t i = 0; i < n; ++i)
+      max_id = std::max(max_id, ids[i]);
+    RefPrims p(xyz, n ? static_cast<uint64_t>(max_id) + 1 : 0, sampling, max_points_per_node);
+    std::vector<IndexedPoint64> items(n);
+    for (uint64_t i = 0; i < n; ++i) {
+      items[i].point_reference = p.refs[ids[i]];
+      items[i].morton_index = MortonIndex64{ keys[i] };
+    }
+    const size_t taken = p.sample(items.data(),
+                                  items.data() + n,
+                                  node_key,
+                                  node_level,
+                                  make_box(bmin, bmax),
+                                  spacing_at_root,
+                                  static_cast<swo::Behaviour>(behaviour));
+    for (uint64_t i = 0; i < n; ++i) {
+      keys_out[i] = items[i].morton_index.get();
+      ids_out[i] = p.id(items[i]);
+    }
+    return static_cast<int64_t>(taken);
+  } catch (const swo::OracleError& e) {
+    return -static_cast<int64_t>(e.code);
+  }
+}
+
+int
+swr_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
+{
+  auto* h = new Handle();
+  *out_handle = h;
+  try {
+    RefPrims prims(xyz, n, params->sampling, params->max_points_per_node);
+    swo::Orchestrator<RefPrims> o(prims, *params);
+    o.run();
+    h->nodes = std::move(o.nodes);
+    h->ids = std::move(o.ids);
+    h->keys = std::move(o.sorted_keys);
+    h->order = std::move(o.sorted_ids);
+    h->duplicate_keys = o.duplicate_keys;
+    h->start_level = o.start_level;
+    /* index_point clamps in place inside the PointBuffer: hand the clamped positions back */
+    for (uint64_t i = 0; i < n; ++i) {
+      const auto& pos = prims.buffer.positions()[i];
+      xyz[3 * i] = pos.x;
+      xyz[3 * i + 1] = pos.y;
+      xyz[3 * i + 2] = pos.z;
+    }
+    return SW_OK;
+  } catch (const swo::OracleError& e) {
+    h->error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    h->error = e.what();
+    return SW_ERR_STATE;
+  }
+}
+
+uint64_t
+swr_node_count(void* handle)
+{
+  return static_cast<Handle*>(handle)->nodes.size();
+}
+
+uint64_t
+swr_point_id_count(void* handle)
+{
+  return static_cast<Handle*>(handle)->ids.size();
+}
+
+int32_t
+swr_start_level(void* handle)
+{
+  return static_cast<Handle*>(handle)->start_level;
+}
+
+uint64_t
+swr_duplicate_keys(void* handle)
+{
+  return static_cast<Handle*>(handle)->duplicate_keys;
+}
+
+void
+swr_get_nodes(void* handle, sw_node* nodes, uint32_t* ids)
+{
+  auto* h = static_cast<Handle*>(handle);
+  if (nodes)
+    std::memcpy(nodes, h->nodes.data(), h->nodes.size() * sizeof(sw_node));
+  if (ids)
+    std::memcpy(ids, h->ids.data(), h->ids.size() * sizeof(uint32_t));
+}
+
+void
+swr_get_keys(void* handle, uint64_t* keys, uint32_t* order)
+{
+  auto* h = static_cast<Handle*>(handle);
+  if (keys)
+    std::memcpy(keys, h->keys.data(), h->keys.size() * sizeof(uint64_t));
+  if (order)
+    std::memcpy(order, h->order.data(), h->order.size() * sizeof(uint32_t));
+}
+
+const char*
+swr_last_error(void* handle)
+{
+  return static_cast<Handle*>(handle)->error.c_str();
+}
+
+void
+swr_destroy(void* handle)
+{
+  delete static_cast<Handle*>(handle);
+}
+
+} /* extern "C" */
