@@ -1,0 +1,116 @@
+/*
+ * swgpu.h — C ABI of libswgpu, the B200 (sm_100a) implementation of Schwarzwald's tiler compute
+ * core: Morton indexing, the node-grouping sort and per-node LOD sampling for ACCURATE and FAST
+ * tiling.  Plain pointers and sizes only; no CUDA, torch or C++ types cross this boundary.
+ *
+ * The reference has no FFI; its seam is the C++ interface TilingAlgorithmBase
+ * (schwarzwald/core/tiling/TilingAlgorithms.h:70-116).  Each entry point below names the
+ * reference construct it stands in for (paths relative to /root/reference/schwarzwald/core).
+ * A drop-in `TilingAlgorithmGPU : TilingAlgorithmBase` built on these calls is shown in
+ * INTEGRATION.md and shipped as schwarzwald_b200/host/TilingAlgorithmGPU.h.
+ *
+ * Conventions: every function returns SW_OK (0) or an SW_ERR_* code (include/sw_types.h); the
+ * message of the last failure is available from swgpu_last_error().  The caller owns all host
+ * buffers, the library owns all device memory.  A handle is used from one host thread at a time
+ * (the reference runs one indexing task per batch, process/Tiler.cpp:499-527).  There is no CPU
+ * fallback: without a CUDA device every compute call fails with SW_ERR_CUDA.
+ */
+#ifndef SWGPU_H
+#define SWGPU_H
+
+#include "sw_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct swgpu_tiler* swgpu_handle;
+
+/* TilingAlgorithmV1 / TilingAlgorithmV3 constructors (tiling/TilingAlgorithms.cpp:567-575,
+ * 1195-1205) + Tiler::Tiler's choice between them (process/Tiler.cpp:189-198).  `device` is the
+ * CUDA device ordinal. */
+int swgpu_create(const sw_params* params, int device, swgpu_handle* out);
+void swgpu_destroy(swgpu_handle h);
+const char* swgpu_last_error(swgpu_handle h);
+
+/* Work is enqueued on this CUDA stream (a cudaStream_t passed as void*; NULL = default stream). */
+int swgpu_set_stream(swgpu_handle h, void* cuda_stream);
+
+/* Pre-allocates device memory for batches of up to n points (optional; batches grow on demand). */
+int swgpu_reserve(swgpu_handle h, uint64_t n);
+
+/*
+ * build_execution_graph() for one batch (TilingAlgorithms.cpp:577-626 for ACCURATE, 1250-1360 for
+ * FAST's first iteration): index every point, sort, run the per-node sampling.
+ *   xyz  AoS n x 3 doubles = PointBuffer::positions() (datastructures/PointBuffer.h:291).
+ *        Points outside the bounds are clamped IN PLACE, as index_point does
+ *        (tiling/OctreeAlgorithms.h:156-170).
+ * swgpu_index_batch takes a HOST buffer (copied to the device, clamped values copied back);
+ * swgpu_index_batch_device takes a DEVICE pointer that stays owned by the caller and must stay
+ * valid until the results have been fetched.
+ */
+int swgpu_index_batch(swgpu_handle h, double* xyz_host, uint64_t n);
+int swgpu_index_batch_device(swgpu_handle h, double* xyz_device, uint64_t n);
+
+/* TilingAlgorithmBase::finalize(bounds): FAST re-samples the skipped upper levels from their
+ * children (reconstruct_left_out_nodes, TilingAlgorithms.cpp:1717-1784); no-op for ACCURATE. */
+int swgpu_finalize(swgpu_handle h);
+
+/* The hand-off that replaces the per-node persist_points() calls (io/PointsPersistence.h:23-31):
+ * a node table plus one node-major array of ORIGINAL point indices, Morton-ordered inside each
+ * node.  The adapter turns row i into persist_points(refs[first..first+count), bounds, name). */
+int swgpu_result_size(swgpu_handle h, uint64_t* n_nodes, uint64_t* n_point_ids);
+int swgpu_get_nodes(swgpu_handle h, sw_node* nodes, uint32_t* point_ids);
+/* Same hand-off without leaving the device: point ids are written to a caller-owned device buffer
+ * of n_point_ids u32 (node table still goes to the host). */
+int swgpu_get_nodes_device_ids(swgpu_handle h, sw_node* nodes, uint32_t* point_ids_device);
+
+/* FAST: _level_of_start_nodes (TilingAlgorithms.cpp:1294-1295); -1 for ACCURATE. */
+int swgpu_get_start_level(swgpu_handle h, int32_t* level);
+/* number of points index_point clamped in the last batch */
+int swgpu_get_clamped_count(swgpu_handle h, uint64_t* n);
+
+/* Test hooks: the sorted Morton keys and the sort permutation (original index of each sorted
+ * position) of the last batch.  Either pointer may be NULL. */
+int swgpu_get_keys(swgpu_handle h, uint64_t* keys, uint32_t* order);
+
+/* Optional attribute permutation (the gather persist_points performs through PointReference):
+ * gathers `n_records` records of `width` bytes (1,2,3,4,8,12 or 24) from a device array indexed
+ * by original point index into node-major order on the device.  src/dst are device pointers. */
+int swgpu_gather_attribute_device(swgpu_handle h, const void* src_device, uint32_t width, void* dst_device);
+
+/* Stand-alone primitives (used by the parity tests and the multi-GPU shuffle). */
+/* index_point<21> over a device batch: keys_device receives n u64; xyz is clamped in place. */
+int swgpu_morton_encode_device(swgpu_handle h, double* xyz_device, uint64_t n, uint64_t* keys_device);
+/* Stable sort of (key, original index) on the device; keys sorted in place, order_device gets n u32. */
+int swgpu_sort_keys_device(swgpu_handle h, uint64_t* keys_device, uint64_t n, uint32_t* order_device);
+
+/* Algorithmic bytes moved by the last index_batch + finalize according to the accounting model
+ * of DESIGN.md (used by bench.py for the roofline line), and the per-stage device times in ms
+ * when timing was enabled with swgpu_enable_timing (cudaEvents on the handle's stream). */
+typedef struct swgpu_stats {
+  uint64_t n_points;
+  uint64_t n_output_ids;
+  uint64_t n_nodes;
+  uint32_t n_levels;     /* sweep levels executed */
+  uint32_t n_reconstruct_levels;
+  uint64_t sweep_points; /* sum over levels of the list length entering the level */
+  uint64_t bytes_index;
+  uint64_t bytes_sort;
+  uint64_t bytes_gather;
+  uint64_t bytes_sample;
+  float ms_index;
+  float ms_sort;
+  float ms_gather;
+  float ms_sample;
+  float ms_total;
+  uint32_t kernel_launches;
+  uint32_t min_distance_rounds;
+} swgpu_stats;
+int swgpu_enable_timing(swgpu_handle h, int enable);
+int swgpu_get_stats(swgpu_handle h, swgpu_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,511 @@
+// kernels_index_sort.cu — K1 (Morton indexing), K2 (onesweep LSD radix sort), K4 (gathers).
+//
+// Reference behaviour replaced (paths relative to /root/reference/schwarzwald/core):
+//   K1  index_point<21> / calculate_morton_index<21>   tiling/OctreeAlgorithms.h:64-87,145-175
+//       (driven by parallel::transform / scatter, tiling/TilingAlgorithms.cpp:588-598,1262-1285)
+//   K2  std::sort over IndexedPoint64 by key           tiling/TilingAlgorithms.cpp:600-604,1289-1292
+//       tie rule: stable w.r.t. the original point index (SURVEY.md §8a "S")
+//   K4  the gather that persist_points performs through PointReference
+//       (tiling/TilingAlgorithms.cpp:232-236,330-334)
+//
+// HBM layout: positions stay AoS (x,y,z doubles, 24 B) exactly as PointBuffer holds them
+// (datastructures/PointBuffer.h:291); keys are one u64 per point; the sort payload is the u32
+// original index.  All kernels are bandwidth bound; no tensor-core work exists on this path.
+#include "swgpu_internal.cuh"
+
+// =============================================================================================
+// K1  Morton encode (+ digit histograms for the sort)
+// =============================================================================================
+#define MORTON_THREADS 256
+
+__device__ __forceinline__ u64
+morton_from_position(double x, double y, double z, const SwBounds& b)
+{
+  // (p - min) * scale: subtract then multiply, two roundings (no FMA), then truncate toward zero
+  // and cap at 2^21 - 1 (OctreeAlgorithms.h:71-79).
+  const double nx = (x - b.min[0]) * b.scale[0];
+  const double ny = (y - b.min[1]) * b.scale[1];
+  const double nz = (z - b.min[2]) * b.scale[2];
+  const u64 cap = (1u << 21) - 1;
+  u64 bx = __double2ull_rz(nx);
+  u64 by = __double2ull_rz(ny);
+  u64 bz = __double2ull_rz(nz);
+  bx = bx < cap ? bx : cap;
+  by = by < cap ? by : cap;
+  bz = bz < cap ? bz : cap;
+  return expand_bits_by_3(bz) | (expand_bits_by_3(by) << 1) | (expand_bits_by_3(bx) << 2);
+}
+
+// std::min(bmax, std::max(bmin, p)) with the exact comparison order of libstdc++
+__device__ __forceinline__ double
+clamp_like_reference(double p, double bmin, double bmax)
+{
+  const double mx = (bmin < p) ? p : bmin;
+  return (mx < bmax) ? mx : bmax;
+}
+
+__device__ __forceinline__ bool
+index_one(double& x, double& y, double& z, const SwBounds& b)
+{
+  // AABB::isInside is inclusive on both ends (math/AABB.h:27-31)
+  const bool inside = x >= b.min[0] && x <= b.max[0] && y >= b.min[1] && y <= b.max[1] && z >= b.min[2] &&
+                      z <= b.max[2];
+  if (!inside) {
+    x = clamp_like_reference(x, b.min[0], b.max[0]);
+    y = clamp_like_reference(y, b.min[1], b.max[1]);
+    z = clamp_like_reference(z, b.min[2], b.max[2]);
+  }
+  return !inside;
+}
+
+__device__ __forceinline__ void
+hist_add(u32* s_hist, u64 key)
+{
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+    atomicAdd(&s_hist[p * 256 + (u32)((key >> (8 * p)) & 255)], 1u);
+}
+
+// Each thread indexes two consecutive points: 48 bytes = three 16-byte loads.
+__global__ void __launch_bounds__(MORTON_THREADS)
+morton_encode_kernel(double* __restrict__ xyz, u64 n, SwBounds b, u64* __restrict__ keys, u32* __restrict__ hist,
+                     u32* __restrict__ n_clamped)
+{
+  __shared__ u32 s_hist[8 * 256];
+  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS)
+    s_hist[i] = 0;
+  __syncthreads();
+
+  const u64 n_pairs = n >> 1;
+  u32 clamped = 0;
+  for (u64 pair = (u64)blockIdx.x * MORTON_THREADS + threadIdx.x; pair < n_pairs;
+       pair += (u64)gridDim.x * MORTON_THREADS) {
+    double2* p2 = reinterpret_cast<double2*>(xyz) + 3 * pair;
+    double2 a = p2[0], c = p2[1], e = p2[2];
+    double x0 = a.x, y0 = a.y, z0 = c.x, x1 = c.y, y1 = e.x, z1 = e.y;
+    const bool c0 = index_one(x0, y0, z0, b);
+    const bool c1 = index_one(x1, y1, z1, b);
+    if (c0 | c1) { // write the clamped coordinates back (OctreeAlgorithms.h:167-169)
+      p2[0] = make_double2(x0, y0);
+      p2[1] = make_double2(z0, x1);
+      p2[2] = make_double2(y1, z1);
+      clamped += (u32)c0 + (u32)c1;
+    }
+    const u64 k0 = morton_from_position(x0, y0, z0, b);
+    const u64 k1 = morton_from_position(x1, y1, z1, b);
+    reinterpret_cast<ulonglong2*>(keys)[pair] = make_ulonglong2(k0, k1);
+    hist_add(s_hist, k0);
+    hist_add(s_hist, k1);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double* p = xyz + 3 * (n - 1);
+    double x = p[0], y = p[1], z = p[2];
+    if (index_one(x, y, z, b)) {
+      p[0] = x;
+      p[1] = y;
+      p[2] = z;
+      ++clamped;
+    }
+    const u64 k = morton_from_position(x, y, z, b);
+    keys[n - 1] = k;
+    hist_add(s_hist, k);
+  }
+  if (clamped)
+    atomicAdd(n_clamped, clamped);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS) {
+    const u32 v = s_hist[i];
+    if (v)
+      atomicAdd(&hist[i], v);
+  }
+}
+
+__global__ void __launch_bounds__(MORTON_THREADS)
+key_histogram_kernel(const u64* __restrict__ keys, u64 n, u32* __restrict__ hist)
+{
+  __shared__ u32 s_hist[8 * 256];
+  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS)
+    s_hist[i] = 0;
+  __syncthreads();
+  for (u64 i = (u64)blockIdx.x * MORTON_THREADS + threadIdx.x; i < n; i += (u64)gridDim.x * MORTON_THREADS)
+    hist_add(s_hist, keys[i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS) {
+    const u32 v = s_hist[i];
+    if (v)
+      atomicAdd(&hist[i], v);
+  }
+}
+
+static int
+persistent_grid(u64 work_items, int threads, int ctas_per_sm)
+{
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  u64 want = (work_items + threads - 1) / threads;
+  u64 cap = (u64)sms * ctas_per_sm;
+  if (want < 1)
+    want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+void
+launch_morton_encode(double* xyz, u64 n, const SwBounds& b, u64* keys, u32* hist, u32* n_clamped, cudaStream_t stream)
+{
+  if (n == 0)
+    return;
+  const int grid = persistent_grid((n + 1) / 2, MORTON_THREADS, 8);
+  morton_encode_kernel<<<grid, MORTON_THREADS, 0, stream>>>(xyz, n, b, keys, hist, n_clamped);
+}
+
+void
+launch_key_histogram(const u64* keys, u64 n, u32* hist, cudaStream_t stream)
+{
+  if (n == 0)
+    return;
+  const int grid = persistent_grid(n, MORTON_THREADS, 8);
+  key_histogram_kernel<<<grid, MORTON_THREADS, 0, stream>>>(keys, n, hist);
+}
+
+// =============================================================================================
+// K2  onesweep LSD radix sort, 8-bit digits, u64 keys + u32 payload
+// =============================================================================================
+#define RS_THREADS 256
+#define RS_WARPS (RS_THREADS / 32)
+#define RS_ITEMS 16
+#define RS_TILE (RS_THREADS * RS_ITEMS) // 4096 pairs per tile
+#define RS_RADIX 256
+
+#define RS_FLAG_AGG (1u << 30)
+#define RS_FLAG_PFX (2u << 30)
+#define RS_VAL_MASK ((1u << 30) - 1)
+
+// exclusive scan of the 8 x 256 histogram rows, in place (one block, one row per warp)
+__global__ void
+digit_base_kernel(u32* __restrict__ hist)
+{
+  const int row = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  u32* h = hist + row * 256;
+  u32 v[8];
+  u32 sum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = h[lane * 8 + i];
+    sum += v[i];
+  }
+  u32 incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o)
+      incl += t;
+  }
+  u32 run = incl - sum;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[lane * 8 + i] = run;
+    run += v[i];
+  }
+}
+
+template<bool FIRST>
+__global__ void __launch_bounds__(RS_THREADS)
+onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
+                     u32* __restrict__ vals_out, u32 n, int shift, const u32* __restrict__ digit_base,
+                     u32* __restrict__ status, u32* __restrict__ ticket)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  u64* s_keys = reinterpret_cast<u64*>(smem);                           // RS_TILE * 8
+  u32* s_vals = reinterpret_cast<u32*>(smem + RS_TILE * 8);             // RS_TILE * 4
+  u32* s_whist = reinterpret_cast<u32*>(smem + RS_TILE * 12);           // RS_WARPS * 256
+  u32* s_excl = s_whist + RS_WARPS * RS_RADIX;                          // 256 tile-local exclusive offsets
+  u32* s_gofs = s_excl + RS_RADIX;                                      // 256 global base - local offset
+  u32* s_wsum = s_gofs + RS_RADIX;                                      // RS_WARPS
+  __shared__ u32 s_tile;
+
+  const u32 tid = threadIdx.x;
+  const u32 warp = tid >> 5;
+  const u32 lane = tid & 31;
+
+  if (tid == 0)
+    s_tile = atomicAdd(ticket, 1u);
+  for (u32 i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS)
+    s_whist[i] = 0;
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u32 tile_base = tile * RS_TILE;
+  const u32 valid = (n - tile_base) < RS_TILE ? (n - tile_base) : RS_TILE;
+
+  // ---- load (warp-striped: item j of a warp is 32 consecutive pairs) -------------------------
+  u64 key[RS_ITEMS];
+  u32 val[RS_ITEMS];
+  const u32 warp_base = warp * (32 * RS_ITEMS) + lane;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const u32 p = warp_base + j * 32;
+    key[j] = (p < valid) ? keys_in[tile_base + p] : ~0ull;
+  }
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const u32 p = warp_base + j * 32;
+    if (FIRST)
+      val[j] = tile_base + p;
+    else
+      val[j] = (p < valid) ? vals_in[tile_base + p] : 0u;
+  }
+
+  // ---- rank inside the warp: match.any on the digit keeps the order stable --------------------
+  u32 rank[RS_ITEMS];
+  u32* my_hist = s_whist + warp * RS_RADIX;
+  const u32 lt = lanemask_lt();
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const u32 d = (u32)(key[j] >> shift) & 255u;
+    const u32 peers = __match_any_sync(0xffffffffu, d);
+    const u32 lower = __popc(peers & lt);
+    const u32 base = my_hist[d];
+    __syncwarp();
+    if (lower == 0)
+      my_hist[d] = base + __popc(peers);
+    __syncwarp();
+    rank[j] = base + lower;
+  }
+  __syncthreads();
+
+  // ---- per digit: offsets of each warp inside the tile, tile count, look-back -----------------
+  {
+    const u32 d = tid; // RS_THREADS == RS_RADIX
+    u32 run = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const u32 c = s_whist[w * RS_RADIX + d];
+      s_whist[w * RS_RADIX + d] = run;
+      run += c;
+    }
+    u32 prev = 0;
+    u32* my_status = status + (size_t)tile * RS_RADIX + d;
+    if (tile == 0) {
+      st_relaxed_u32(my_status, RS_FLAG_PFX | run);
+    } else {
+      st_relaxed_u32(my_status, RS_FLAG_AGG | run);
+      const u32* look = my_status - RS_RADIX;
+      while (true) {
+        u32 s;
+        do {
+          s = ld_relaxed_u32(look);
+        } while ((s >> 30) == 0);
+        prev += s & RS_VAL_MASK;
+        if ((s >> 30) == 2)
+          break;
+        look -= RS_RADIX;
+      }
+      st_relaxed_u32(my_status, RS_FLAG_PFX | ((prev + run) & RS_VAL_MASK));
+    }
+    // exclusive scan of the tile counts over the 256 digits
+    u32 incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o)
+        incl += t;
+    }
+    if (lane == 31)
+      s_wsum[warp] = incl;
+    __syncthreads();
+    u32 wofs = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w)
+      wofs += (w < (int)warp) ? s_wsum[w] : 0u;
+    const u32 excl = wofs + incl - run;
+    s_excl[d] = excl;
+    s_gofs[d] = digit_base[d] + prev - excl;
+  }
+  __syncthreads();
+
+  // ---- exchange through shared memory so that global writes are runs of consecutive addresses --
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const u32 d = (u32)(key[j] >> shift) & 255u;
+    rank[j] += s_excl[d] + my_hist[d];
+    s_keys[rank[j]] = key[j];
+    s_vals[rank[j]] = val[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const u32 p = tid + k * RS_THREADS;
+    if (p < valid) {
+      const u64 kk = s_keys[p];
+      const u32 d = (u32)(kk >> shift) & 255u;
+      const u32 dst = s_gofs[d] + p;
+      keys_out[dst] = kk;
+      vals_out[dst] = s_vals[p];
+    }
+  }
+}
+
+#define RS_SMEM_BYTES (RS_TILE * 12 + (RS_WARPS * RS_RADIX + 2 * RS_RADIX + RS_WARPS) * 4)
+
+size_t
+sort_status_words(u64 n)
+{
+  const size_t tiles = (size_t)((n + RS_TILE - 1) / RS_TILE);
+  return (tiles ? tiles : 1) * RS_RADIX;
+}
+
+void
+launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hist, u32* status, u32* ticket,
+                  cudaStream_t stream)
+{
+  if (n == 0)
+    return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(onesweep_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES);
+    cudaFuncSetAttribute(onesweep_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES);
+    attr_set = true;
+  }
+  const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
+  digit_base_kernel<<<1, 256, 0, stream>>>(hist);
+  cudaMemsetAsync(ticket, 0, 8 * sizeof(u32), stream);
+  u64* kin = keys0;
+  u64* kout = keys1;
+  u32* vin = vals0;
+  u32* vout = vals1;
+  for (int pass = 0; pass < 8; ++pass) {
+    cudaMemsetAsync(status, 0, (size_t)tiles * RS_RADIX * sizeof(u32), stream);
+    if (pass == 0)
+      onesweep_pass_kernel<true><<<tiles, RS_THREADS, RS_SMEM_BYTES, stream>>>(
+        kin, vin, kout, vout, (u32)n, 8 * pass, hist + pass * 256, status, ticket + pass);
+    else
+      onesweep_pass_kernel<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, stream>>>(
+        kin, vin, kout, vout, (u32)n, 8 * pass, hist + pass * 256, status, ticket + pass);
+    u64* tk = kin;
+    kin = kout;
+    kout = tk;
+    u32* tv = vin;
+    vin = vout;
+    vout = tv;
+  }
+}
+
+// =============================================================================================
+// K4  gathers
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+gather_positions_kernel(const double* __restrict__ src, const u32* __restrict__ perm, u64 n, double* __restrict__ dst)
+{
+  for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) {
+    const u64 s = perm[i];
+    const double x = src[3 * s], y = src[3 * s + 1], z = src[3 * s + 2];
+    dst[3 * i] = x;
+    dst[3 * i + 1] = y;
+    dst[3 * i + 2] = z;
+  }
+}
+
+template<int W>
+__global__ void __launch_bounds__(256)
+gather_bytes_kernel(const unsigned char* __restrict__ src, const u32* __restrict__ perm, u64 n,
+                    unsigned char* __restrict__ dst)
+{
+  for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) {
+    const u64 s = perm[i];
+#pragma unroll
+    for (int k = 0; k < W; ++k)
+      dst[i * W + k] = src[s * W + k];
+  }
+}
+
+template<typename T>
+__global__ void __launch_bounds__(256)
+gather_words_kernel(const T* __restrict__ src, const u32* __restrict__ perm, u64 n, T* __restrict__ dst)
+{
+  for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256)
+    dst[i] = src[perm[i]];
+}
+
+void
+launch_gather_positions(const double* src, const u32* perm, u64 n, double* dst, cudaStream_t stream)
+{
+  if (n == 0)
+    return;
+  gather_positions_kernel<<<persistent_grid(n, 256, 8), 256, 0, stream>>>(src, perm, n, dst);
+}
+
+void
+launch_gather_bytes(const void* src, const u32* perm, u64 n, u32 width, void* dst, cudaStream_t stream)
+{
+  if (n == 0)
+    return;
+  const int grid = persistent_grid(n, 256, 8);
+  const unsigned char* s = static_cast<const unsigned char*>(src);
+  unsigned char* d = static_cast<unsigned char*>(dst);
+  switch (width) {
+    case 1:
+      gather_words_kernel<unsigned char><<<grid, 256, 0, stream>>>(s, perm, n, d);
+      break;
+    case 2:
+      gather_words_kernel<unsigned short>
+        <<<grid, 256, 0, stream>>>((const unsigned short*)src, perm, n, (unsigned short*)dst);
+      break;
+    case 3:
+      gather_bytes_kernel<3><<<grid, 256, 0, stream>>>(s, perm, n, d);
+      break;
+    case 4:
+      gather_words_kernel<u32><<<grid, 256, 0, stream>>>((const u32*)src, perm, n, (u32*)dst);
+      break;
+    case 8:
+      gather_words_kernel<u64><<<grid, 256, 0, stream>>>((const u64*)src, perm, n, (u64*)dst);
+      break;
+    case 12:
+      gather_bytes_kernel<12><<<grid, 256, 0, stream>>>(s, perm, n, d);
+      break;
+    default:
+      break;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+compose_ids_kernel(const u32* __restrict__ perm, const u32* __restrict__ idx, u64 n, u32* __restrict__ out)
+{
+  for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256)
+    out[i] = perm[idx[i]];
+}
+
+void
+launch_compose_ids(const u32* perm, const u32* idx, u64 n, u32* out, cudaStream_t stream)
+{
+  if (n == 0)
+    return;
+  compose_ids_kernel<<<persistent_grid(n, 256, 8), 256, 0, stream>>>(perm, idx, n, out);
+}
+
+// =============================================================================================
+// FAST start-level support: boundaries of the 8^6 level-5 prefixes in the sorted keys
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+level5_bins_kernel(const u64* __restrict__ keys, u64 n, u32* __restrict__ bin_start)
+{
+  const u32 b = blockIdx.x * 256 + threadIdx.x;
+  if (b > 262144u)
+    return;
+  const u64 target = (u64)b << 45; // 6 levels = 18 bits, 63 - 18 = 45
+  u64 lo = 0, hi = n;
+  while (lo < hi) {
+    const u64 mid = (lo + hi) >> 1;
+    if ((keys[mid] & SW_KEY_MASK) < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  bin_start[b] = (u32)lo;
+}
+
+void
+launch_level5_bins(const u64* sorted_keys, u64 n, u32* bin_start, cudaStream_t stream)
+{
+  level5_bins_kernel<<<(262145 + 255) / 256, 256, 0, stream>>>(sorted_keys, n, bin_start);
+}

@@ -1,0 +1,148 @@
+// swgpu_internal.cuh — host-callable launchers implemented in the kernel translation units.
+// All launchers enqueue on `stream` and never synchronise; errors are reported through
+// cudaGetLastError() by the caller.
+#pragma once
+
+#include "common.cuh"
+
+#include "../../include/sw_types.h"
+
+// ---- index + sort (kernels_index_sort.cu) ---------------------------------------------------
+// K1: index_point<21> (clamp + Morton encode) fused with the 8 digit histograms of the sort.
+//   xyz        AoS n x 3 doubles (clamped in place when a point lies outside the bounds)
+//   keys       n x u64
+//   hist       8 x 256 u32, zeroed by the caller
+//   n_clamped  device counter of points that were clamped (zeroed by the caller)
+void launch_morton_encode(double* xyz, u64 n, const SwBounds& b, u64* keys, u32* hist, u32* n_clamped,
+                          cudaStream_t stream);
+
+// histogram only (keys already exist: tests, multi-GPU path after the shuffle)
+void launch_key_histogram(const u64* keys, u64 n, u32* hist, cudaStream_t stream);
+
+// Stable LSD radix sort of (key, id) pairs, 8 passes of 8 bits (onesweep: one read + one write per
+// pass, decoupled look-back between tiles).  `hist` are the 8 x 256 digit counts of the keys.
+// Sorted result ends in keys[0] / vals[0] (8 passes = even number of ping-pongs).  vals[0] need
+// not be initialised: the first pass generates ids 0..n-1 on the fly.
+// `status` must hold sort_status_words(n) u32; `ticket` 8 u32.
+size_t sort_status_words(u64 n);
+void launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hist, u32* status, u32* ticket,
+                       cudaStream_t stream);
+
+// positions gathered into Morton order: dst[i] = src[perm[i]] (24-byte records)
+void launch_gather_positions(const double* src, const u32* perm, u64 n, double* dst, cudaStream_t stream);
+// generic attribute gather for records of `width` bytes (1, 2, 3, 4, 8, 12)
+void launch_gather_bytes(const void* src, const u32* perm, u64 n, u32 width, void* dst, cudaStream_t stream);
+// out[i] = perm[idx[i]]
+void launch_compose_ids(const u32* perm, const u32* idx, u64 n, u32* out, cudaStream_t stream);
+
+// FAST start-level estimate support: bin_start[b] = lower_bound(sorted keys, b << 45) for the
+// 8^6 level-5 prefixes (+1 sentinel = n).  TilingAlgorithms.cpp:1473-1535 only needs the sizes of
+// the non-empty ranges at levels 0..5, which are sums of these bins.
+void launch_level5_bins(const u64* sorted_keys, u64 n, u32* bin_start /* 262145 */, cudaStream_t stream);
+
+// ---- sampling sweep (kernels_sampling.cu) -----------------------------------------------------
+#define SW_SWEEP_TILE 2048 /* elements per tile of the rle / select / compact kernels */
+
+struct SwLevelArgs
+{
+  // input list (Morton ordered)
+  const u64* in_key; // bit 63 clear
+  const u32* in_idx; // index into the sorted order; nullptr = identity
+  u64 count;
+  // node definition: nodes are runs of equal (key >> node_shift)
+  int node_shift;
+  // sampling cell definition for the grid strategies: runs of equal (key >> cell_shift)
+  int cell_shift;
+  // behaviour
+  int sampling;          // sw_sampling
+  int force_all;         // terminal level: every point is taken
+  int allow_take_all;    // TakeAllWhenCountBelowMaxPoints (1) or AlwaysAdhereToMinSpacing (0)
+  u64 max_points_per_node;
+  // node table produced by the run-length encoder
+  const u32* node_start; // n_nodes + 1 entries (sentinel = count)
+  const u32* tile_rank0; // per tile: number of node heads before the tile
+  // optional per-element selection flags (argmin / min-distance strategies)
+  const unsigned char* sel;
+  // outputs
+  u64* out_key;
+  u32* out_idx;
+  u64 out_offset; // where this level's chunk starts in out_key / out_idx
+  u64* rem_key;   // nullptr = remainder is dropped (reconstruct)
+  u32* rem_idx;
+  // node table output (indexed by node rank + node_base)
+  u64* node_index;
+  u64* node_first;
+  u64 node_base;
+  int levels; // number of levels of the nodes at this level (node level + 1)
+};
+
+size_t sweep_tiles(u64 count);
+// run-length encode nodes: node_start[], tile_rank0[], *n_nodes.  `status` >= sweep_tiles u64.
+void launch_node_rle(const u64* keys, u64 count, int node_shift, u32* node_start, u32* tile_rank0, u32* n_nodes,
+                     u64* status, u32* ticket, cudaStream_t stream);
+// stable two-way compaction of one level; *n_selected receives the number of selected points
+void launch_level_compact(const SwLevelArgs& a, u64* n_selected, u64* status, u32* ticket, cudaStream_t stream);
+
+struct SwArgminArgs
+{
+  const u64* in_key;
+  const u32* in_idx; // nullptr = identity
+  u64 count;
+  const double* pos_sorted; // AoS positions in Morton order
+  int sampling;             // SW_GRID_CENTER or SW_JITTERED
+  int node_shift;
+  int node_level; // reference node level (root = -1)
+  int cell_shift; // GRID_CENTER: shift of the candidate level; JITTERED: computed per node
+  int cand_level; // GRID_CENTER candidate level c (cell bounds at depth c + 1)
+  double spacing_at_node;
+  SwBounds bounds;
+  unsigned char* sel; // zeroed by the caller; 1 = winner of its cell
+  u32* error_flag;    // JITTERED: set to SW_ERR_JITTER_* by the kernel
+  // take-all nodes are skipped (they are never sampled: Sampling.h:328-335, 612-619)
+  const u32* node_start;
+  const u32* tile_rank0;
+  int allow_take_all;
+  u64 max_points_per_node;
+};
+// status >= 5 * sweep_tiles(count) u64
+void launch_select_argmin(const SwArgminArgs& a, u64* status, u32* ticket, cudaStream_t stream);
+
+struct SwMinDistArgs
+{
+  const u64* in_key;
+  const u32* in_idx;
+  u64 count;
+  const double* pos_sorted;
+  int node_shift;
+  int node_level;
+  int cell_level;   // Morton level of the neighbour-search cells (side >= spacing)
+  int cell_shift;
+  double threshold; // (double)(float)(spacing_f * spacing_f), SparseGrid.cpp:11-14
+  SwBounds bounds;
+  unsigned char* sel; // out: 1 = accepted
+  const u32* node_start;
+  const u32* tile_rank0;
+  int allow_take_all;
+  u64 max_points_per_node;
+};
+struct SwMinDistScratch
+{
+  u32* cell_start; // count + 1
+  u32* tile_rank0; // sweep_tiles
+  u32* n_cells;    // device scalar
+  u32* cursor;     // count
+  unsigned char* state; // count
+  u32* changed;    // device scalar
+  u64* status;
+  u32* ticket;
+  // host mirror of the device scalar block (pinned) for the per-round convergence test
+  void* d_scalars;
+  void* h_scalars;
+  size_t scalars_bytes;
+  u32* h_changed;
+  // growable neighbour / hash scratch owned by the caller
+  void** nbr_buf;
+  size_t* nbr_cap;
+};
+cudaError_t run_min_distance(const SwMinDistArgs& a, const SwMinDistScratch& sc, cudaStream_t stream, u32* rounds,
+                             u32* launches, u64* bytes);

@@ -1,0 +1,971 @@
+// tiler.cu — host-side orchestration of the device pipeline and the C ABI of include/swgpu.h.
+//
+// One batch (the parity regime of SURVEY.md: internal_cache_size >= N):
+//   index (K1) -> sort (K2) -> [gather positions (K4)] -> level-synchronous sampling sweep
+//   ACCURATE (TilingAlgorithmV1, tiling/TilingAlgorithms.cpp:577-626): sweep starts at the root
+//            (node level -1, one node holding every point)
+//   FAST     (TilingAlgorithmV3, :1250-1360): start level S from the sizes of the sorted key
+//            ranges (:1473-1535), sweep starts at node level S-1 (nodes with S levels);
+//            swgpu_finalize() re-samples levels S-1..0 from their children (:1661-1784)
+//
+// Per-level decisions that the reference takes per node but that only depend on the node LEVEL are
+// tabulated on the host with the reference's exact float/double narrowing
+// (tiling/Node.cpp:37-57, tiling/Sampling.cpp:29-62, tiling/Sampling.h:210-229).
+#include "swgpu_internal.cuh"
+
+#include "../../include/swgpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+
+  // Grows the buffer to at least `bytes`; optionally preserves `keep_bytes` of content.
+  cudaError_t ensure(size_t bytes, cudaStream_t stream = nullptr, size_t keep_bytes = 0)
+  {
+    if (bytes <= cap)
+      return cudaSuccess;
+    size_t want = bytes;
+    if (keep_bytes) // amortise growth of append-only buffers
+      want = std::max(bytes, cap + cap / 2);
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess)
+      return e;
+    if (p && keep_bytes) {
+      e = cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, stream);
+      if (e != cudaSuccess)
+        return e;
+      cudaStreamSynchronize(stream);
+    }
+    if (p)
+      cudaFree(p);
+    p = np;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template<typename T>
+  T* as() const
+  {
+    return static_cast<T*>(p);
+  }
+};
+
+struct Chunk
+{
+  int levels;     // number of levels of the nodes in this chunk (node level + 1)
+  u64 out_offset; // first id of the chunk in the output arrays
+  u64 count;      // ids in the chunk
+  u64 node_base;  // first row in the node table
+  u32 n_nodes;
+  u32 flags;
+};
+
+struct HostScalars
+{
+  u32 n_nodes;
+  u32 n_clamped;
+  u32 error_flag;
+  u32 changed;
+  u64 n_selected;
+};
+
+enum LevelKind
+{
+  KIND_INTERNAL = 0,
+  KIND_TERMINAL = 1,
+  KIND_REROOT = 2
+};
+
+} // namespace
+
+struct swgpu_tiler
+{
+  sw_params prm{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  SwBounds bounds{};
+
+  // current batch
+  double* d_xyz = nullptr; // owned (xyz_own) or borrowed
+  u64 n = 0;
+  bool batch_done = false;
+  bool finalized = false;
+  int32_t start_level = -1;
+  u64 n_clamped = 0;
+
+  DevBuf xyz_own;
+  DevBuf keys[2], vals[2];
+  DevBuf wkey2, widx2;
+  DevBuf hist, sort_status, scalars;
+  DevBuf pos_sorted;
+  DevBuf out_key, out_idx;
+  u64 out_count = 0;
+  DevBuf node_start, tile_rank0, sel, scan_status;
+  DevBuf node_index, node_first;
+  u64 node_count = 0;
+  DevBuf bins;
+  DevBuf ids_tmp;
+  // min-distance scratch
+  DevBuf md_cell_start, md_tile_rank0, md_nbr, md_cursor, md_state;
+
+  HostScalars* h_scalars = nullptr; // pinned
+  std::vector<Chunk> chunks;
+
+  // stats
+  swgpu_stats stats{};
+  bool timing = false;
+  cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+
+  // device scalar slots inside `scalars`
+  u32* d_n_nodes() { return scalars.as<u32>() + 0; }
+  u32* d_n_clamped() { return scalars.as<u32>() + 1; }
+  u32* d_error() { return scalars.as<u32>() + 2; }
+  u32* d_changed() { return scalars.as<u32>() + 3; }
+  u64* d_n_selected() { return reinterpret_cast<u64*>(scalars.as<u32>() + 4); }
+  u32* d_tickets() { return scalars.as<u32>() + 8; } // 16 u32
+  u32* d_md_ncells() { return scalars.as<u32>() + 24; }
+};
+
+namespace {
+
+#define CK(expr)                                                                                                       \
+  do {                                                                                                                 \
+    cudaError_t _e = (expr);                                                                                           \
+    if (_e != cudaSuccess)                                                                                             \
+      return fail_cuda(h, _e, #expr);                                                                                  \
+  } while (0)
+
+int
+fail(swgpu_tiler* h, int code, const std::string& msg)
+{
+  h->err = msg;
+  return code;
+}
+
+int
+fail_cuda(swgpu_tiler* h, cudaError_t e, const char* what)
+{
+  h->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  cudaGetLastError();
+  return e == cudaErrorMemoryAllocation ? SW_ERR_OUT_OF_MEMORY : SW_ERR_CUDA;
+}
+
+bool
+needs_positions(int sampling)
+{
+  return sampling != SW_RANDOM_GRID;
+}
+
+double
+root_extent_x(const swgpu_tiler* h)
+{
+  return h->prm.bounds_max[0] - h->prm.bounds_min[0];
+}
+
+// candidate level used inside sample_points: Sampling.h:210-229 (double spacing)
+int
+cand_level_sampler(const swgpu_tiler* h, int node_level)
+{
+  const double spacing_at_this_node = h->prm.spacing_at_root / std::pow(2, node_level + 1);
+  const float ratio = static_cast<float>(root_extent_x(h) / spacing_at_this_node);
+  return std::max(-1, static_cast<int>(std::floor(std::log2f(ratio))) - 1);
+}
+
+uint32_t
+prev_pow2_u32(uint32_t x)
+{
+  x |= x >> 1;
+  x |= x >> 2;
+  x |= x >> 4;
+  x |= x >> 8;
+  x |= x >> 16;
+  return x - (x >> 1);
+}
+
+// required_morton_index_depth with the real root (Sampling.cpp:29-62, Node.cpp:37-57)
+int
+required_depth(const swgpu_tiler* h, int node_level)
+{
+  switch (h->prm.sampling) {
+    case SW_RANDOM_GRID:
+    case SW_GRID_CENTER: {
+      const double spacing_at_target = h->prm.spacing_at_root / std::pow(2, node_level + 1);
+      const float target_spacing = static_cast<float>(spacing_at_target); // narrowed PARAMETER
+      const float ratio = static_cast<float>(root_extent_x(h) / target_spacing);
+      return std::max(-1, static_cast<int>(std::floor(std::log2f(ratio))) - 1);
+    }
+    case SW_MIN_DISTANCE:
+      return node_level;
+    case SW_JITTERED: {
+      const double spacing_at_this_node = h->prm.spacing_at_root / std::pow(2, node_level + 1);
+      const double perfect = (root_extent_x(h) / std::pow(2, node_level + 1)) / spacing_at_this_node;
+      const uint32_t cells = prev_pow2_u32(static_cast<uint32_t>(perfect));
+      const uint32_t levels = cells ? static_cast<uint32_t>(std::log2(cells)) : 0u;
+      return static_cast<int32_t>(static_cast<uint32_t>(node_level + levels));
+    }
+  }
+  return node_level;
+}
+
+// tile_node branching, TilingAlgorithms.cpp:406-491
+LevelKind
+level_kind(const swgpu_tiler* h, int node_level)
+{
+  const int sample_level = required_depth(h, node_level);
+  const bool requires_deeper = sample_level > node_level;
+  const int max_level = static_cast<int>(std::min<uint32_t>(20u, h->prm.max_depth));
+  if (!requires_deeper)
+    return sample_level >= max_level ? KIND_TERMINAL : KIND_INTERNAL;
+  if (node_level >= max_level)
+    return KIND_TERMINAL;
+  if (sample_level >= 21)
+    return KIND_REROOT;
+  return KIND_INTERNAL;
+}
+
+int
+sync_scalars(swgpu_tiler* h)
+{
+  CK(cudaMemcpyAsync(h->h_scalars, h->scalars.p, sizeof(HostScalars), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SW_OK;
+}
+
+int
+ensure_batch_buffers(swgpu_tiler* h, u64 n)
+{
+  const size_t nn = (size_t)std::max<u64>(n, 1);
+  for (int i = 0; i < 2; ++i) {
+    CK(h->keys[i].ensure(nn * 8));
+    CK(h->vals[i].ensure(nn * 4));
+  }
+  CK(h->wkey2.ensure(nn * 8));
+  CK(h->widx2.ensure(nn * 4));
+  CK(h->hist.ensure(8 * 256 * 4));
+  CK(h->sort_status.ensure(sort_status_words(n) * 4));
+  CK(h->node_start.ensure((nn + 1) * 4));
+  CK(h->tile_rank0.ensure(sweep_tiles(n) * 4));
+  CK(h->scan_status.ensure(sweep_tiles(n) * 8 * 5));
+  CK(h->bins.ensure(262145 * 4));
+  if (needs_positions(h->prm.sampling)) {
+    CK(h->pos_sorted.ensure(nn * 24));
+    CK(h->sel.ensure(nn));
+  }
+  CK(h->out_key.ensure(nn * 8));
+  CK(h->out_idx.ensure(nn * 4));
+  return SW_OK;
+}
+
+void
+record(swgpu_tiler* h, int i)
+{
+  if (h->timing)
+    cudaEventRecord(h->ev[i], h->stream);
+}
+
+// One sampling level over the list [in_key, in_idx) of `count` points whose nodes have `levels`
+// levels (reference node level = levels - 1).  Appends the selected points to the output arrays
+// and, if rem_key != nullptr, writes the remainder list.
+int
+sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int levels, bool allow_take_all,
+            bool force_all, u64* rem_key, u32* rem_idx, u32 chunk_flags, u64* n_selected_out, bool input_in_out_buffers,
+            u64 input_out_offset)
+{
+  const int node_level = levels - 1;
+  const int node_shift = shift_for_levels(levels);
+  cudaStream_t s = h->stream;
+
+  // grow the append-only outputs before taking pointers into them
+  CK(h->out_key.ensure((h->out_count + count) * 8, s, h->out_count * 8));
+  CK(h->out_idx.ensure((h->out_count + count) * 4, s, h->out_count * 4));
+  if (input_in_out_buffers) {
+    in_key = h->out_key.as<u64>() + input_out_offset;
+    in_idx = h->out_idx.as<u32>() + input_out_offset;
+  }
+
+  launch_node_rle(in_key, count, node_shift, h->node_start.as<u32>(), h->tile_rank0.as<u32>(), h->d_n_nodes(),
+                  h->scan_status.as<u64>(), h->d_tickets(), s);
+  h->stats.kernel_launches += 1;
+  h->stats.bytes_sample += 8 * count;
+  int rc = sync_scalars(h);
+  if (rc)
+    return rc;
+  const u32 n_nodes = h->h_scalars->n_nodes;
+  CK(h->node_index.ensure((h->node_count + n_nodes) * 8, s, h->node_count * 8));
+  CK(h->node_first.ensure((h->node_count + n_nodes + 1) * 8, s, h->node_count * 8));
+
+  SwLevelArgs a{};
+  a.in_key = in_key;
+  a.in_idx = in_idx;
+  a.count = count;
+  a.node_shift = node_shift;
+  a.cell_shift = 63;
+  a.sampling = h->prm.sampling;
+  a.force_all = force_all ? 1 : 0;
+  a.allow_take_all = allow_take_all ? 1 : 0;
+  a.max_points_per_node = h->prm.max_points_per_node;
+  a.node_start = h->node_start.as<u32>();
+  a.tile_rank0 = h->tile_rank0.as<u32>();
+  a.sel = nullptr;
+
+  if (!force_all) {
+    const int cand = cand_level_sampler(h, node_level);
+    int sampling = h->prm.sampling;
+    // GridCenterSampling takes the first point when the candidate level is the root
+    // (`return ++partition_point`, Sampling.h:346-348): same selection as RANDOM_GRID at level -1
+    if (sampling == SW_GRID_CENTER && cand < 0) {
+      sampling = SW_RANDOM_GRID;
+      a.sampling = SW_RANDOM_GRID;
+    }
+    switch (sampling) {
+      case SW_RANDOM_GRID: {
+        if (cand >= 21)
+          return fail(h, SW_ERR_DEEP_REROOT, "sampling grid deeper than MortonIndex64 (re-root path not supported)");
+        a.cell_shift = cand < 0 ? 63 : 3 * (20 - cand);
+        break;
+      }
+      case SW_GRID_CENTER:
+      case SW_JITTERED: {
+        if (h->prm.sampling == SW_GRID_CENTER && cand >= 21)
+          return fail(h, SW_ERR_DEEP_REROOT, "sampling grid deeper than MortonIndex64 (re-root path not supported)");
+        CK(cudaMemsetAsync(h->sel.p, 0, count, s));
+        CK(cudaMemsetAsync(h->d_error(), 0, 4, s));
+        SwArgminArgs g{};
+        g.in_key = in_key;
+        g.in_idx = in_idx;
+        g.count = count;
+        g.pos_sorted = h->pos_sorted.as<double>();
+        g.sampling = h->prm.sampling;
+        g.node_shift = node_shift;
+        g.node_level = node_level;
+        g.cand_level = cand;
+        g.cell_shift = cand < 0 ? 63 : 3 * (20 - cand);
+        g.spacing_at_node = h->prm.spacing_at_root / std::pow(2, node_level + 1);
+        g.bounds = h->bounds;
+        g.sel = h->sel.as<unsigned char>();
+        g.error_flag = h->d_error();
+        g.node_start = h->node_start.as<u32>();
+        g.tile_rank0 = h->tile_rank0.as<u32>();
+        g.allow_take_all = allow_take_all ? 1 : 0;
+        g.max_points_per_node = h->prm.max_points_per_node;
+        launch_select_argmin(g, h->scan_status.as<u64>(), h->d_tickets(), s);
+        h->stats.kernel_launches += 1;
+        h->stats.bytes_sample += (8 + 4 + 24 + 1 + 1) * count;
+        a.sel = h->sel.as<unsigned char>();
+        break;
+      }
+      case SW_MIN_DISTANCE: {
+        SwMinDistArgs m{};
+        m.in_key = in_key;
+        m.in_idx = in_idx;
+        m.count = count;
+        m.pos_sorted = h->pos_sorted.as<double>();
+        m.node_shift = node_shift;
+        m.node_level = node_level;
+        const double spacing_at_node = h->prm.spacing_at_root / std::pow(2, node_level + 1);
+        const float sf = static_cast<float>(spacing_at_node);
+        const float sq = sf * sf; // SparseGrid.cpp:11-14: squared in float
+        m.threshold = static_cast<double>(sq);
+        // Morton cell whose side is >= spacing * (1 + 1e-6): any two points closer than the spacing
+        // lie in the same or in adjacent cells.
+        {
+          const double ratio = root_extent_x(h) / (spacing_at_node * (1.0 + 1e-6));
+          int cl = static_cast<int>(std::floor(std::log2(ratio))) - 1; // cell level (0 = half the root)
+          if (cl > 20)
+            cl = 20;
+          m.cell_level = cl;
+          m.cell_shift = cl < 0 ? 63 : 3 * (20 - cl);
+        }
+        m.bounds = h->bounds;
+        m.sel = h->sel.as<unsigned char>();
+        m.node_start = h->node_start.as<u32>();
+        m.tile_rank0 = h->tile_rank0.as<u32>();
+        m.allow_take_all = allow_take_all ? 1 : 0;
+        m.max_points_per_node = h->prm.max_points_per_node;
+        CK(h->md_cell_start.ensure((count + 1) * 4));
+        CK(h->md_tile_rank0.ensure(sweep_tiles(count) * 4));
+        CK(h->md_cursor.ensure(count * 4));
+        CK(h->md_state.ensure(count));
+        SwMinDistScratch sc{};
+        sc.cell_start = h->md_cell_start.as<u32>();
+        sc.tile_rank0 = h->md_tile_rank0.as<u32>();
+        sc.n_cells = h->d_md_ncells();
+        sc.cursor = h->md_cursor.as<u32>();
+        sc.state = h->md_state.as<unsigned char>();
+        sc.changed = h->d_changed();
+        sc.status = h->scan_status.as<u64>();
+        sc.ticket = h->d_tickets();
+        sc.h_changed = &h->h_scalars->changed;
+        sc.d_scalars = h->scalars.p;
+        sc.h_scalars = h->h_scalars;
+        sc.scalars_bytes = sizeof(HostScalars);
+        sc.nbr_buf = &h->md_nbr.p;
+        sc.nbr_cap = &h->md_nbr.cap;
+        u32 rounds = 0, launches = 0;
+        u64 bytes = 0;
+        cudaError_t e = run_min_distance(m, sc, s, &rounds, &launches, &bytes);
+        if (e != cudaSuccess)
+          return fail_cuda(h, e, "run_min_distance");
+        h->stats.min_distance_rounds += rounds;
+        h->stats.kernel_launches += launches;
+        h->stats.bytes_sample += bytes;
+        a.sel = h->sel.as<unsigned char>();
+        break;
+      }
+      default:
+        return fail(h, SW_ERR_INVALID_ARGUMENT, "unknown sampling strategy");
+    }
+  }
+
+  a.out_key = h->out_key.as<u64>();
+  a.out_idx = h->out_idx.as<u32>();
+  a.out_offset = h->out_count;
+  a.rem_key = rem_key;
+  a.rem_idx = rem_idx;
+  a.node_index = h->node_index.as<u64>();
+  a.node_first = h->node_first.as<u64>();
+  a.node_base = h->node_count;
+  a.levels = levels;
+  launch_level_compact(a, h->d_n_selected(), h->scan_status.as<u64>(), h->d_tickets(), s);
+  h->stats.kernel_launches += 1;
+  rc = sync_scalars(h);
+  if (rc)
+    return rc;
+  if (h->h_scalars->error_flag)
+    return fail(h,
+                (int)h->h_scalars->error_flag,
+                h->h_scalars->error_flag == SW_ERR_JITTER_GRID_TOO_SMALL
+                  ? "Grids smaller than 16x16 are not supported currently!"
+                  : "Node is too small to be sampled with ImprovedPoissonSampling!");
+  const u64 n_sel = h->h_scalars->n_selected;
+  h->stats.bytes_sample += (8 + (in_idx ? 4 : 0)) * count + 12 * n_sel + (rem_key ? 12 * (count - n_sel) : 0);
+  h->stats.sweep_points += count;
+
+  Chunk c{};
+  c.levels = levels;
+  c.out_offset = h->out_count;
+  c.count = n_sel;
+  c.node_base = h->node_count;
+  c.n_nodes = n_nodes;
+  c.flags = chunk_flags | (force_all ? SW_NODE_TERMINAL : 0u);
+  h->chunks.push_back(c);
+  h->out_count += n_sel;
+  h->node_count += n_nodes;
+  *n_selected_out = n_sel;
+  return SW_OK;
+}
+
+// estimate_start_node_level_in_octree, TilingAlgorithms.cpp:1473-1535, from the level-5 bins
+int
+estimate_start_level(swgpu_tiler* h, int* S_out)
+{
+  launch_level5_bins(h->keys[0].as<u64>(), h->n, h->bins.as<u32>(), h->stream);
+  h->stats.kernel_launches += 1;
+  std::vector<u32> bins(262145);
+  CK(cudaMemcpyAsync(bins.data(), h->bins.p, 262145 * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t concurrency = h->prm.concurrency;
+  const u32 MIN_LEVEL = 3, MAX_LEVEL = 6;
+  for (u32 level = 0; level < MAX_LEVEL; ++level) {
+    // ranges at `level` = prefixes of (level + 1) levels = groups of 8^(5 - level) bins
+    const u32 group = 1u << (3 * (5 - level));
+    size_t ranges = 0, large = 0;
+    for (u32 b = 0; b < 262144u; b += group) {
+      const u32 cnt = bins[b + group] - bins[b];
+      if (cnt > 0) {
+        ++ranges;
+        if (cnt >= 100000u)
+          ++large;
+      }
+    }
+    float score = 0.f;
+    if (!(ranges <= concurrency / 2))
+      score = static_cast<float>(large) / static_cast<float>(concurrency);
+    if (score >= 1.f) {
+      *S_out = (int)std::max(level + 1, MIN_LEVEL);
+      return SW_OK;
+    }
+  }
+  *S_out = (int)MAX_LEVEL;
+  return SW_OK;
+}
+
+int
+run_batch(swgpu_tiler* h)
+{
+  const u64 n = h->n;
+  cudaStream_t s = h->stream;
+  h->chunks.clear();
+  h->out_count = 0;
+  h->node_count = 0;
+  h->start_level = -1;
+  h->batch_done = false;
+  h->finalized = false;
+  std::memset(&h->stats, 0, sizeof(h->stats));
+  h->stats.n_points = n;
+
+  if (n >= (1ull << 30))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "a batch is limited to 2^30 - 1 points per GPU");
+  if (h->prm.tiling == SW_FAST && n < h->prm.concurrency)
+    return fail(h, SW_ERR_TOO_FEW_POINTS, "Can't scatter a range that has less than 'scatter_factor' elements!");
+  if (n == 0)
+    return fail(h, SW_ERR_EMPTY_NODE, "tile_internal_node: Got zero points to tile @ node r");
+  int rc = ensure_batch_buffers(h, n);
+  if (rc)
+    return rc;
+
+  record(h, 0);
+  // K1
+  CK(cudaMemsetAsync(h->hist.p, 0, 8 * 256 * 4, s));
+  CK(cudaMemsetAsync(h->scalars.p, 0, 128, s));
+  launch_morton_encode(h->d_xyz, n, h->bounds, h->keys[0].as<u64>(), h->hist.as<u32>(), h->d_n_clamped(), s);
+  h->stats.kernel_launches += 1;
+  h->stats.bytes_index = 32 * n;
+  record(h, 1);
+  // K2
+  launch_radix_sort(h->keys[0].as<u64>(), h->keys[1].as<u64>(), h->vals[0].as<u32>(), h->vals[1].as<u32>(), n,
+                    h->hist.as<u32>(), h->sort_status.as<u32>(), h->d_tickets() + 8, s);
+  h->stats.kernel_launches += 9;
+  h->stats.bytes_sort = (8 * 24 - 4) * n;
+  record(h, 2);
+  // K4
+  if (needs_positions(h->prm.sampling)) {
+    launch_gather_positions(h->d_xyz, h->vals[0].as<u32>(), n, h->pos_sorted.as<double>(), s);
+    h->stats.kernel_launches += 1;
+    h->stats.bytes_gather = (4 + 24 + 24) * n;
+  }
+  record(h, 3);
+  CK(cudaGetLastError());
+
+  int first_levels = 0; // ACCURATE: root has 0 levels
+  if (h->prm.tiling == SW_FAST) {
+    int S = 0;
+    rc = estimate_start_level(h, &S);
+    if (rc)
+      return rc;
+    h->start_level = S;
+    first_levels = S;
+  }
+
+  // level-synchronous sweep
+  const u64* in_key = h->keys[0].as<u64>();
+  const u32* in_idx = nullptr;
+  u64 count = n;
+  u64* rem_key[2] = { h->keys[1].as<u64>(), h->wkey2.as<u64>() };
+  u32* rem_idx[2] = { h->vals[1].as<u32>(), h->widx2.as<u32>() };
+  int flip = 0;
+  for (int levels = first_levels; count > 0; ++levels) {
+    const int node_level = levels - 1;
+    const LevelKind kind = level_kind(h, node_level);
+    if (kind == KIND_REROOT || levels > 21)
+      return fail(h, SW_ERR_DEEP_REROOT, "deep re-root path (TilingAlgorithms.cpp:444-483) is not supported");
+    const bool terminal = (kind == KIND_TERMINAL);
+    if (!terminal && levels >= 21)
+      return fail(h, SW_ERR_DEEP_REROOT, "child level exceeds MortonIndex64 capacity");
+    u64 n_sel = 0;
+    rc = sweep_level(h, in_key, in_idx, count, levels, /*allow_take_all=*/true, terminal, rem_key[flip],
+                     rem_idx[flip], 0u, &n_sel, false, 0);
+    if (rc)
+      return rc;
+    h->stats.n_levels += 1;
+    in_key = rem_key[flip];
+    in_idx = rem_idx[flip];
+    flip ^= 1;
+    count -= n_sel;
+  }
+  record(h, 4);
+  CK(cudaGetLastError());
+  h->n_clamped = h->h_scalars->n_clamped;
+  h->batch_done = true;
+  return SW_OK;
+}
+
+int
+run_finalize(swgpu_tiler* h)
+{
+  if (!h->batch_done)
+    return SW_OK; // build_execution_graph never ran (TilingAlgorithms.cpp:1242-1246)
+  if (h->prm.tiling != SW_FAST || h->finalized)
+    return SW_OK;
+  const int S = h->start_level;
+  // input of the first reconstruct level: the chunk of the start nodes themselves
+  size_t src = 0; // chunks[0] has levels == S
+  for (int lv = S - 1; lv >= 0; --lv) {
+    const Chunk in = h->chunks[src];
+    u64 n_sel = 0;
+    const int rc = sweep_level(h, nullptr, nullptr, in.count, lv, /*allow_take_all=*/false, false, nullptr, nullptr,
+                               SW_NODE_RECONSTRUCTED, &n_sel, true, in.out_offset);
+    if (rc)
+      return rc;
+    h->stats.n_reconstruct_levels += 1;
+    src = h->chunks.size() - 1;
+  }
+  record(h, 5);
+  h->finalized = true;
+  return SW_OK;
+}
+
+} // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int
+swgpu_create(const sw_params* params, int device, swgpu_handle* out)
+{
+  if (!params || !out)
+    return SW_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (params->sampling < 0 || params->sampling > 3 || params->tiling < 0 || params->tiling > 1)
+    return SW_ERR_INVALID_ARGUMENT;
+  for (int a = 0; a < 3; ++a)
+    if (!(params->bounds_max[a] > params->bounds_min[a]))
+      return SW_ERR_INVALID_ARGUMENT;
+  if (!(params->spacing_at_root > 0.f))
+    return SW_ERR_INVALID_ARGUMENT;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    cudaGetLastError();
+    return SW_ERR_CUDA; // no CPU fallback
+  }
+  if (cudaSetDevice(device) != cudaSuccess)
+    return SW_ERR_CUDA;
+  // Tiler::Tiler refuses spacings that are too small for the bounds (process/Tiler.cpp:178-183)
+  const float ratio = std::log2f(static_cast<float>((params->bounds_max[0] - params->bounds_min[0]) /
+                                                    params->spacing_at_root));
+  if (ratio >= 21.f)
+    return SW_ERR_INVALID_ARGUMENT;
+
+  auto* h = new swgpu_tiler();
+  h->prm = *params;
+  if (h->prm.concurrency == 0)
+    h->prm.concurrency = 1;
+  h->device = device;
+  for (int a = 0; a < 3; ++a) {
+    h->bounds.min[a] = params->bounds_min[a];
+    h->bounds.max[a] = params->bounds_max[a];
+    // std::pow(2, MaxLevels) / node_bounds.extent(), OctreeAlgorithms.h:69
+    h->bounds.scale[a] = 2097152.0 / (params->bounds_max[a] - params->bounds_min[a]);
+  }
+  if (cudaMallocHost(reinterpret_cast<void**>(&h->h_scalars), sizeof(HostScalars)) != cudaSuccess ||
+      h->scalars.ensure(256) != cudaSuccess) {
+    delete h;
+    return SW_ERR_CUDA;
+  }
+  std::memset(h->h_scalars, 0, sizeof(HostScalars));
+  for (auto& e : h->ev)
+    cudaEventCreate(&e);
+  *out = h;
+  return SW_OK;
+}
+
+void
+swgpu_destroy(swgpu_handle h)
+{
+  if (!h)
+    return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = { &h->xyz_own,    &h->keys[0],   &h->keys[1],       &h->vals[0],     &h->vals[1],  &h->wkey2,
+                     &h->widx2,      &h->hist,      &h->sort_status,   &h->scalars,     &h->pos_sorted, &h->out_key,
+                     &h->out_idx,    &h->node_start, &h->tile_rank0,   &h->sel,         &h->scan_status, &h->node_index,
+                     &h->node_first, &h->bins,      &h->ids_tmp,       &h->md_cell_start, &h->md_tile_rank0, &h->md_nbr,
+                     &h->md_cursor,  &h->md_state };
+  for (DevBuf* b : bufs)
+    b->release();
+  if (h->h_scalars)
+    cudaFreeHost(h->h_scalars);
+  for (auto& e : h->ev)
+    if (e)
+      cudaEventDestroy(e);
+  delete h;
+}
+
+const char*
+swgpu_last_error(swgpu_handle h)
+{
+  return h ? h->err.c_str() : "invalid handle";
+}
+
+int
+swgpu_set_stream(swgpu_handle h, void* cuda_stream)
+{
+  if (!h)
+    return SW_ERR_INVALID_ARGUMENT;
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  return SW_OK;
+}
+
+int
+swgpu_reserve(swgpu_handle h, uint64_t n)
+{
+  if (!h)
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  return ensure_batch_buffers(h, n);
+}
+
+int
+swgpu_index_batch_device(swgpu_handle h, double* xyz_device, uint64_t n)
+{
+  if (!h || (!xyz_device && n))
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  h->d_xyz = xyz_device;
+  h->n = n;
+  return run_batch(h);
+}
+
+int
+swgpu_index_batch(swgpu_handle h, double* xyz_host, uint64_t n)
+{
+  if (!h || (!xyz_host && n))
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  CK(h->xyz_own.ensure(std::max<size_t>(n, 1) * 24));
+  CK(cudaMemcpyAsync(h->xyz_own.p, xyz_host, n * 24, cudaMemcpyHostToDevice, h->stream));
+  h->d_xyz = h->xyz_own.as<double>();
+  h->n = n;
+  const int rc = run_batch(h);
+  if (rc)
+    return rc;
+  if (h->n_clamped) { // index_point wrote clamped coordinates back into the PointBuffer
+    CK(cudaMemcpyAsync(xyz_host, h->xyz_own.p, n * 24, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return SW_OK;
+}
+
+int
+swgpu_finalize(swgpu_handle h)
+{
+  if (!h)
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  return run_finalize(h);
+}
+
+int
+swgpu_result_size(swgpu_handle h, uint64_t* n_nodes, uint64_t* n_point_ids)
+{
+  if (!h)
+    return SW_ERR_INVALID_ARGUMENT;
+  if (n_nodes)
+    *n_nodes = h->node_count;
+  if (n_point_ids)
+    *n_point_ids = h->out_count;
+  return SW_OK;
+}
+
+static int
+fill_node_table(swgpu_tiler* h, sw_node* nodes)
+{
+  if (!nodes || !h->node_count)
+    return SW_OK;
+  std::vector<u64> index(h->node_count), first(h->node_count);
+  CK(cudaMemcpyAsync(index.data(), h->node_index.p, h->node_count * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(first.data(), h->node_first.p, h->node_count * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (const Chunk& c : h->chunks) {
+    for (u32 k = 0; k < c.n_nodes; ++k) {
+      sw_node& nd = nodes[c.node_base + k];
+      nd.index = index[c.node_base + k];
+      nd.levels = (uint32_t)c.levels;
+      nd.flags = c.flags;
+      nd.first = first[c.node_base + k];
+      const u64 end = (k + 1 < c.n_nodes) ? first[c.node_base + k + 1] : (c.out_offset + c.count);
+      nd.count = end - nd.first;
+    }
+  }
+  return SW_OK;
+}
+
+int
+swgpu_get_nodes_device_ids(swgpu_handle h, sw_node* nodes, uint32_t* point_ids_device)
+{
+  if (!h)
+    return SW_ERR_INVALID_ARGUMENT;
+  if (!h->batch_done)
+    return fail(h, SW_ERR_STATE, "no batch has been indexed");
+  cudaSetDevice(h->device);
+  if (point_ids_device && h->out_count) {
+    launch_compose_ids(h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, point_ids_device, h->stream);
+    CK(cudaGetLastError());
+  }
+  return fill_node_table(h, nodes);
+}
+
+int
+swgpu_get_nodes(swgpu_handle h, sw_node* nodes, uint32_t* point_ids)
+{
+  if (!h)
+    return SW_ERR_INVALID_ARGUMENT;
+  if (!h->batch_done)
+    return fail(h, SW_ERR_STATE, "no batch has been indexed");
+  cudaSetDevice(h->device);
+  if (point_ids && h->out_count) {
+    CK(h->ids_tmp.ensure(h->out_count * 4));
+    launch_compose_ids(h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, h->ids_tmp.as<u32>(), h->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(point_ids, h->ids_tmp.p, h->out_count * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  const int rc = fill_node_table(h, nodes);
+  if (rc)
+    return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return SW_OK;
+}
+
+int
+swgpu_get_start_level(swgpu_handle h, int32_t* level)
+{
+  if (!h || !level)
+    return SW_ERR_INVALID_ARGUMENT;
+  *level = h->start_level;
+  return SW_OK;
+}
+
+int
+swgpu_get_clamped_count(swgpu_handle h, uint64_t* n)
+{
+  if (!h || !n)
+    return SW_ERR_INVALID_ARGUMENT;
+  *n = h->n_clamped;
+  return SW_OK;
+}
+
+int
+swgpu_get_keys(swgpu_handle h, uint64_t* keys, uint32_t* order)
+{
+  if (!h)
+    return SW_ERR_INVALID_ARGUMENT;
+  if (!h->batch_done)
+    return fail(h, SW_ERR_STATE, "no batch has been indexed");
+  cudaSetDevice(h->device);
+  if (keys)
+    CK(cudaMemcpyAsync(keys, h->keys[0].p, h->n * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (order)
+    CK(cudaMemcpyAsync(order, h->vals[0].p, h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SW_OK;
+}
+
+int
+swgpu_gather_attribute_device(swgpu_handle h, const void* src_device, uint32_t width, void* dst_device)
+{
+  if (!h || !src_device || !dst_device)
+    return SW_ERR_INVALID_ARGUMENT;
+  if (!h->batch_done)
+    return fail(h, SW_ERR_STATE, "no batch has been indexed");
+  cudaSetDevice(h->device);
+  CK(h->ids_tmp.ensure(std::max<u64>(h->out_count, 1) * 4));
+  launch_compose_ids(h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, h->ids_tmp.as<u32>(), h->stream);
+  if (width == 24)
+    launch_gather_positions(static_cast<const double*>(src_device), h->ids_tmp.as<u32>(), h->out_count,
+                            static_cast<double*>(dst_device), h->stream);
+  else if (width == 1 || width == 2 || width == 3 || width == 4 || width == 8 || width == 12)
+    launch_gather_bytes(src_device, h->ids_tmp.as<u32>(), h->out_count, width, dst_device, h->stream);
+  else
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "unsupported attribute width");
+  CK(cudaGetLastError());
+  return SW_OK;
+}
+
+int
+swgpu_morton_encode_device(swgpu_handle h, double* xyz_device, uint64_t n, uint64_t* keys_device)
+{
+  if (!h || (n && (!xyz_device || !keys_device)))
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  CK(h->hist.ensure(8 * 256 * 4));
+  CK(cudaMemsetAsync(h->hist.p, 0, 8 * 256 * 4, h->stream));
+  CK(cudaMemsetAsync(h->scalars.p, 0, 128, h->stream));
+  launch_morton_encode(xyz_device, n, h->bounds, reinterpret_cast<u64*>(keys_device), h->hist.as<u32>(), h->d_n_clamped(), h->stream);
+  CK(cudaGetLastError());
+  const int rc = sync_scalars(h);
+  if (rc)
+    return rc;
+  h->n_clamped = h->h_scalars->n_clamped;
+  return SW_OK;
+}
+
+int
+swgpu_sort_keys_device(swgpu_handle h, uint64_t* keys_device, uint64_t n, uint32_t* order_device)
+{
+  if (!h || (n && (!keys_device || !order_device)))
+    return SW_ERR_INVALID_ARGUMENT;
+  if (n >= (1ull << 30))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "a batch is limited to 2^30 - 1 points per GPU");
+  if (n == 0)
+    return SW_OK;
+  cudaSetDevice(h->device);
+  CK(h->keys[1].ensure(n * 8));
+  CK(h->vals[1].ensure(n * 4));
+  CK(h->hist.ensure(8 * 256 * 4));
+  CK(h->sort_status.ensure(sort_status_words(n) * 4));
+  CK(cudaMemsetAsync(h->hist.p, 0, 8 * 256 * 4, h->stream));
+  launch_key_histogram(reinterpret_cast<const u64*>(keys_device), n, h->hist.as<u32>(), h->stream);
+  launch_radix_sort(reinterpret_cast<u64*>(keys_device), h->keys[1].as<u64>(), order_device, h->vals[1].as<u32>(), n, h->hist.as<u32>(),
+                    h->sort_status.as<u32>(), h->d_tickets() + 8, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return SW_OK;
+}
+
+int
+swgpu_enable_timing(swgpu_handle h, int enable)
+{
+  if (!h)
+    return SW_ERR_INVALID_ARGUMENT;
+  h->timing = enable != 0;
+  return SW_OK;
+}
+
+int
+swgpu_get_stats(swgpu_handle h, swgpu_stats* out)
+{
+  if (!h || !out)
+    return SW_ERR_INVALID_ARGUMENT;
+  h->stats.n_output_ids = h->out_count;
+  h->stats.n_nodes = h->node_count;
+  if (h->timing && h->batch_done) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaEventElapsedTime(&h->stats.ms_index, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->stats.ms_sort, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&h->stats.ms_gather, h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&h->stats.ms_sample, h->ev[3], h->ev[4]);
+    const bool fin = h->finalized && h->prm.tiling == SW_FAST;
+    cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], fin ? h->ev[5] : h->ev[4]);
+    if (fin) {
+      float r = 0.f;
+      cudaEventElapsedTime(&r, h->ev[4], h->ev[5]);
+      h->stats.ms_sample += r;
+    }
+    cudaGetLastError();
+  }
+  *out = h->stats;
+  return SW_OK;
+}
+
+} // extern "C"

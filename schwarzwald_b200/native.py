@@ -1,0 +1,93 @@
+"""ctypes binding of include/swgpu.h.  Fails loudly when the CUDA library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class SwParams(C.Structure):
+    """sw_params, include/sw_types.h (mirrors TilerMetaParameters, reference process/Tiler.h:64-75)."""
+
+    _fields_ = [
+        ("sampling", C.c_int32),
+        ("tiling", C.c_int32),
+        ("spacing_at_root", C.c_float),
+        ("max_depth", C.c_uint32),
+        ("max_points_per_node", C.c_uint64),
+        ("bounds_min", C.c_double * 3),
+        ("bounds_max", C.c_double * 3),
+        ("concurrency", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class SwgpuStats(C.Structure):
+    _fields_ = [
+        ("n_points", C.c_uint64),
+        ("n_output_ids", C.c_uint64),
+        ("n_nodes", C.c_uint64),
+        ("n_levels", C.c_uint32),
+        ("n_reconstruct_levels", C.c_uint32),
+        ("sweep_points", C.c_uint64),
+        ("bytes_index", C.c_uint64),
+        ("bytes_sort", C.c_uint64),
+        ("bytes_gather", C.c_uint64),
+        ("bytes_sample", C.c_uint64),
+        ("ms_index", C.c_float),
+        ("ms_sort", C.c_float),
+        ("ms_gather", C.c_float),
+        ("ms_sample", C.c_float),
+        ("ms_total", C.c_float),
+        ("kernel_launches", C.c_uint32),
+        ("min_distance_rounds", C.c_uint32),
+    ]
+
+
+# every symbol include/swgpu.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("swgpu_create", C.c_int, [C.POINTER(SwParams), C.c_int, C.POINTER(C.c_void_p)]),
+    ("swgpu_destroy", None, [C.c_void_p]),
+    ("swgpu_last_error", C.c_char_p, [C.c_void_p]),
+    ("swgpu_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("swgpu_reserve", C.c_int, [C.c_void_p, C.c_uint64]),
+    ("swgpu_index_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    ("swgpu_index_batch_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    ("swgpu_finalize", C.c_int, [C.c_void_p]),
+    ("swgpu_result_size", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("swgpu_get_nodes", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("swgpu_get_nodes_device_ids", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("swgpu_get_start_level", C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    ("swgpu_get_clamped_count", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    ("swgpu_get_keys", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("swgpu_gather_attribute_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    ("swgpu_morton_encode_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    ("swgpu_sort_keys_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    ("swgpu_enable_timing", C.c_int, [C.c_void_p, C.c_int]),
+    ("swgpu_get_stats", C.c_int, [C.c_void_p, C.POINTER(SwgpuStats)]),
+]
+
+
+def library_path() -> str:
+    return os.path.join(HERE, "libswgpu.so")
+
+
+def load_library():
+    """Loads libswgpu.so and binds every declared symbol.  No fallback of any kind."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            "schwarzwald_b200/libswgpu.so is missing: build it with ./build_native.sh "
+            "(or __graft_entry__.build()).  There is no CPU fallback for the tiler kernels.")
+    lib = C.CDLL(path)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _LIB = lib
+    return lib
