@@ -150,7 +150,7 @@ node_level_to_sample_from(int32_t source_level, const NodeStructure& root)
 }
 
 /* PERMUTATIONS_{16,32,64}, Sampling.h:14-138, regenerated into oracle/jitter_tables.inc by
- * oracle/gen_jitter_tables.py (data tables, not code). */
+ * tools/gen_jitter_tables.py (data tables, not code). */
 #include "jitter_tables.inc"
 
 static inline double

@@ -197,7 +197,7 @@ level_compact_kernel(SwLevelArgs a, u64* __restrict__ n_selected, u64* __restric
         else if (a.sampling == SW_RANDOM_GRID)
           sel = (cmask[j] >> lane) & 1u; // first point of each cell run (Sampling.h:253-284)
         else
-          sel = a.sel[i] != 0;
+          sel = a.sel[i] == 1;
       }
       smask[j] = __ballot_sync(0xffffffffu, sel);
       wsel += __popc(smask[j]);
@@ -654,10 +654,403 @@ launch_select_argmin(const SwArgminArgs& a, u64* status, u32* ticket, cudaStream
 }
 
 // =============================================================================================
-// K9  MIN_DISTANCE (placeholder until the conflict-resolution kernels land)
+// K9  MIN_DISTANCE: greedy minimum-distance selection in Morton order
 // =============================================================================================
-cudaError_t
-run_min_distance(const SwMinDistArgs&, const SwMinDistScratch&, cudaStream_t, u32*, u32*, u64*)
+//   PoissonDiskSampling::sample_points   tiling/Sampling.h:421-471
+//   SparseGrid::add / GridCell::isDistant datastructures/SparseGrid.cpp:116-146, GridCell.cpp:41-58
+// Reference semantics: walk the node's points in Morton order; accept a point iff no previously
+// ACCEPTED point lies closer than the spacing (squared distance < (double)(float)(s*s), strict).
+// The SparseGrid only accelerates the search (its 27-cell stencil covers every point within the
+// spacing because its cells are 5 spacings wide), so the result is the lexicographically first
+// maximal independent set of the "closer than spacing" graph.
+//
+// Parallel formulation (exact): a point is REJECTED as soon as one earlier in-range point is
+// ACCEPTED, and ACCEPTED once every earlier in-range point is REJECTED.  Candidates are found
+// through Morton cells whose side is >= spacing: the list is sorted, so a cell is a contiguous run
+// and "earlier" = earlier in the own cell + every point of the neighbour cells with a smaller
+// Morton code.  Each undecided point scans its candidates in a fixed order with a persistent
+// cursor and stops at the first in-range candidate that is still undecided.  One cooperative
+// kernel iterates to the fix point with grid-wide barriers and a shrinking work list.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+#define MD_UNDECIDED 0
+#define MD_ACCEPTED 1
+#define MD_REJECTED 2
+#define MD_NBR_SLOTS 27 /* slot 0 = count, then up to 26 earlier neighbour cells */
+
+static cudaError_t
+grow(SwGrowBuf& b, size_t bytes)
 {
-  return cudaErrorNotSupported;
+  if (bytes <= b.cap)
+    return cudaSuccess;
+  if (b.p)
+    cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = bytes + bytes / 4;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e == cudaSuccess)
+    b.cap = want;
+  return e;
+}
+
+void
+free_min_distance_scratch(SwMinDistScratch& sc)
+{
+  SwGrowBuf* all[] = { &sc.cell_start, &sc.cell_tile_rank0, &sc.cell_of, &sc.state, &sc.cur_off, &sc.cur_seg, &sc.lpos,
+                       &sc.wl0,        &sc.wl1,             &sc.hkeys,   &sc.hvals, &sc.nbr,     &sc.counters };
+  for (SwGrowBuf* b : all) {
+    if (b->p)
+      cudaFree(b->p);
+    b->p = nullptr;
+    b->cap = 0;
+  }
+}
+
+// per point: cell rank, activity (take-all nodes are never sampled), compact position copy
+__global__ void __launch_bounds__(SWP_THREADS)
+md_setup_kernel(SwMinDistArgs a, int cell_shift, const u32* __restrict__ cell_tile_rank0, u32* __restrict__ cell_of,
+                unsigned char* __restrict__ state, u32* __restrict__ cur_off, unsigned char* __restrict__ cur_seg,
+                double* __restrict__ lpos)
+{
+  __shared__ u32 s_w[SWP_WARPS];
+  __shared__ u32 s_w2[SWP_WARPS];
+  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 tile = blockIdx.x;
+  const u64 base = (u64)tile * SW_SWEEP_TILE;
+  const u32 lt = lanemask_lt();
+  u32 nmask[SWP_ITEMS], cmask[SWP_ITEMS];
+  u32 wn = 0, wc = 0;
+#pragma unroll
+  for (int j = 0; j < SWP_ITEMS; ++j) {
+    const u64 i = base + item_pos(warp, lane, j);
+    bool nh = false, ch = false;
+    if (i < a.count) {
+      const u64 k = a.in_key[i] & SW_KEY_MASK;
+      if (i == 0) {
+        nh = ch = true;
+      } else {
+        const u64 pk = a.in_key[i - 1] & SW_KEY_MASK;
+        nh = (k >> a.node_shift) != (pk >> a.node_shift);
+        ch = (k >> cell_shift) != (pk >> cell_shift);
+      }
+    }
+    nmask[j] = __ballot_sync(0xffffffffu, nh);
+    cmask[j] = __ballot_sync(0xffffffffu, ch);
+    wn += __popc(nmask[j]);
+    wc += __popc(cmask[j]);
+  }
+  u32 tn, tc;
+  const u32 nexcl = warp_totals_exclusive(wn, warp, lane, s_w, tn);
+  const u32 cexcl = warp_totals_exclusive(wc, warp, lane, s_w2, tc);
+  u32 nrun = a.tile_rank0[tile] + nexcl;
+  u32 crun = cell_tile_rank0[tile] + cexcl;
+#pragma unroll
+  for (int j = 0; j < SWP_ITEMS; ++j) {
+    const u64 i = base + item_pos(warp, lane, j);
+    const u32 self = lt | (1u << lane);
+    const u32 node_rank = nrun + __popc(nmask[j] & self) - 1;
+    const u32 cell_rank = crun + __popc(cmask[j] & self) - 1;
+    nrun += __popc(nmask[j]);
+    crun += __popc(cmask[j]);
+    if (i < a.count) {
+      bool active = true;
+      if (a.allow_take_all) {
+        const u32 cnt = a.node_start[node_rank + 1] - a.node_start[node_rank];
+        active = (u64)cnt > a.max_points_per_node;
+      }
+      cell_of[i] = cell_rank;
+      state[i] = active ? MD_UNDECIDED : MD_REJECTED;
+      cur_off[i] = 0;
+      cur_seg[i] = 0;
+      if (lpos) {
+        const u64 idx = a.in_idx[i];
+        lpos[3 * i] = a.pos_sorted[3 * idx];
+        lpos[3 * i + 1] = a.pos_sorted[3 * idx + 1];
+        lpos[3 * i + 2] = a.pos_sorted[3 * idx + 2];
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ u32
+md_hash(u64 code, u32 mask)
+{
+  code ^= code >> 33;
+  code *= 0xff51afd7ed558ccdull;
+  code ^= code >> 33;
+  return (u32)code & mask;
+}
+
+__global__ void __launch_bounds__(256)
+md_hash_insert_kernel(const u64* __restrict__ in_key, const u32* __restrict__ cell_start, u32 n_cells, int cell_shift,
+                      u64* __restrict__ hkeys, u32* __restrict__ hvals, u32 mask)
+{
+  const u32 c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= n_cells)
+    return;
+  const u64 code = (in_key[cell_start[c]] & SW_KEY_MASK) >> cell_shift;
+  u32 slot = md_hash(code, mask);
+  while (true) {
+    const u64 prev = atomicCAS(&hkeys[slot], 0ull, code + 1);
+    if (prev == 0ull || prev == code + 1) {
+      hvals[slot] = c;
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
+// earlier neighbour cells (smaller Morton code, same node) of every cell
+__global__ void __launch_bounds__(256)
+md_neighbors_kernel(const u64* __restrict__ in_key, const u32* __restrict__ cell_start, u32 n_cells, int cell_shift,
+                    int cell_levels, int node_levels, const u64* __restrict__ hkeys, const u32* __restrict__ hvals,
+                    u32 mask, u32* __restrict__ nbr)
+{
+  const u32 c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= n_cells)
+    return;
+  u32* out = nbr + (size_t)c * MD_NBR_SLOTS;
+  u32 cnt = 0;
+  const int below = cell_levels - node_levels; // cell levels below the node
+  if (below > 0) {
+    const u64 code = (in_key[cell_start[c]] & SW_KEY_MASK) >> cell_shift;
+    const long long side = 1ll << cell_levels;
+    const long long x = (long long)contract_bits_by_3(code >> 2);
+    const long long y = (long long)contract_bits_by_3(code >> 1);
+    const long long z = (long long)contract_bits_by_3(code);
+    const u64 node_prefix = code >> (3 * below);
+    for (int dx = -1; dx <= 1; ++dx)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dz = -1; dz <= 1; ++dz) {
+          if (!dx && !dy && !dz)
+            continue;
+          const long long X = x + dx, Y = y + dy, Z = z + dz;
+          if (X < 0 || Y < 0 || Z < 0 || X >= side || Y >= side || Z >= side)
+            continue;
+          const u64 nc = expand_bits_by_3((u64)Z) | (expand_bits_by_3((u64)Y) << 1) | (expand_bits_by_3((u64)X) << 2);
+          if (nc >= code || (nc >> (3 * below)) != node_prefix)
+            continue;
+          u32 slot = md_hash(nc, mask);
+          while (true) {
+            const u64 k = hkeys[slot];
+            if (k == 0ull)
+              break;
+            if (k == nc + 1) {
+              out[1 + cnt++] = hvals[slot];
+              break;
+            }
+            slot = (slot + 1) & mask;
+          }
+        }
+  }
+  out[0] = cnt;
+}
+
+__device__ __forceinline__ unsigned char
+ld_state(const unsigned char* p)
+{
+  return __ldcg(p); // L2: sees decisions made by other SMs during the same round
+}
+
+// counters: [0] work-list length A, [1] work-list length B, [2] rounds
+__global__ void __launch_bounds__(256)
+md_rounds_kernel(u64 count, const double* __restrict__ P, const u32* __restrict__ cell_start,
+                 const u32* __restrict__ cell_of, const u32* __restrict__ nbr, unsigned char* state,
+                 u32* __restrict__ cur_off, unsigned char* __restrict__ cur_seg, u32* wl0, u32* wl1, u32* counters,
+                 double threshold)
+{
+  cg::grid_group grid = cg::this_grid();
+  const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 nthreads = (u64)gridDim.x * blockDim.x;
+  const u32 lane = threadIdx.x & 31;
+  u64 work = count; // round 0 visits every point
+  u32* wl_in = nullptr;
+  u32* wl_out = wl0;
+  u32 round = 0;
+  while (true) {
+    u32* out_count = counters + (round & 1u);
+    // uniform trip count per warp so that the aggregated append below stays convergent
+    const u64 iters = (work + nthreads - 1) / nthreads;
+    for (u64 it = 0; it < iters; ++it) {
+      const u64 w = it * nthreads + tid;
+      bool still = false;
+      u32 i = 0;
+      if (w < work) {
+        i = wl_in ? wl_in[w] : (u32)w;
+        if (ld_state(state + i) == MD_UNDECIDED) {
+          const u32 c = cell_of[i];
+          const u32* nb = nbr + (size_t)c * MD_NBR_SLOTS;
+          const u32 nseg = 1 + nb[0];
+          u32 seg = cur_seg[i], off = cur_off[i];
+          const double px = P[3 * (u64)i], py = P[3 * (u64)i + 1], pz = P[3 * (u64)i + 2];
+          int decided = 0;
+          while (seg < nseg) {
+            u32 b, e;
+            if (seg == 0) {
+              b = cell_start[c];
+              e = i;
+            } else {
+              const u32 nc = nb[seg];
+              b = cell_start[nc];
+              e = cell_start[nc + 1];
+            }
+            u32 q = b + off;
+            bool blocked = false;
+            for (; q < e; ++q) {
+              const unsigned char s = ld_state(state + q);
+              if (s == MD_REJECTED)
+                continue;
+              const double dx = px - P[3 * (u64)q];
+              const double dy = py - P[3 * (u64)q + 1];
+              const double dz = pz - P[3 * (u64)q + 2];
+              const double d = dx * dx + dy * dy + dz * dz; // x*x + y*y + z*z, no FMA
+              if (d < threshold) {
+                if (s == MD_ACCEPTED)
+                  decided = MD_REJECTED;
+                else
+                  blocked = true;
+                break;
+              }
+            }
+            if (decided || blocked) {
+              off = q - b;
+              break;
+            }
+            ++seg;
+            off = 0;
+          }
+          if (decided) {
+            state[i] = MD_REJECTED;
+          } else if (seg >= nseg) {
+            state[i] = MD_ACCEPTED;
+          } else {
+            cur_seg[i] = (unsigned char)seg;
+            cur_off[i] = off;
+            still = true;
+          }
+        }
+      }
+      // warp-aggregated append of the points that are still undecided
+      const u32 m = __ballot_sync(0xffffffffu, still);
+      if (m) {
+        u32 basep = 0;
+        if (lane == (u32)(__ffs(m) - 1))
+          basep = atomicAdd(out_count, __popc(m));
+        basep = __shfl_sync(0xffffffffu, basep, __ffs(m) - 1);
+        if (still)
+          wl_out[basep + __popc(m & lanemask_lt())] = i;
+      }
+    }
+    __threadfence();
+    grid.sync();
+    const u32 remaining = *((volatile u32*)out_count);
+    ++round;
+    if (remaining == 0)
+      break;
+    // next round reads what was just written; reset the other counter for the round after
+    work = remaining;
+    wl_in = wl_out;
+    wl_out = (wl_out == wl0) ? wl1 : wl0;
+    if (tid == 0)
+      counters[round & 1u] = 0;
+    grid.sync();
+  }
+  if (tid == 0)
+    counters[2] = round;
+}
+
+cudaError_t
+run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stream, u32* rounds, u32* launches,
+                 u64* bytes)
+{
+  const u64 n = a.count;
+  cudaError_t e;
+  const size_t tiles = sweep_tiles(n);
+#define MD_TRY(x)                                                                                                      \
+  do {                                                                                                                 \
+    e = (x);                                                                                                           \
+    if (e != cudaSuccess)                                                                                              \
+      return e;                                                                                                        \
+  } while (0)
+  MD_TRY(grow(sc.cell_start, (n + 1) * 4));
+  MD_TRY(grow(sc.cell_tile_rank0, tiles * 4));
+  MD_TRY(grow(sc.cell_of, n * 4));
+  MD_TRY(grow(sc.state, n));
+  MD_TRY(grow(sc.cur_off, n * 4));
+  MD_TRY(grow(sc.cur_seg, n));
+  MD_TRY(grow(sc.wl0, n * 4));
+  MD_TRY(grow(sc.wl1, n * 4));
+  MD_TRY(grow(sc.counters, 64));
+  if (a.in_idx)
+    MD_TRY(grow(sc.lpos, n * 24));
+
+  // cells never span nodes: use the finer of the two prefixes
+  int cell_levels = a.cell_levels;
+  if (cell_levels < a.node_levels)
+    cell_levels = a.node_levels;
+  const int cell_shift = shift_for_levels(cell_levels);
+
+  u32* counters = static_cast<u32*>(sc.counters.p);
+  MD_TRY(cudaMemsetAsync(counters, 0, 64, stream));
+  launch_node_rle(a.in_key, n, cell_shift, static_cast<u32*>(sc.cell_start.p), static_cast<u32*>(sc.cell_tile_rank0.p),
+                  counters + 4, sc.status, sc.ticket, stream);
+  md_setup_kernel<<<(u32)tiles, SWP_THREADS, 0, stream>>>(
+    a, cell_shift, static_cast<const u32*>(sc.cell_tile_rank0.p), static_cast<u32*>(sc.cell_of.p),
+    static_cast<unsigned char*>(sc.state.p), static_cast<u32*>(sc.cur_off.p), static_cast<unsigned char*>(sc.cur_seg.p),
+    a.in_idx ? static_cast<double*>(sc.lpos.p) : nullptr);
+  MD_TRY(cudaMemcpyAsync(sc.h_pinned, counters + 4, 4, cudaMemcpyDeviceToHost, stream));
+  MD_TRY(cudaStreamSynchronize(stream));
+  const u32 n_cells = sc.h_pinned[0];
+
+  u32 cap = 64;
+  while (cap < 2 * n_cells)
+    cap <<= 1;
+  MD_TRY(grow(sc.hkeys, (size_t)cap * 8));
+  MD_TRY(grow(sc.hvals, (size_t)cap * 4));
+  MD_TRY(grow(sc.nbr, (size_t)n_cells * MD_NBR_SLOTS * 4));
+  MD_TRY(cudaMemsetAsync(sc.hkeys.p, 0, (size_t)cap * 8, stream));
+  const u32 cgrid = (n_cells + 255) / 256;
+  md_hash_insert_kernel<<<cgrid, 256, 0, stream>>>(a.in_key, static_cast<const u32*>(sc.cell_start.p), n_cells,
+                                                   cell_shift, static_cast<u64*>(sc.hkeys.p),
+                                                   static_cast<u32*>(sc.hvals.p), cap - 1);
+  md_neighbors_kernel<<<cgrid, 256, 0, stream>>>(a.in_key, static_cast<const u32*>(sc.cell_start.p), n_cells, cell_shift,
+                                                 cell_levels, a.node_levels, static_cast<const u64*>(sc.hkeys.p),
+                                                 static_cast<const u32*>(sc.hvals.p), cap - 1,
+                                                 static_cast<u32*>(sc.nbr.p));
+
+  // persistent cooperative kernel: as many CTAs as are co-resident
+  static int coop_blocks = 0;
+  if (!coop_blocks) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, md_rounds_kernel, 256, 0);
+    coop_blocks = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  u64 count = n;
+  const double* P = a.in_idx ? static_cast<const double*>(sc.lpos.p) : a.pos_sorted;
+  const u32* cell_start = static_cast<const u32*>(sc.cell_start.p);
+  const u32* cell_of = static_cast<const u32*>(sc.cell_of.p);
+  const u32* nbr = static_cast<const u32*>(sc.nbr.p);
+  unsigned char* state = static_cast<unsigned char*>(sc.state.p);
+  u32* cur_off = static_cast<u32*>(sc.cur_off.p);
+  unsigned char* cur_seg = static_cast<unsigned char*>(sc.cur_seg.p);
+  u32* wl0 = static_cast<u32*>(sc.wl0.p);
+  u32* wl1 = static_cast<u32*>(sc.wl1.p);
+  double thr = a.threshold;
+  void* args[] = { &count, &P, &cell_start, &cell_of, &nbr, &state, &cur_off, &cur_seg, &wl0, &wl1, &counters, &thr };
+  u64 want_blocks = (n + 255) / 256;
+  int blocks = (int)(want_blocks < (u64)coop_blocks ? want_blocks : (u64)coop_blocks);
+  if (blocks < 1)
+    blocks = 1;
+  MD_TRY(cudaLaunchCooperativeKernel((void*)md_rounds_kernel, dim3(blocks), dim3(256), args, 0, stream));
+  MD_TRY(cudaMemcpyAsync(sc.h_pinned, counters + 2, 4, cudaMemcpyDeviceToHost, stream));
+  MD_TRY(cudaStreamSynchronize(stream));
+  *rounds = sc.h_pinned[0];
+  *launches = 5;
+  *bytes = n * (8 + 8 + 8 + (a.in_idx ? 52 : 0) + 24 + 10);
+  return cudaGetLastError();
+#undef MD_TRY
 }

@@ -107,42 +107,40 @@ struct SwArgminArgs
 // status >= 5 * sweep_tiles(count) u64
 void launch_select_argmin(const SwArgminArgs& a, u64* status, u32* ticket, cudaStream_t stream);
 
+// grow-only device buffer owned by the caller (freed by the tiler handle)
+struct SwGrowBuf
+{
+  void* p;
+  size_t cap;
+};
+
 struct SwMinDistArgs
 {
   const u64* in_key;
-  const u32* in_idx;
+  const u32* in_idx; // nullptr = identity
   u64 count;
   const double* pos_sorted;
   int node_shift;
-  int node_level;
-  int cell_level;   // Morton level of the neighbour-search cells (side >= spacing)
-  int cell_shift;
+  int node_levels;  // levels of the nodes of this sweep level (node level + 1)
+  int cell_levels;  // levels of the neighbour-search cells (cell side >= spacing), <= 21
   double threshold; // (double)(float)(spacing_f * spacing_f), SparseGrid.cpp:11-14
-  SwBounds bounds;
-  unsigned char* sel; // out: 1 = accepted
   const u32* node_start;
   const u32* tile_rank0;
   int allow_take_all;
   u64 max_points_per_node;
 };
+
 struct SwMinDistScratch
 {
-  u32* cell_start; // count + 1
-  u32* tile_rank0; // sweep_tiles
-  u32* n_cells;    // device scalar
-  u32* cursor;     // count
-  unsigned char* state; // count
-  u32* changed;    // device scalar
-  u64* status;
+  SwGrowBuf cell_start, cell_tile_rank0, cell_of, state, cur_off, cur_seg, lpos, wl0, wl1, hkeys, hvals, nbr,
+    counters;
+  u64* status; // look-back descriptors (>= sweep_tiles u64)
   u32* ticket;
-  // host mirror of the device scalar block (pinned) for the per-round convergence test
-  void* d_scalars;
-  void* h_scalars;
-  size_t scalars_bytes;
-  u32* h_changed;
-  // growable neighbour / hash scratch owned by the caller
-  void** nbr_buf;
-  size_t* nbr_cap;
+  u32* h_pinned; // pinned host scratch, >= 8 u32
 };
-cudaError_t run_min_distance(const SwMinDistArgs& a, const SwMinDistScratch& sc, cudaStream_t stream, u32* rounds,
+
+// Greedy minimum-distance selection for every sampled node of one level.  On return
+// scratch.state.p holds one byte per point: 1 = accepted, 2 = rejected / not sampled.
+cudaError_t run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stream, u32* rounds,
                              u32* launches, u64* bytes);
+void free_min_distance_scratch(SwMinDistScratch& sc);

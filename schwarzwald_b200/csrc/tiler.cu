@@ -84,6 +84,7 @@ struct HostScalars
   u32 error_flag;
   u32 changed;
   u64 n_selected;
+  u32 scratch[16]; // pinned scratch for the min-distance driver (starts at u32 index 8... see below)
 };
 
 enum LevelKind
@@ -123,8 +124,7 @@ struct swgpu_tiler
   u64 node_count = 0;
   DevBuf bins;
   DevBuf ids_tmp;
-  // min-distance scratch
-  DevBuf md_cell_start, md_tile_rank0, md_nbr, md_cursor, md_state;
+  SwMinDistScratch md{}; // min-distance scratch
 
   HostScalars* h_scalars = nullptr; // pinned
   std::vector<Chunk> chunks;
@@ -244,7 +244,7 @@ level_kind(const swgpu_tiler* h, int node_level)
 int
 sync_scalars(swgpu_tiler* h)
 {
-  CK(cudaMemcpyAsync(h->h_scalars, h->scalars.p, sizeof(HostScalars), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_scalars, h->scalars.p, 24, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return SW_OK;
 }
@@ -379,55 +379,38 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
         m.count = count;
         m.pos_sorted = h->pos_sorted.as<double>();
         m.node_shift = node_shift;
-        m.node_level = node_level;
+        m.node_levels = levels;
         const double spacing_at_node = h->prm.spacing_at_root / std::pow(2, node_level + 1);
         const float sf = static_cast<float>(spacing_at_node);
         const float sq = sf * sf; // SparseGrid.cpp:11-14: squared in float
         m.threshold = static_cast<double>(sq);
-        // Morton cell whose side is >= spacing * (1 + 1e-6): any two points closer than the spacing
-        // lie in the same or in adjacent cells.
+        // Morton cells whose side is >= spacing * (1 + 1e-6): two points closer than the spacing lie
+        // in the same or in adjacent cells.  side(levels) = extent / 2^levels.
         {
           const double ratio = root_extent_x(h) / (spacing_at_node * (1.0 + 1e-6));
-          int cl = static_cast<int>(std::floor(std::log2(ratio))) - 1; // cell level (0 = half the root)
-          if (cl > 20)
-            cl = 20;
-          m.cell_level = cl;
-          m.cell_shift = cl < 0 ? 63 : 3 * (20 - cl);
+          int cl = ratio >= 1.0 ? static_cast<int>(std::floor(std::log2(ratio))) : 0;
+          if (cl > 21)
+            cl = 21;
+          if (cl < 0)
+            cl = 0;
+          m.cell_levels = cl;
         }
-        m.bounds = h->bounds;
-        m.sel = h->sel.as<unsigned char>();
         m.node_start = h->node_start.as<u32>();
         m.tile_rank0 = h->tile_rank0.as<u32>();
         m.allow_take_all = allow_take_all ? 1 : 0;
         m.max_points_per_node = h->prm.max_points_per_node;
-        CK(h->md_cell_start.ensure((count + 1) * 4));
-        CK(h->md_tile_rank0.ensure(sweep_tiles(count) * 4));
-        CK(h->md_cursor.ensure(count * 4));
-        CK(h->md_state.ensure(count));
-        SwMinDistScratch sc{};
-        sc.cell_start = h->md_cell_start.as<u32>();
-        sc.tile_rank0 = h->md_tile_rank0.as<u32>();
-        sc.n_cells = h->d_md_ncells();
-        sc.cursor = h->md_cursor.as<u32>();
-        sc.state = h->md_state.as<unsigned char>();
-        sc.changed = h->d_changed();
-        sc.status = h->scan_status.as<u64>();
-        sc.ticket = h->d_tickets();
-        sc.h_changed = &h->h_scalars->changed;
-        sc.d_scalars = h->scalars.p;
-        sc.h_scalars = h->h_scalars;
-        sc.scalars_bytes = sizeof(HostScalars);
-        sc.nbr_buf = &h->md_nbr.p;
-        sc.nbr_cap = &h->md_nbr.cap;
+        h->md.status = h->scan_status.as<u64>();
+        h->md.ticket = h->d_tickets();
+        h->md.h_pinned = h->h_scalars->scratch;
         u32 rounds = 0, launches = 0;
         u64 bytes = 0;
-        cudaError_t e = run_min_distance(m, sc, s, &rounds, &launches, &bytes);
+        cudaError_t e = run_min_distance(m, h->md, s, &rounds, &launches, &bytes);
         if (e != cudaSuccess)
           return fail_cuda(h, e, "run_min_distance");
         h->stats.min_distance_rounds += rounds;
         h->stats.kernel_launches += launches;
         h->stats.bytes_sample += bytes;
-        a.sel = h->sel.as<unsigned char>();
+        a.sel = static_cast<const unsigned char*>(h->md.state.p);
         break;
       }
       default:
@@ -689,10 +672,10 @@ swgpu_destroy(swgpu_handle h)
   DevBuf* bufs[] = { &h->xyz_own,    &h->keys[0],   &h->keys[1],       &h->vals[0],     &h->vals[1],  &h->wkey2,
                      &h->widx2,      &h->hist,      &h->sort_status,   &h->scalars,     &h->pos_sorted, &h->out_key,
                      &h->out_idx,    &h->node_start, &h->tile_rank0,   &h->sel,         &h->scan_status, &h->node_index,
-                     &h->node_first, &h->bins,      &h->ids_tmp,       &h->md_cell_start, &h->md_tile_rank0, &h->md_nbr,
-                     &h->md_cursor,  &h->md_state };
+                     &h->node_first, &h->bins,      &h->ids_tmp };
   for (DevBuf* b : bufs)
     b->release();
+  free_min_distance_scratch(h->md);
   if (h->h_scalars)
     cudaFreeHost(h->h_scalars);
   for (auto& e : h->ev)

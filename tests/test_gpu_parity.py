@@ -1,0 +1,304 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): Morton codes, sort order, node membership and the selections of
+all four sampling strategies are BIT-EXACT (integer / index work; the FP64 distance arithmetic is
+reproduced without FMA contraction, so even GRID_CENTER / JITTERED / MIN_DISTANCE are exact).
+The oracle here is oracle/tiler_oracle.cpp ("port"), itself pinned against the reference's own code
+in tests/test_oracle_*.py.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SAMPLINGS = ["RANDOM_GRID", "GRID_CENTER", "JITTERED", "MIN_DISTANCE"]
+TILINGS = ["ACCURATE", "FAST"]
+
+
+def _torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def make_cloud(kind, n, seed, **kw):
+    from schwarzwald_b200 import synth
+    return synth.generate(kind, n, seed, device="cpu", **kw).numpy()
+
+
+def setup_case(xyz, fraction=250.0, origin=False):
+    import schwarzwald_b200 as sw
+    if origin:
+        bmin, bmax = sw.cubic_bounds_at_origin(xyz.min(0), xyz.max(0))
+    else:
+        bmin, bmax = sw.cubic_bounds(xyz.min(0), xyz.max(0))
+    return bmin, bmax, sw.spacing_from_diagonal_fraction(bmin, bmax, fraction)
+
+
+def run_both(port_oracle, xyz, sampling, tiling, bmin, bmax, spacing, max_pts, conc, max_depth=100):
+    import schwarzwald_b200 as sw
+    from oracle import sworacle
+    params = sworacle.make_params(sampling, tiling, spacing, bmin, bmax, max_points_per_node=max_pts,
+                                  concurrency=conc, max_depth=max_depth)
+    want, clamped = port_oracle.tile(params, xyz, return_clamped=True)
+    with sw.GpuTiler(sampling, tiling, bmin, bmax, spacing, max_points_per_node=max_pts, concurrency=conc,
+                     max_depth=max_depth) as t:
+        host = xyz.copy()
+        got = t.tile(host)
+        keys, order = t.keys(len(xyz))
+    return want, clamped, got, host, keys, order
+
+
+def assert_same(want, clamped, got, host, keys, order):
+    assert np.array_equal(keys, want.keys), "Morton keys differ"
+    assert np.array_equal(order, want.order), "sort permutation differs"
+    assert np.array_equal(host, clamped), "clamped positions differ"
+    assert got.start_level == want.start_level
+    wt, wi = want.canonical()
+    gt, gi = got.canonical()
+    assert np.array_equal(wt[:, :3], gt[:, :3]), "node table (levels, index, count) differs"
+    assert np.array_equal(wt[:, 3] & 6, gt[:, 3] & 6), "node flags (terminal / reconstructed) differ"
+    assert np.array_equal(wi, gi), "node contents differ"
+
+
+@pytest.mark.parametrize("tiling", TILINGS)
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+def test_uniform_small(port_oracle, sampling, tiling):
+    _torch_cuda()
+    xyz = make_cloud("uniform", 60_000, 11, side_m=100.0)
+    bmin, bmax, spacing = setup_case(xyz)
+    assert_same(*run_both(port_oracle, xyz, sampling, tiling, bmin, bmax, spacing, 500, 2))
+
+
+@pytest.mark.parametrize("tiling", TILINGS)
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+def test_terrain_medium(port_oracle, sampling, tiling):
+    _torch_cuda()
+    n = 1_500_000 if sampling != "MIN_DISTANCE" else 600_000
+    xyz = make_cloud("terrain", n, 2, side_m=2000.0)
+    bmin, bmax, spacing = setup_case(xyz)
+    assert_same(*run_both(port_oracle, xyz, sampling, tiling, bmin, bmax, spacing, 20000, 8))
+
+
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+def test_urban_clustered(port_oracle, sampling):
+    _torch_cuda()
+    xyz = make_cloud("urban", 400_000, 3, side_m=400.0, height_m=60.0, n_primitives=100)
+    bmin, bmax, spacing = setup_case(xyz)
+    assert_same(*run_both(port_oracle, xyz, sampling, "FAST", bmin, bmax, spacing, 5000, 4))
+
+
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+def test_skewed_density(port_oracle, sampling):
+    """95 % of the points in 1 % of the volume: long cells, unbalanced nodes."""
+    _torch_cuda()
+    xyz = make_cloud("skewed", 500_000, 5, side_m=200.0)
+    bmin, bmax, spacing = setup_case(xyz)
+    assert_same(*run_both(port_oracle, xyz, sampling, "ACCURATE", bmin, bmax, spacing, 20000, 8))
+
+
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+def test_config1_shape_3dtiles_float32(port_oracle, sampling):
+    """BASELINE configs[0] shape: uniform cloud shifted to the centre and rounded to float32
+    (process/TilerProcess.cpp:552-559), bounds = cubic at origin; FAST with concurrency 8."""
+    torch = _torch_cuda()
+    import schwarzwald_b200 as sw
+    from schwarzwald_b200 import synth
+    raw = synth.generate("uniform", 800_000, 1, device="cpu", side_m=1000.0)
+    mn, mx = synth.tight_bounds(raw)
+    cmin, cmax = sw.cubic_bounds(mn, mx)
+    xyz = synth.shift_to_centre_float32(raw, cmin, cmax).numpy()
+    bmin, bmax = sw.cubic_bounds_at_origin(mn, mx)
+    spacing = sw.spacing_from_diagonal_fraction(bmin, bmax)
+    assert_same(*run_both(port_oracle, xyz, sampling, "FAST", bmin, bmax, spacing, 20000, 8))
+
+
+@pytest.mark.parametrize("tiling", TILINGS)
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+def test_outliers_duplicates_and_ties(port_oracle, sampling, tiling):
+    """Outliers are clamped in place; duplicate points produce identical 63-bit keys whose order
+    must follow the original index (stable sort rule)."""
+    _torch_cuda()
+    rng = np.random.default_rng(5)
+    xyz = np.round(rng.random((50_000, 3)) * np.array([300.0, 200.0, 50.0]) + 1000.0, 2)
+    inner = xyz[100:].copy()
+    xyz[:50] += 900.0          # outside the bounds computed from the rest
+    xyz[50:100] -= 700.0
+    xyz[200:260] = xyz[200]    # 60 exact duplicates
+    xyz[300:400, 2] = xyz[300, 2]
+    bmin, bmax, spacing = setup_case(inner)
+    want, clamped, got, host, keys, order = run_both(port_oracle, xyz, sampling, tiling, bmin, bmax, spacing, 300, 2)
+    assert want.duplicate_keys > 0
+    assert_same(want, clamped, got, host, keys, order)
+
+
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+def test_tiny_inputs(port_oracle, sampling):
+    _torch_cuda()
+    rng = np.random.default_rng(9)
+    for n in (1, 2, 33, 2049):
+        xyz = rng.random((n, 3)) * 10.0
+        bmin, bmax = np.zeros(3), np.full(3, 10.0)
+        import schwarzwald_b200 as sw
+        spacing = sw.spacing_from_diagonal_fraction(bmin, bmax)
+        assert_same(*run_both(port_oracle, xyz, sampling, "ACCURATE", bmin, bmax, spacing, 4, 1))
+
+
+@pytest.mark.parametrize("sampling", ["RANDOM_GRID", "MIN_DISTANCE"])
+def test_max_depth_terminal_nodes(port_oracle, sampling):
+    """max_depth = 2: nodes at level 2 become terminal and keep every remaining point unsampled
+    (tile_terminal_node, TilingAlgorithms.cpp:206-241)."""
+    _torch_cuda()
+    xyz = make_cloud("uniform", 100_000, 4, side_m=50.0)
+    bmin, bmax, spacing = setup_case(xyz)
+    want, clamped, got, host, keys, order = run_both(port_oracle, xyz, sampling, "ACCURATE", bmin, bmax, spacing, 100, 2,
+                                                     max_depth=2)
+    assert (want.nodes["flags"] & 2).any()
+    assert_same(want, clamped, got, host, keys, order)
+
+
+def test_coarse_spacing_candidate_level_root(port_oracle):
+    """Spacing of the order of the extent: the candidate level is -1 and the grid strategies take
+    the first point of the node (Sampling.h:290-301, 346-348)."""
+    _torch_cuda()
+    xyz = make_cloud("uniform", 30_000, 6, side_m=10.0)
+    bmin, bmax, _ = setup_case(xyz)
+    spacing = np.float32((bmax[0] - bmin[0]) * 0.8)
+    for sampling in ("RANDOM_GRID", "GRID_CENTER"):
+        assert_same(*run_both(port_oracle, xyz, sampling, "ACCURATE", bmin, bmax, spacing, 50, 1))
+
+
+def test_error_codes_match_reference_exceptions(port_oracle):
+    """JITTERED throws for grids below 16 cells per axis (Sampling.h:632-635); FAST's scatter throws
+    when a batch has fewer points than indexing threads (threading/Parallel.h:181-186)."""
+    _torch_cuda()
+    import schwarzwald_b200 as sw
+    from oracle import sworacle
+    xyz = make_cloud("uniform", 30_000, 6, side_m=10.0)
+    bmin, bmax, _ = setup_case(xyz)
+    spacing = sw.spacing_from_diagonal_fraction(bmin, bmax, 20.0)  # E/spacing ~ 11.5 < 16
+    params = sworacle.make_params("JITTERED", "ACCURATE", spacing, bmin, bmax, max_points_per_node=1000, concurrency=1)
+    with pytest.raises(sworacle.OracleFailure) as oe:
+        port_oracle.tile(params, xyz)
+    with sw.GpuTiler("JITTERED", "ACCURATE", bmin, bmax, spacing, max_points_per_node=1000, concurrency=1) as t:
+        with pytest.raises(sw.SwgpuError) as ge:
+            t.tile(xyz.copy())
+    assert ge.value.code == oe.value.code == 4
+
+    few = xyz[:3].copy()
+    spacing = sw.spacing_from_diagonal_fraction(bmin, bmax)
+    params = sworacle.make_params("RANDOM_GRID", "FAST", spacing, bmin, bmax, concurrency=8)
+    with pytest.raises(sworacle.OracleFailure) as oe:
+        port_oracle.tile(params, few)
+    with sw.GpuTiler("RANDOM_GRID", "FAST", bmin, bmax, spacing, concurrency=8) as t:
+        with pytest.raises(sw.SwgpuError) as ge:
+            t.tile(few.copy())
+    assert ge.value.code == oe.value.code == 9
+
+
+def test_device_resident_input_and_reuse(port_oracle):
+    """Device pointer input (bench path), handle reuse across batches, attribute permutation."""
+    torch = _torch_cuda()
+    import schwarzwald_b200 as sw
+    from oracle import sworacle
+    xyz = make_cloud("terrain", 700_000, 2, side_m=1000.0)
+    bmin, bmax, spacing = setup_case(xyz)
+    params = sworacle.make_params("GRID_CENTER", "FAST", spacing, bmin, bmax, concurrency=8)
+    want = port_oracle.tile(params, xyz)
+    dev = torch.from_numpy(xyz).cuda()
+    intensity = torch.arange(len(xyz), dtype=torch.int32, device="cuda").to(torch.int16)
+    rgb = (torch.arange(len(xyz) * 3, device="cuda") % 251).to(torch.uint8).reshape(-1, 3).contiguous()
+    with sw.GpuTiler("GRID_CENTER", "FAST", bmin, bmax, spacing, concurrency=8) as t:
+        t.set_stream(torch.cuda.current_stream().cuda_stream)
+        for _ in range(2):  # second pass reuses every buffer
+            t.build_execution_graph(dev)
+            t.finalize()
+            got = t.result()
+            wt, wi = want.canonical()
+            gt, gi = got.canonical()
+            assert np.array_equal(wt[:, :3], gt[:, :3]) and np.array_equal(wi, gi)
+        nn, ni = t.result_size()
+        ids_dev = torch.empty(ni, dtype=torch.int32, device="cuda")
+        t.result_device_ids(ids_dev.data_ptr())
+        out_i = torch.empty(ni, dtype=torch.int16, device="cuda")
+        out_rgb = torch.empty((ni, 3), dtype=torch.uint8, device="cuda")
+        out_xyz = torch.empty((ni, 3), dtype=torch.float64, device="cuda")
+        t.gather_attribute_device(intensity.data_ptr(), 2, out_i.data_ptr())
+        t.gather_attribute_device(rgb.data_ptr(), 3, out_rgb.data_ptr())
+        t.gather_attribute_device(dev.data_ptr(), 24, out_xyz.data_ptr())
+        torch.cuda.synchronize()
+        ids = got.ids.astype(np.int64)
+        assert np.array_equal(ids_dev.cpu().numpy().view(np.uint32), got.ids)
+        assert np.array_equal(out_i.cpu().numpy(), intensity.cpu().numpy()[ids])
+        assert np.array_equal(out_rgb.cpu().numpy(), rgb.cpu().numpy()[ids])
+        assert np.array_equal(out_xyz.cpu().numpy(), xyz[ids])
+
+
+def test_primitives_morton_and_sort(port_oracle):
+    """Stand-alone K1 / K2 entry points on device buffers."""
+    torch = _torch_cuda()
+    import schwarzwald_b200 as sw
+    rng = np.random.default_rng(3)
+    n = 1_000_003
+    xyz = rng.random((n, 3)) * np.array([10.0, 20.0, 5.0]) - 3.0
+    bmin, bmax = np.array([-2.5, -2.0, -2.9]), np.array([6.5, 16.0, 1.5])
+    want_keys, want_xyz = port_oracle.index_points(xyz, (bmin, bmax))
+    dev = torch.from_numpy(xyz).cuda()
+    keys = torch.empty(n, dtype=torch.int64, device="cuda")
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    with sw.GpuTiler("RANDOM_GRID", "ACCURATE", bmin, bmax, 0.1) as t:
+        t.morton_encode_device(dev.data_ptr(), n, keys.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(keys.cpu().numpy().view(np.uint64), want_keys)
+        assert np.array_equal(dev.cpu().numpy(), want_xyz)
+        assert t.clamped_count() == int((xyz != want_xyz).any(axis=1).sum())
+        t.sort_keys_device(keys.data_ptr(), n, order.data_ptr())
+        torch.cuda.synchronize()
+    perm = np.argsort(want_keys, kind="stable")
+    assert np.array_equal(keys.cpu().numpy().view(np.uint64), want_keys[perm])
+    assert np.array_equal(order.cpu().numpy().view(np.uint32), perm.astype(np.uint32))
+
+
+def test_full_size_properties():
+    """BASELINE-size run (100 M points is the bench; here 20 M keeps the suite short) checked through
+    size-independent properties: sortedness, permutation, every point stored exactly once below the
+    start level, node membership by key prefix, one RANDOM_GRID winner per occupied cell."""
+    torch = _torch_cuda()
+    import schwarzwald_b200 as sw
+    from schwarzwald_b200 import synth
+    n = 20_000_000
+    dev = synth.generate("terrain", n, 2, device="cuda")
+    mn, mx = synth.tight_bounds(dev)
+    bmin, bmax = sw.cubic_bounds(mn, mx)
+    spacing = sw.spacing_from_diagonal_fraction(bmin, bmax)
+    with sw.GpuTiler("RANDOM_GRID", "FAST", bmin, bmax, spacing, concurrency=32) as t:
+        t.build_execution_graph(dev)
+        t.finalize()
+        res = t.result()
+        keys, order = t.keys(n)
+    assert (np.diff(keys.astype(np.int64)) >= 0).all(), "keys not sorted"
+    seen = np.zeros(n, np.uint8)
+    seen[order] += 1
+    assert (seen == 1).all(), "sort permutation is not a permutation"
+    S = res.start_level
+    key_of = np.empty(n, np.uint64)
+    key_of[order] = keys
+    counts = np.zeros(n, np.uint32)
+    for node in res.nodes:
+        ids = res.ids[int(node["first"]): int(node["first"]) + int(node["count"])]
+        lv = int(node["levels"])
+        k = key_of[ids]
+        assert (np.diff(k.astype(np.int64)) >= 0).all(), "node content not in Morton order"
+        if lv:
+            assert ((k >> np.uint64(3 * (21 - lv))) == node["index"]).all(), "point outside its node"
+        if lv >= S:
+            np.add.at(counts, ids, 1)
+    assert (counts == 1).all(), "every point must be stored exactly once at or below the start level"
+    # root node (reconstructed): one point per occupied cell of its sampling grid, at most
+    root = res.nodes[(res.nodes["levels"] == 0)][0]
+    ids = res.ids[int(root["first"]): int(root["first"]) + int(root["count"])]
+    e = bmax[0] - bmin[0]
+    cand = max(-1, int(np.floor(np.log2(np.float32(e / float(spacing))))) - 1)
+    cells = key_of[ids] >> np.uint64(3 * (20 - cand))
+    assert len(np.unique(cells)) == len(cells)
