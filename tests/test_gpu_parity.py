@@ -145,13 +145,14 @@ def test_tiny_inputs(port_oracle, sampling):
         assert_same(*run_both(port_oracle, xyz, sampling, "ACCURATE", bmin, bmax, spacing, 4, 1))
 
 
-@pytest.mark.parametrize("sampling", ["RANDOM_GRID", "MIN_DISTANCE"])
+@pytest.mark.parametrize("sampling", SAMPLINGS)
 def test_max_depth_terminal_nodes(port_oracle, sampling):
     """max_depth = 2: nodes at level 2 become terminal and keep every remaining point unsampled
-    (tile_terminal_node, TilingAlgorithms.cpp:206-241)."""
+    (tile_terminal_node, TilingAlgorithms.cpp:206-241).  The coarse spacing (diagonal / 60) leaves
+    enough points unselected for the sweep to reach level 2."""
     _torch_cuda()
     xyz = make_cloud("uniform", 100_000, 4, side_m=50.0)
-    bmin, bmax, spacing = setup_case(xyz)
+    bmin, bmax, spacing = setup_case(xyz, fraction=60.0)
     want, clamped, got, host, keys, order = run_both(port_oracle, xyz, sampling, "ACCURATE", bmin, bmax, spacing, 100, 2,
                                                      max_depth=2)
     assert (want.nodes["flags"] & 2).any()
