@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--points", type=int, default=WORKLOAD_POINTS, help="points per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -250,7 +251,7 @@ def main():
 
     # ---- e2e: host buffers in, node table + point ids out, copies inside the timed region -----------
     e2e = None
-    if world == 1:
+    if world == 1 and not args.no_e2e:
         host = torch.empty((n_local, 3), dtype=torch.float64, pin_memory=True)
         host.copy_(xyz)
         host_np = host.numpy()

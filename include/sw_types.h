@@ -72,6 +72,7 @@ typedef struct sw_node {
 #define SW_ERR_EMPTY_NODE 7            /* TilingAlgorithms.cpp:253-259 */
 #define SW_ERR_STATE 8
 #define SW_ERR_TOO_FEW_POINTS 9        /* Parallel.h:181-186: fewer points than indexing threads */
+#define SW_ERR_COLLECTIVE 10           /* multi-GPU: the caller-supplied all-reduce hook failed */
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,56 @@ int swgpu_morton_encode_device(swgpu_handle h, double* xyz_device, uint64_t n, u
 /* Stable sort of (key, original index) on the device; keys sorted in place, order_device gets n u32. */
 int swgpu_sort_keys_device(swgpu_handle h, uint64_t* keys_device, uint64_t n, uint32_t* order_device);
 
+/*
+ * ---- Multi-GPU: one handle per GPU / process, every GPU tiles whole Morton-prefix subtrees -------
+ * The reference is a single process; its unit of independent work is the octree node (one taskflow
+ * task per start node, tiling/TilingAlgorithms.cpp:1314-1351, :499-561).  These entry points let a
+ * host driver (schwarzwald_b200/distributed.py over torch.distributed/NCCL, or a C++ driver over
+ * ncclSend/ncclRecv) shard the points by the leading octree levels of their Morton key:
+ *   1. swgpu_morton_encode_device       local keys (index_point, clamps in place)
+ *   2. swgpu_prefix_histogram_device    local counts of the 8^6 level-5 prefixes; the caller SUMS
+ *                                       them over the ranks (all-reduce)
+ *   3. swgpu_estimate_start_level       FAST: global start level from the summed histogram
+ *      swgpu_choose_splitters           contiguous prefix ranges of (nearly) equal point count
+ *   4. swgpu_partition_device           stable send buffer (positions + global ids) per destination
+ *   5. [caller: all-to-all over NVLink]
+ *   6. swgpu_set_shard + swgpu_index_batch_device on the received points, swgpu_finalize
+ * Nodes with fewer than `shard_levels` levels span GPUs: every GPU reports its part of such a node
+ * (same index/levels, ids in Morton order); the parts concatenated in rank order are the node.
+ * Their take-all decision (Sampling.h:201-208) uses the global point count, summed through the
+ * caller's all-reduce hook.  Grid strategies stay bit-exact because a sampling cell never spans
+ * shards as long as shard_levels <= swgpu_max_shard_levels().
+ */
+#define SWGPU_MAX_RANKS 16
+#define SWGPU_PREFIX_BINS 262144
+
+/* In-place SUM all-reduce of `count` u32 device counters over all ranks, enqueued on (or ordered
+ * with) `cuda_stream`.  Returns 0 on success.  Called once per sweep level below shard_levels by
+ * every rank, in the same order on every rank. */
+typedef int (*swgpu_allreduce_u32_fn)(void* ctx, uint32_t* device_counters, uint64_t count, void* cuda_stream);
+
+int swgpu_prefix_histogram_device(swgpu_handle h, const uint64_t* keys_device, uint64_t n, uint32_t* bins_device);
+/* estimate_start_node_level_in_octree (TilingAlgorithms.cpp:1473-1535) on GLOBAL level-5 prefix
+ * counts (host array of SWGPU_PREFIX_BINS).  Pure host function. */
+int swgpu_estimate_start_level(const uint32_t* bins_host, uint32_t concurrency, int32_t* level);
+/* first_prefix[r] .. first_prefix[r+1] = level-5 prefixes owned by rank r (n_ranks + 1 entries),
+ * boundaries snapped to multiples of 8^(6 - shard_levels).  Pure host function. */
+int swgpu_choose_splitters(const uint32_t* bins_host, uint32_t n_ranks, uint32_t shard_levels, uint32_t* first_prefix);
+/* Deepest shard prefix for which every sampling cell of this handle's strategy lies inside one
+ * shard (<= 6). */
+int swgpu_max_shard_levels(swgpu_handle h, uint32_t* shard_levels);
+/* Stable partition of the local points by destination rank.  out_xyz_device (n x 3 doubles) and
+ * out_id_device (n u32 = id_base + local index) are ordered by destination; send_counts_host
+ * receives n_ranks counts. */
+int swgpu_partition_device(swgpu_handle h, const uint64_t* keys_device, const double* xyz_device, uint64_t n,
+                           const uint32_t* first_prefix, uint32_t n_ranks, uint32_t id_base, double* out_xyz_device,
+                           uint32_t* out_id_device, uint64_t* send_counts_host);
+/* Marks the handle as tiling one shard.  start_level: FAST's global start level (-1 = estimate from
+ * the local points); global_ids_device: id of every received point (returned by swgpu_get_nodes
+ * instead of local indices; may be NULL).  shard_levels = 0 switches sharding off. */
+int swgpu_set_shard(swgpu_handle h, uint32_t shard_levels, int32_t start_level, swgpu_allreduce_u32_fn allreduce,
+                    void* allreduce_ctx, const uint32_t* global_ids_device);
+
 /* Algorithmic bytes moved by the last index_batch + finalize according to the accounting model
  * of DESIGN.md (used by bench.py for the roofline line), and the per-stage device times in ms
  * when timing was enabled with swgpu_enable_timing (cudaEvents on the handle's stream). */

@@ -176,6 +176,12 @@ launch_key_histogram(const u64* keys, u64 n, u32* hist, cudaStream_t stream)
 #define RS_ITEMS 16
 #define RS_TILE (RS_THREADS * RS_ITEMS) // 4096 pairs per tile
 #define RS_RADIX 256
+#ifndef RS_MATCH_MODE
+#define RS_MATCH_MODE 2 /* 0 = __match_any_sync, 1 = eight ballots, 2 = shared-memory atomicOr */
+#endif
+#ifndef RS_MIN_CTAS
+#define RS_MIN_CTAS 4 /* CTAs per SM the register allocation is capped for */
+#endif
 
 #define RS_FLAG_AGG (1u << 30)
 #define RS_FLAG_PFX (2u << 30)
@@ -210,19 +216,33 @@ digit_base_kernel(u32* __restrict__ hist)
   }
 }
 
-template<bool FIRST>
-__global__ void __launch_bounds__(RS_THREADS)
+// One pass = one read and one write of every (key, id) pair.  Per tile of 4096 pairs:
+//   1. early counts   per-warp digit histograms by shared-memory atomics; the tile's digit counts
+//                     are published (AGG) before any ranking work, so successors never spin on us
+//   2. ranking        stable rank of every key inside the tile: __match_any_sync groups the lanes
+//                     holding the same digit, the group leader reserves the group's slots in the
+//                     warp's running offset, lanes keep their lane order
+//   3. exchange       keys (then ids) go through shared memory in ranked order so that the global
+//                     writes are runs of consecutive addresses per digit
+//   4. look-back      thread d resolves digit d's global offset (decoupled look-back) between the
+//                     key and the id exchange, long after step 1 published this tile's counts
+// The warp histograms alias the exchange buffer (they are dead once the ranks are final), which
+// keeps a CTA at ~50 KB of shared memory: four CTAs per SM.
+template<int PASS, bool FIRST>
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
 onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
-                     u32* __restrict__ vals_out, u32 n, int shift, const u32* __restrict__ digit_base,
-                     u32* __restrict__ status, u32* __restrict__ ticket)
+                     u32* __restrict__ vals_out, u32 n, const u32* __restrict__ digit_base, u32* __restrict__ status,
+                     u32* __restrict__ ticket)
 {
+  constexpr int SHIFT = 8 * PASS;
   extern __shared__ __align__(16) unsigned char smem[];
-  u64* s_keys = reinterpret_cast<u64*>(smem);                           // RS_TILE * 8
-  u32* s_vals = reinterpret_cast<u32*>(smem + RS_TILE * 8);             // RS_TILE * 4
-  u32* s_whist = reinterpret_cast<u32*>(smem + RS_TILE * 12);           // RS_WARPS * 256
-  u32* s_excl = s_whist + RS_WARPS * RS_RADIX;                          // 256 tile-local exclusive offsets
-  u32* s_gofs = s_excl + RS_RADIX;                                      // 256 global base - local offset
-  u32* s_wsum = s_gofs + RS_RADIX;                                      // RS_WARPS
+  u64* s_keys = reinterpret_cast<u64*>(smem);               // RS_TILE * 8
+  u32* s_vals = reinterpret_cast<u32*>(smem + RS_TILE * 8); // RS_TILE * 4
+  // per (warp, digit) table entry: .x = lanes currently holding the digit (RS_MATCH_MODE 2),
+  // .y = count, later the next free tile-local rank.  Aliases s_keys.
+  uint2* s_tab = reinterpret_cast<uint2*>(smem);             // RS_WARPS * 256 * 8 B
+  u32* s_gofs = reinterpret_cast<u32*>(smem + RS_TILE * 12); // 256: global base - tile-local offset
+  u32* s_wsum = s_gofs + RS_RADIX;                           // RS_WARPS
   __shared__ u32 s_tile;
 
   const u32 tid = threadIdx.x;
@@ -231,78 +251,51 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
 
   if (tid == 0)
     s_tile = atomicAdd(ticket, 1u);
-  for (u32 i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS)
-    s_whist[i] = 0;
+#pragma unroll
+  for (int i = 0; i < RS_WARPS; ++i)
+    s_tab[i * RS_RADIX + tid] = make_uint2(0u, 0u);
   __syncthreads();
   const u32 tile = s_tile;
   const u32 tile_base = tile * RS_TILE;
   const u32 valid = (n - tile_base) < RS_TILE ? (n - tile_base) : RS_TILE;
+  const bool full = valid == RS_TILE;
 
   // ---- load (warp-striped: item j of a warp is 32 consecutive pairs) -------------------------
   u64 key[RS_ITEMS];
-  u32 val[RS_ITEMS];
   const u32 warp_base = warp * (32 * RS_ITEMS) + lane;
+  if (full) {
 #pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) {
-    const u32 p = warp_base + j * 32;
-    key[j] = (p < valid) ? keys_in[tile_base + p] : ~0ull;
-  }
+    for (int j = 0; j < RS_ITEMS; ++j)
+      key[j] = keys_in[tile_base + warp_base + j * 32];
+  } else {
 #pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) {
-    const u32 p = warp_base + j * 32;
-    if (FIRST)
-      val[j] = tile_base + p;
-    else
-      val[j] = (p < valid) ? vals_in[tile_base + p] : 0u;
+    for (int j = 0; j < RS_ITEMS; ++j) {
+      const u32 p = warp_base + j * 32;
+      key[j] = (p < valid) ? keys_in[tile_base + p] : ~0ull;
+    }
   }
 
-  // ---- rank inside the warp: match.any on the digit keeps the order stable --------------------
-  u32 rank[RS_ITEMS];
-  u32* my_hist = s_whist + warp * RS_RADIX;
-  const u32 lt = lanemask_lt();
+  // ---- 1. early counts --------------------------------------------------------------------------
+  uint2* my_tab = s_tab + warp * RS_RADIX;
 #pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) {
-    const u32 d = (u32)(key[j] >> shift) & 255u;
-    const u32 peers = __match_any_sync(0xffffffffu, d);
-    const u32 lower = __popc(peers & lt);
-    const u32 base = my_hist[d];
-    __syncwarp();
-    if (lower == 0)
-      my_hist[d] = base + __popc(peers);
-    __syncwarp();
-    rank[j] = base + lower;
-  }
+  for (int j = 0; j < RS_ITEMS; ++j)
+    atomicAdd(&my_tab[(u32)(key[j] >> SHIFT) & 255u].y, 1u);
   __syncthreads();
 
-  // ---- per digit: offsets of each warp inside the tile, tile count, look-back -----------------
+  u32 my_excl;  // tile-local exclusive offset of digit `tid`
+  u32 my_count; // keys of the tile with digit `tid`
   {
     const u32 d = tid; // RS_THREADS == RS_RADIX
+    u32 c[RS_WARPS];
     u32 run = 0;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
-      const u32 c = s_whist[w * RS_RADIX + d];
-      s_whist[w * RS_RADIX + d] = run;
-      run += c;
+      c[w] = s_tab[w * RS_RADIX + d].y;
+      run += c[w];
     }
-    u32 prev = 0;
+    my_count = run;
     u32* my_status = status + (size_t)tile * RS_RADIX + d;
-    if (tile == 0) {
-      st_relaxed_u32(my_status, RS_FLAG_PFX | run);
-    } else {
-      st_relaxed_u32(my_status, RS_FLAG_AGG | run);
-      const u32* look = my_status - RS_RADIX;
-      while (true) {
-        u32 s;
-        do {
-          s = ld_relaxed_u32(look);
-        } while ((s >> 30) == 0);
-        prev += s & RS_VAL_MASK;
-        if ((s >> 30) == 2)
-          break;
-        look -= RS_RADIX;
-      }
-      st_relaxed_u32(my_status, RS_FLAG_PFX | ((prev + run) & RS_VAL_MASK));
-    }
+    st_relaxed_u32(my_status, (tile == 0 ? RS_FLAG_PFX : RS_FLAG_AGG) | run);
     // exclusive scan of the tile counts over the 256 digits
     u32 incl = run;
 #pragma unroll
@@ -318,35 +311,135 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w)
       wofs += (w < (int)warp) ? s_wsum[w] : 0u;
-    const u32 excl = wofs + incl - run;
-    s_excl[d] = excl;
-    s_gofs[d] = digit_base[d] + prev - excl;
+    my_excl = wofs + incl - run;
+    // warp counts -> first tile-local rank of (warp, digit)
+    u32 acc = my_excl;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      s_tab[w * RS_RADIX + d].y = acc;
+      acc += c[w];
+    }
   }
   __syncthreads();
 
-  // ---- exchange through shared memory so that global writes are runs of consecutive addresses --
+  // ---- 2. ranking ---------------------------------------------------------------------------------
+  // Lanes holding the same digit form a group; the group takes the next `size` ranks of its
+  // (warp, digit) entry in lane order.  RS_MATCH_MODE picks how the group is found: measured on
+  // B200, __match_any_sync costs ~60 SM-cycles per warp instruction (ADU pipe), eight ballots ~25,
+  // a shared-memory atomicOr + load ~7.
+  unsigned short rank[RS_ITEMS];
+  {
+    const u32 lt = lanemask_lt();
+#if RS_MATCH_MODE == 2
+    const u32 lane_bit = 1u << lane;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+      uint2* e = &my_tab[(u32)(key[j] >> SHIFT) & 255u];
+      atomicOr(&e->x, lane_bit);
+      __syncwarp();
+      const uint2 v = *e; // .x = group, .y = first free rank
+      __syncwarp();
+      const u32 lower = __popc(v.x & lt);
+      if ((v.x >> lane) <= 1u) // highest lane of the group: reserve the ranks, clear the group
+        *e = make_uint2(0u, v.y + lower + 1u);
+      __syncwarp();
+      rank[j] = (unsigned short)(v.y + lower);
+    }
+#else
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+      const u32 d = (u32)(key[j] >> SHIFT) & 255u;
+#if RS_MATCH_MODE == 1
+      u32 peers = 0xffffffffu;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const u32 vote = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? vote : ~vote;
+      }
+#else
+      const u32 peers = __match_any_sync(0xffffffffu, d);
+#endif
+      const u32 lower = __popc(peers & lt);
+      const u32 base = my_tab[d].y;
+      __syncwarp();
+      if ((peers >> lane) <= 1u)
+        my_tab[d].y = base + lower + 1u;
+      __syncwarp();
+      rank[j] = (unsigned short)(base + lower);
+    }
+#endif
+  }
+  __syncthreads(); // ranks are final: the histograms may be overwritten
+
+  // ---- 3a. keys through shared memory --------------------------------------------------------------
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j)
+    s_keys[rank[j]] = key[j];
+
+  // ids are loaded only now: their latency overlaps the look-back below
+  u32 val[RS_ITEMS];
 #pragma unroll
   for (int j = 0; j < RS_ITEMS; ++j) {
-    const u32 d = (u32)(key[j] >> shift) & 255u;
-    rank[j] += s_excl[d] + my_hist[d];
-    s_keys[rank[j]] = key[j];
-    s_vals[rank[j]] = val[j];
+    const u32 p = warp_base + j * 32;
+    if (FIRST)
+      val[j] = tile_base + p;
+    else
+      val[j] = (full || p < valid) ? vals_in[tile_base + p] : 0u;
   }
-  __syncthreads();
+
+  // ---- 4. look-back for digit `tid` ---------------------------------------------------------------
+  {
+    const u32 d = tid;
+    u32 prev = 0;
+    if (tile != 0) {
+      u32* my_status = status + (size_t)tile * RS_RADIX + d;
+      const u32* look = my_status - RS_RADIX;
+      while (true) {
+        u32 s;
+        do {
+          s = ld_relaxed_u32(look);
+        } while ((s >> 30) == 0);
+        prev += s & RS_VAL_MASK;
+        if ((s >> 30) == 2)
+          break;
+        look -= RS_RADIX;
+      }
+      st_relaxed_u32(my_status, RS_FLAG_PFX | ((prev + my_count) & RS_VAL_MASK));
+    }
+    s_gofs[d] = digit_base[d] + prev - my_excl;
+  }
+
+  // ---- 3b. ids through shared memory ----------------------------------------------------------------
 #pragma unroll
-  for (int k = 0; k < RS_ITEMS; ++k) {
-    const u32 p = tid + k * RS_THREADS;
-    if (p < valid) {
+  for (int j = 0; j < RS_ITEMS; ++j)
+    s_vals[rank[j]] = val[j];
+  __syncthreads();
+
+  if (full) {
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+      const u32 p = tid + k * RS_THREADS;
       const u64 kk = s_keys[p];
-      const u32 d = (u32)(kk >> shift) & 255u;
-      const u32 dst = s_gofs[d] + p;
+      const u32 dst = s_gofs[(u32)(kk >> SHIFT) & 255u] + p;
       keys_out[dst] = kk;
       vals_out[dst] = s_vals[p];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+      const u32 p = tid + k * RS_THREADS;
+      if (p < valid) {
+        const u64 kk = s_keys[p];
+        const u32 dst = s_gofs[(u32)(kk >> SHIFT) & 255u] + p;
+        keys_out[dst] = kk;
+        vals_out[dst] = s_vals[p];
+      }
     }
   }
 }
 
-#define RS_SMEM_BYTES (RS_TILE * 12 + (RS_WARPS * RS_RADIX + 2 * RS_RADIX + RS_WARPS) * 4)
+#define RS_SMEM_BYTES (RS_TILE * 12 + (RS_RADIX + RS_WARPS) * 4)
 
 size_t
 sort_status_words(u64 n)
@@ -355,18 +448,27 @@ sort_status_words(u64 n)
   return (tiles ? tiles : 1) * RS_RADIX;
 }
 
+template<int PASS>
+static void
+launch_onesweep_pass(const u64* kin, const u32* vin, u64* kout, u32* vout, u32 n, const u32* digit_base, u32* status,
+                     u32* ticket, u32 tiles, cudaStream_t stream)
+{
+  auto kernel = onesweep_pass_kernel<PASS, PASS == 0>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_set = true;
+  }
+  kernel<<<tiles, RS_THREADS, RS_SMEM_BYTES, stream>>>(kin, vin, kout, vout, n, digit_base, status, ticket);
+}
+
 void
 launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hist, u32* status, u32* ticket,
                   cudaStream_t stream)
 {
   if (n == 0)
     return;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(onesweep_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES);
-    cudaFuncSetAttribute(onesweep_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES);
-    attr_set = true;
-  }
   const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
   digit_base_kernel<<<1, 256, 0, stream>>>(hist);
   cudaMemsetAsync(ticket, 0, 8 * sizeof(u32), stream);
@@ -375,16 +477,23 @@ launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hi
   u32* vin = vals0;
   u32* vout = vals1;
   for (int pass = 0; pass < 8; ++pass) {
+    // two status arrays alternate so that the memset of pass p+1 is independent of pass p's kernel
     cudaMemsetAsync(status, 0, (size_t)tiles * RS_RADIX * sizeof(u32), stream);
-    if (pass == 0)
-      onesweep_pass_kernel<true><<<tiles, RS_THREADS, RS_SMEM_BYTES, stream>>>(
-        kin, vin, kout, vout, (u32)n, 8 * pass, hist + pass * 256, status, ticket + pass);
-    else
-      onesweep_pass_kernel<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, stream>>>(
-        kin, vin, kout, vout, (u32)n, 8 * pass, hist + pass * 256, status, ticket + pass);
-    u64* tk = kin;
+    const u32* base = hist + pass * 256;
+    u32* tk = ticket + pass;
+    switch (pass) {
+      case 0: launch_onesweep_pass<0>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+      case 1: launch_onesweep_pass<1>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+      case 2: launch_onesweep_pass<2>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+      case 3: launch_onesweep_pass<3>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+      case 4: launch_onesweep_pass<4>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+      case 5: launch_onesweep_pass<5>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+      case 6: launch_onesweep_pass<6>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+      default: launch_onesweep_pass<7>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+    }
+    u64* tk2 = kin;
     kin = kout;
-    kout = tk;
+    kout = tk2;
     u32* tv = vin;
     vin = vout;
     vout = tv;

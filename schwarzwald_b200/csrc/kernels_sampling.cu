@@ -30,6 +30,15 @@ sweep_tiles(u64 count)
   return t ? t : 1;
 }
 
+// Points of node `rank` for the take-all decision (Sampling.h:201-208).  Single GPU: the length of
+// the node's run.  Sharded: nodes above the shard prefix depth span GPUs, gcount holds the
+// all-reduced count.
+__device__ __forceinline__ u32
+node_point_count(const u32* __restrict__ node_start, const u32* __restrict__ gcount, u32 rank)
+{
+  return gcount ? gcount[rank] : node_start[rank + 1] - node_start[rank];
+}
+
 // position of item j of this lane inside the tile (warp-striped)
 __device__ __forceinline__ u32
 item_pos(u32 warp, u32 lane, int j)
@@ -189,7 +198,7 @@ level_compact_kernel(SwLevelArgs a, u64* __restrict__ n_selected, u64* __restric
       if (i < a.count) {
         bool take = a.force_all != 0;
         if (!take && a.allow_take_all) {
-          const u32 cnt = a.node_start[node_rank[j] + 1] - a.node_start[node_rank[j]];
+          const u32 cnt = node_point_count(a.node_start, a.node_gcount, node_rank[j]);
           take = (u64)cnt <= a.max_points_per_node;
         }
         if (take)
@@ -451,7 +460,7 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
       if (i < a.count) {
         bool active = true;
         if (a.allow_take_all) {
-          const u32 cnt = a.node_start[node_rank + 1] - a.node_start[node_rank];
+          const u32 cnt = node_point_count(a.node_start, a.node_gcount, node_rank);
           active = (u64)cnt > a.max_points_per_node;
         }
         if (active) {
@@ -757,7 +766,7 @@ md_setup_kernel(SwMinDistArgs a, int cell_shift, const u32* __restrict__ cell_ti
     if (i < a.count) {
       bool active = true;
       if (a.allow_take_all) {
-        const u32 cnt = a.node_start[node_rank + 1] - a.node_start[node_rank];
+        const u32 cnt = node_point_count(a.node_start, a.node_gcount, node_rank);
         active = (u64)cnt > a.max_points_per_node;
       }
       cell_of[i] = cell_rank;

@@ -1,0 +1,315 @@
+// kernels_shard.cu — device side of the multi-GPU path: every GPU ends up owning
+// whole Morton-prefix subtrees.
+//
+// The reference is a single process (no collective exists in it); its unit of independent work is
+// the octree node (do_tiling_for_node, tiling/TilingAlgorithms.cpp:499-561, one task per start node
+// at :1314-1351).  Sharding by the leading `shard_levels` octree levels of the Morton key keeps
+// that unit intact:
+//
+//   prefix_histogram      counts of the 8^6 level-5 prefixes of UNSORTED keys.  Summed over the
+//                         ranks it yields (a) FAST's start level exactly as
+//                         estimate_start_node_level_in_octree computes it (:1473-1535) and (b) the
+//                         splitters: contiguous prefix ranges of equal point count
+//   partition_by_splitter stable multi-way partition of (position, global id) by destination rank
+//                         = the send buffer of the all-to-all.  Stability + rank-ordered receive
+//                         keeps points in global-id order on the receiver, so the receiver's stable
+//                         sort reproduces the single-GPU tie rule (key, original index)
+//   node_count exchange   nodes above the shard prefix depth span GPUs; their take-all decision
+//                         (Sampling.h:201-208) needs the global point count: dense per-prefix
+//                         counters are filled here, summed by the caller's collective, read back
+#include "swgpu_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// level-5 prefix histogram of unsorted keys
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prefix_histogram_kernel(const u64* __restrict__ keys, u64 n, u32* __restrict__ bins)
+{
+  const u32 lane = threadIdx.x & 31;
+  for (u64 base = ((u64)blockIdx.x * 256 + (threadIdx.x & ~31u)); base < n; base += (u64)gridDim.x * 256) {
+    const u64 i = base + lane;
+    const bool ok = i < n;
+    const u32 b = ok ? (u32)((keys[i] & SW_KEY_MASK) >> 45) : 0xFFFFFFFFu;
+    // neighbouring input points often share a prefix (scan lines): aggregate equal bins per warp
+    const u32 peers = __match_any_sync(0xffffffffu, b);
+    if (ok && (peers & lanemask_lt()) == 0)
+      atomicAdd(&bins[b], (u32)__popc(peers));
+  }
+}
+
+void
+launch_prefix_histogram(const u64* keys, u64 n, u32* bins, cudaStream_t stream)
+{
+  if (n == 0)
+    return;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  u64 want = (n + 255) / 256;
+  const u64 cap = (u64)sms * 8;
+  prefix_histogram_kernel<<<(u32)(want < cap ? want : cap), 256, 0, stream>>>(keys, n, bins);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stable multi-way partition by destination rank
+// ---------------------------------------------------------------------------------------------
+#define PT_THREADS 256
+#define PT_WARPS 8
+#define PT_ITEMS 8
+#define PT_TILE (PT_THREADS * PT_ITEMS)
+
+struct SwSplitters
+{
+  u32 first_prefix[SW_MAX_RANKS]; // rank r owns level-5 prefixes [first_prefix[r], first_prefix[r+1])
+  u32 n_ranks;
+};
+
+__device__ __forceinline__ u32
+dest_of(u64 key, const SwSplitters& sp)
+{
+  const u32 prefix = (u32)((key & SW_KEY_MASK) >> 45);
+  u32 d = 0;
+#pragma unroll
+  for (u32 r = 1; r < SW_MAX_RANKS; ++r)
+    d += (r < sp.n_ranks && prefix >= sp.first_prefix[r]) ? 1u : 0u;
+  return d;
+}
+
+// tile_counts[tile * SW_MAX_RANKS + d] = points of the tile that go to rank d
+__global__ void __launch_bounds__(PT_THREADS)
+partition_count_kernel(const u64* __restrict__ keys, u64 n, SwSplitters sp, u32* __restrict__ tile_counts)
+{
+  __shared__ u32 s_cnt[SW_MAX_RANKS];
+  if (threadIdx.x < SW_MAX_RANKS)
+    s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const u64 base = (u64)blockIdx.x * PT_TILE;
+  u32 local[SW_MAX_RANKS];
+#pragma unroll
+  for (u32 r = 0; r < SW_MAX_RANKS; ++r)
+    local[r] = 0;
+#pragma unroll
+  for (int j = 0; j < PT_ITEMS; ++j) {
+    const u64 i = base + j * PT_THREADS + threadIdx.x;
+    if (i < n) {
+      const u32 d = dest_of(keys[i], sp);
+#pragma unroll
+      for (u32 r = 0; r < SW_MAX_RANKS; ++r)
+        local[r] += (d == r) ? 1u : 0u;
+    }
+  }
+#pragma unroll
+  for (u32 r = 0; r < SW_MAX_RANKS; ++r) {
+    u32 v = local[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v)
+      atomicAdd(&s_cnt[r], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < SW_MAX_RANKS)
+    tile_counts[(u64)blockIdx.x * SW_MAX_RANKS + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// One block per destination: exclusive scan of its column over the tiles (in place), total to
+// send_counts[d].
+__global__ void __launch_bounds__(1024)
+partition_scan_kernel(u32* __restrict__ tile_counts, u32 n_tiles, u64* __restrict__ send_counts)
+{
+  __shared__ u32 s_warp[32];
+  __shared__ u32 s_carry;
+  const u32 d = blockIdx.x;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0)
+    s_carry = 0;
+  __syncthreads();
+  for (u32 t0 = 0; t0 < n_tiles; t0 += 1024) {
+    const u32 t = t0 + threadIdx.x;
+    const u32 v = (t < n_tiles) ? tile_counts[(u64)t * SW_MAX_RANKS + d] : 0u;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (u32)o)
+        incl += up;
+    }
+    if (lane == 31)
+      s_warp[warp] = incl;
+    __syncthreads();
+    u32 wofs = 0;
+    for (u32 w = 0; w < warp; ++w)
+      wofs += s_warp[w];
+    const u32 carry = s_carry;
+    if (t < n_tiles)
+      tile_counts[(u64)t * SW_MAX_RANKS + d] = carry + wofs + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023)
+      s_carry = carry + wofs + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    send_counts[d] = s_carry;
+}
+
+// Scatter: out position = dest_base[d] + tile offset + rank inside the tile (tile order = index
+// order, so the partition is stable).
+__global__ void __launch_bounds__(PT_THREADS)
+partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict__ xyz, u64 n, SwSplitters sp,
+                         const u32* __restrict__ tile_offsets, const u64* __restrict__ send_counts, u32 id_base,
+                         double* __restrict__ out_xyz, u32* __restrict__ out_id)
+{
+  __shared__ u32 s_wcnt[PT_WARPS][SW_MAX_RANKS];
+  __shared__ u64 s_base[SW_MAX_RANKS];
+  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u64 base = (u64)blockIdx.x * PT_TILE;
+  const u32 lt = lanemask_lt();
+  // warp-striped: item j of a warp covers 32 consecutive points; a warp owns PT_ITEMS * 32 of them
+  u32 dest[PT_ITEMS];
+  u32 cnt[SW_MAX_RANKS];
+#pragma unroll
+  for (u32 r = 0; r < SW_MAX_RANKS; ++r)
+    cnt[r] = 0;
+#pragma unroll
+  for (int j = 0; j < PT_ITEMS; ++j) {
+    const u64 i = base + warp * (32 * PT_ITEMS) + j * 32 + lane;
+    dest[j] = (i < n) ? dest_of(keys[i], sp) : 0xFFu;
+#pragma unroll
+    for (u32 r = 0; r < SW_MAX_RANKS; ++r)
+      cnt[r] += __popc(__ballot_sync(0xffffffffu, dest[j] == r));
+  }
+  if (lane < SW_MAX_RANKS) {
+    u32 mine = 0;
+#pragma unroll
+    for (u32 r = 0; r < SW_MAX_RANKS; ++r)
+      mine = (lane == r) ? cnt[r] : mine;
+    s_wcnt[warp][lane] = mine;
+  }
+  if (threadIdx.x < SW_MAX_RANKS) {
+    u64 b = 0;
+    for (u32 r = 0; r < threadIdx.x; ++r)
+      b += send_counts[r];
+    s_base[threadIdx.x] = b + tile_offsets[(u64)blockIdx.x * SW_MAX_RANKS + threadIdx.x];
+  }
+  __syncthreads();
+  u32 run[SW_MAX_RANKS]; // rank of the next point of this warp per destination, inside the tile
+#pragma unroll
+  for (u32 r = 0; r < SW_MAX_RANKS; ++r) {
+    u32 o = 0;
+    for (u32 w = 0; w < warp; ++w)
+      o += s_wcnt[w][r];
+    run[r] = o;
+  }
+#pragma unroll
+  for (int j = 0; j < PT_ITEMS; ++j) {
+    const u64 i = base + warp * (32 * PT_ITEMS) + j * 32 + lane;
+    u64 pos = 0;
+#pragma unroll
+    for (u32 r = 0; r < SW_MAX_RANKS; ++r) {
+      const u32 m = __ballot_sync(0xffffffffu, dest[j] == r);
+      if (dest[j] == r)
+        pos = s_base[r] + run[r] + __popc(m & lt);
+      run[r] += __popc(m);
+    }
+    if (i < n) {
+      const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+      out_xyz[3 * pos] = x;
+      out_xyz[3 * pos + 1] = y;
+      out_xyz[3 * pos + 2] = z;
+      out_id[pos] = id_base + (u32)i;
+    }
+  }
+}
+
+size_t
+partition_tiles(u64 n)
+{
+  const size_t t = (size_t)((n + PT_TILE - 1) / PT_TILE);
+  return t ? t : 1;
+}
+
+void
+launch_partition_by_splitters(const u64* keys, const double* xyz, u64 n, const u32* first_prefix, u32 n_ranks,
+                              u32 id_base, u32* tile_counts, u64* send_counts, double* out_xyz, u32* out_id,
+                              cudaStream_t stream)
+{
+  SwSplitters sp{};
+  sp.n_ranks = n_ranks;
+  for (u32 r = 0; r < SW_MAX_RANKS; ++r)
+    sp.first_prefix[r] = r < n_ranks ? first_prefix[r] : 0xFFFFFFFFu;
+  const u32 tiles = (u32)partition_tiles(n);
+  if (n == 0) {
+    cudaMemsetAsync(send_counts, 0, SW_MAX_RANKS * sizeof(u64), stream);
+    return;
+  }
+  partition_count_kernel<<<tiles, PT_THREADS, 0, stream>>>(keys, n, sp, tile_counts);
+  partition_scan_kernel<<<SW_MAX_RANKS, 1024, 0, stream>>>(tile_counts, tiles, send_counts);
+  partition_scatter_kernel<<<tiles, PT_THREADS, 0, stream>>>(keys, xyz, n, sp, tile_counts, send_counts, id_base, out_xyz,
+                                                            out_id);
+}
+
+// ---------------------------------------------------------------------------------------------
+// global node counts for nodes that span shards
+// ---------------------------------------------------------------------------------------------
+// dense[prefix of node r] = local point count of node r   (dense has 8^levels entries, zeroed)
+__global__ void __launch_bounds__(256)
+node_counts_to_dense_kernel(const u64* __restrict__ keys, const u32* __restrict__ node_start, u32 n_nodes,
+                            int node_shift, u32* __restrict__ dense)
+{
+  const u32 r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= n_nodes)
+    return;
+  const u32 b = node_start[r];
+  // saturate: the sum over <= 16 ranks must not wrap; exact for thresholds below 2^28
+  const u32 c = node_start[r + 1] - b;
+  dense[(keys[b] & SW_KEY_MASK) >> node_shift] = c < 0x0FFFFFFFu ? c : 0x0FFFFFFFu;
+}
+
+// gcount[r] = dense[prefix of node r]   (after the caller summed `dense` over the ranks)
+__global__ void __launch_bounds__(256)
+node_counts_from_dense_kernel(const u64* __restrict__ keys, const u32* __restrict__ node_start, u32 n_nodes,
+                              int node_shift, const u32* __restrict__ dense, u32* __restrict__ gcount)
+{
+  const u32 r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= n_nodes)
+    return;
+  gcount[r] = dense[(keys[node_start[r]] & SW_KEY_MASK) >> node_shift];
+}
+
+void
+launch_node_counts_to_dense(const u64* keys, const u32* node_start, u32 n_nodes, int node_shift, u32* dense,
+                            cudaStream_t stream)
+{
+  if (n_nodes)
+    node_counts_to_dense_kernel<<<(n_nodes + 255) / 256, 256, 0, stream>>>(keys, node_start, n_nodes, node_shift, dense);
+}
+
+void
+launch_node_counts_from_dense(const u64* keys, const u32* node_start, u32 n_nodes, int node_shift, const u32* dense,
+                              u32* gcount, cudaStream_t stream)
+{
+  if (n_nodes)
+    node_counts_from_dense_kernel<<<(n_nodes + 255) / 256, 256, 0, stream>>>(keys, node_start, n_nodes, node_shift, dense,
+                                                                          gcount);
+}
+
+// out[i] = map[perm[idx[i]]]: sorted position -> received point -> global point id
+__global__ void __launch_bounds__(256)
+compose_ids_mapped_kernel(const u32* __restrict__ perm, const u32* __restrict__ idx, const u32* __restrict__ map, u64 n,
+                          u32* __restrict__ out)
+{
+  for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256)
+    out[i] = map[perm[idx[i]]];
+}
+
+void
+launch_compose_ids_mapped(const u32* perm, const u32* idx, const u32* map, u64 n, u32* out, cudaStream_t stream)
+{
+  if (n == 0)
+    return;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const u64 want = (n + 255) / 256, cap = (u64)sms * 8;
+  compose_ids_mapped_kernel<<<(u32)(want < cap ? want : cap), 256, 0, stream>>>(perm, idx, map, n, out);
+}

@@ -61,6 +61,7 @@ struct SwLevelArgs
   // node table produced by the run-length encoder
   const u32* node_start; // n_nodes + 1 entries (sentinel = count)
   const u32* tile_rank0; // per tile: number of node heads before the tile
+  const u32* node_gcount; // optional: global (all-shard) point count per node rank, nullptr = local run length
   // optional per-element selection flags (argmin / min-distance strategies)
   const unsigned char* sel;
   // outputs
@@ -101,6 +102,7 @@ struct SwArgminArgs
   // take-all nodes are skipped (they are never sampled: Sampling.h:328-335, 612-619)
   const u32* node_start;
   const u32* tile_rank0;
+  const u32* node_gcount; // see SwLevelArgs
   int allow_take_all;
   u64 max_points_per_node;
 };
@@ -126,6 +128,7 @@ struct SwMinDistArgs
   double threshold; // (double)(float)(spacing_f * spacing_f), SparseGrid.cpp:11-14
   const u32* node_start;
   const u32* tile_rank0;
+  const u32* node_gcount; // see SwLevelArgs
   int allow_take_all;
   u64 max_points_per_node;
 };
@@ -144,3 +147,24 @@ struct SwMinDistScratch
 cudaError_t run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stream, u32* rounds,
                              u32* launches, u64* bytes);
 void free_min_distance_scratch(SwMinDistScratch& sc);
+
+// ---- multi-GPU support (kernels_shard.cu) ---------------------------------------------------------
+#define SW_MAX_RANKS 16
+#define SW_PREFIX_BINS 262144 /* 8^6 level-5 prefixes = key >> 45 */
+
+// bins[key >> 45] += 1 for unsorted keys (bins are accumulated, not zeroed)
+void launch_prefix_histogram(const u64* keys, u64 n, u32* bins, cudaStream_t stream);
+// Stable multi-way partition of (xyz, id_base + i) by destination rank; rank r owns the level-5
+// prefixes [first_prefix[r], first_prefix[r+1]).  tile_counts: partition_tiles(n) * SW_MAX_RANKS
+// u32 scratch; send_counts: SW_MAX_RANKS u64 (device).
+size_t partition_tiles(u64 n);
+void launch_partition_by_splitters(const u64* keys, const double* xyz, u64 n, const u32* first_prefix, u32 n_ranks,
+                                   u32 id_base, u32* tile_counts, u64* send_counts, double* out_xyz, u32* out_id,
+                                   cudaStream_t stream);
+// node counts of one sweep level <-> dense per-prefix counters (8^levels entries)
+void launch_node_counts_to_dense(const u64* keys, const u32* node_start, u32 n_nodes, int node_shift, u32* dense,
+                                 cudaStream_t stream);
+void launch_node_counts_from_dense(const u64* keys, const u32* node_start, u32 n_nodes, int node_shift,
+                                   const u32* dense, u32* gcount, cudaStream_t stream);
+// out[i] = map[perm[idx[i]]]
+void launch_compose_ids_mapped(const u32* perm, const u32* idx, const u32* map, u64 n, u32* out, cudaStream_t stream);

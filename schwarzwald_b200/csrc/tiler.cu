@@ -129,6 +129,15 @@ struct swgpu_tiler
   HostScalars* h_scalars = nullptr; // pinned
   std::vector<Chunk> chunks;
 
+  // multi-GPU: this handle tiles one shard (whole Morton-prefix subtrees)
+  u32 shard_levels = 0;             // nodes with fewer levels may span GPUs
+  int32_t start_level_override = -1; // FAST: the global start level
+  swgpu_allreduce_u32_fn allreduce = nullptr;
+  void* allreduce_ctx = nullptr;
+  const u32* global_ids = nullptr; // device: received point -> global point id
+  DevBuf dense_counts, node_gcount;
+  DevBuf part_tile_counts, part_send_counts;
+
   // stats
   swgpu_stats stats{};
   bool timing = false;
@@ -281,6 +290,34 @@ record(swgpu_tiler* h, int i)
     cudaEventRecord(h->ev[i], h->stream);
 }
 
+bool
+spans_shards(const swgpu_tiler* h, int levels)
+{
+  return h->allreduce && (u32)levels < h->shard_levels;
+}
+
+// Sums the per-node point counts of one sweep level over all shards.  Every rank calls this once
+// per level below the shard prefix depth, with n_nodes == 0 when it has nothing left there.
+int
+exchange_node_counts(swgpu_tiler* h, const u64* in_key, u32 n_nodes, int levels)
+{
+  const size_t dense_n = (size_t)1 << (3 * levels);
+  cudaStream_t s = h->stream;
+  CK(h->dense_counts.ensure(dense_n * 4));
+  CK(h->node_gcount.ensure((size_t)std::max<u32>(n_nodes, 1) * 4));
+  CK(cudaMemsetAsync(h->dense_counts.p, 0, dense_n * 4, s));
+  launch_node_counts_to_dense(in_key, h->node_start.as<u32>(), n_nodes, shift_for_levels(levels),
+                              h->dense_counts.as<u32>(), s);
+  CK(cudaGetLastError());
+  const int rc = h->allreduce(h->allreduce_ctx, h->dense_counts.as<u32>(), dense_n, s);
+  if (rc)
+    return fail(h, SW_ERR_COLLECTIVE, "the caller's all-reduce hook failed");
+  launch_node_counts_from_dense(in_key, h->node_start.as<u32>(), n_nodes, shift_for_levels(levels),
+                                h->dense_counts.as<u32>(), h->node_gcount.as<u32>(), s);
+  h->stats.kernel_launches += 2;
+  return SW_OK;
+}
+
 // One sampling level over the list [in_key, in_idx) of `count` points whose nodes have `levels`
 // levels (reference node level = levels - 1).  Appends the selected points to the output arrays
 // and, if rem_key != nullptr, writes the remainder list.
@@ -312,6 +349,15 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
   CK(h->node_index.ensure((h->node_count + n_nodes) * 8, s, h->node_count * 8));
   CK(h->node_first.ensure((h->node_count + n_nodes + 1) * 8, s, h->node_count * 8));
 
+  // nodes above the shard prefix depth span GPUs: take-all needs their global point count
+  const u32* node_gcount = nullptr;
+  if (allow_take_all && !force_all && spans_shards(h, levels)) {
+    rc = exchange_node_counts(h, in_key, n_nodes, levels);
+    if (rc)
+      return rc;
+    node_gcount = h->node_gcount.as<u32>();
+  }
+
   SwLevelArgs a{};
   a.in_key = in_key;
   a.in_idx = in_idx;
@@ -324,6 +370,7 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
   a.max_points_per_node = h->prm.max_points_per_node;
   a.node_start = h->node_start.as<u32>();
   a.tile_rank0 = h->tile_rank0.as<u32>();
+  a.node_gcount = node_gcount;
   a.sel = nullptr;
 
   if (!force_all) {
@@ -364,6 +411,7 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
         g.error_flag = h->d_error();
         g.node_start = h->node_start.as<u32>();
         g.tile_rank0 = h->tile_rank0.as<u32>();
+        g.node_gcount = node_gcount;
         g.allow_take_all = allow_take_all ? 1 : 0;
         g.max_points_per_node = h->prm.max_points_per_node;
         launch_select_argmin(g, h->scan_status.as<u64>(), h->d_tickets(), s);
@@ -397,6 +445,7 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
         }
         m.node_start = h->node_start.as<u32>();
         m.tile_rank0 = h->tile_rank0.as<u32>();
+        m.node_gcount = node_gcount;
         m.allow_take_all = allow_take_all ? 1 : 0;
         m.max_points_per_node = h->prm.max_points_per_node;
         h->md.status = h->scan_status.as<u64>();
@@ -456,23 +505,19 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
   return SW_OK;
 }
 
-// estimate_start_node_level_in_octree, TilingAlgorithms.cpp:1473-1535, from the level-5 bins
+// estimate_start_node_level_in_octree, TilingAlgorithms.cpp:1473-1535.  `count_of(b, group)` returns
+// the number of points in the level-5 prefixes [b, b + group).
+template<typename CountOf>
 int
-estimate_start_level(swgpu_tiler* h, int* S_out)
+start_level_from_prefix_counts(CountOf count_of, size_t concurrency)
 {
-  launch_level5_bins(h->keys[0].as<u64>(), h->n, h->bins.as<u32>(), h->stream);
-  h->stats.kernel_launches += 1;
-  std::vector<u32> bins(262145);
-  CK(cudaMemcpyAsync(bins.data(), h->bins.p, 262145 * 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  const size_t concurrency = h->prm.concurrency;
   const u32 MIN_LEVEL = 3, MAX_LEVEL = 6;
   for (u32 level = 0; level < MAX_LEVEL; ++level) {
     // ranges at `level` = prefixes of (level + 1) levels = groups of 8^(5 - level) bins
     const u32 group = 1u << (3 * (5 - level));
     size_t ranges = 0, large = 0;
     for (u32 b = 0; b < 262144u; b += group) {
-      const u32 cnt = bins[b + group] - bins[b];
+      const u64 cnt = count_of(b, group);
       if (cnt > 0) {
         ++ranges;
         if (cnt >= 100000u)
@@ -482,12 +527,23 @@ estimate_start_level(swgpu_tiler* h, int* S_out)
     float score = 0.f;
     if (!(ranges <= concurrency / 2))
       score = static_cast<float>(large) / static_cast<float>(concurrency);
-    if (score >= 1.f) {
-      *S_out = (int)std::max(level + 1, MIN_LEVEL);
-      return SW_OK;
-    }
+    if (score >= 1.f)
+      return (int)std::max(level + 1, MIN_LEVEL);
   }
-  *S_out = (int)MAX_LEVEL;
+  return (int)MAX_LEVEL;
+}
+
+// single GPU: bin boundaries by binary search in the sorted keys
+int
+estimate_start_level(swgpu_tiler* h, int* S_out)
+{
+  launch_level5_bins(h->keys[0].as<u64>(), h->n, h->bins.as<u32>(), h->stream);
+  h->stats.kernel_launches += 1;
+  std::vector<u32> bins(262145);
+  CK(cudaMemcpyAsync(bins.data(), h->bins.p, 262145 * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *S_out = start_level_from_prefix_counts([&](u32 b, u32 group) -> u64 { return bins[b + group] - bins[b]; },
+                                          h->prm.concurrency);
   return SW_OK;
 }
 
@@ -507,16 +563,17 @@ run_batch(swgpu_tiler* h)
 
   if (n >= (1ull << 30))
     return fail(h, SW_ERR_INVALID_ARGUMENT, "a batch is limited to 2^30 - 1 points per GPU");
-  if (h->prm.tiling == SW_FAST && n < h->prm.concurrency)
+  const bool sharded = h->shard_levels > 0; // the caller checked the GLOBAL point count
+  if (!sharded && h->prm.tiling == SW_FAST && n < h->prm.concurrency)
     return fail(h, SW_ERR_TOO_FEW_POINTS, "Can't scatter a range that has less than 'scatter_factor' elements!");
-  if (n == 0)
+  if (!sharded && n == 0)
     return fail(h, SW_ERR_EMPTY_NODE, "tile_internal_node: Got zero points to tile @ node r");
   int rc = ensure_batch_buffers(h, n);
   if (rc)
     return rc;
 
   record(h, 0);
-  // K1
+  // K1 (every launcher is a no-op for an empty shard)
   CK(cudaMemsetAsync(h->hist.p, 0, 8 * 256 * 4, s));
   CK(cudaMemsetAsync(h->scalars.p, 0, 128, s));
   launch_morton_encode(h->d_xyz, n, h->bounds, h->keys[0].as<u64>(), h->hist.as<u32>(), h->d_n_clamped(), s);
@@ -541,9 +598,13 @@ run_batch(swgpu_tiler* h)
   int first_levels = 0; // ACCURATE: root has 0 levels
   if (h->prm.tiling == SW_FAST) {
     int S = 0;
-    rc = estimate_start_level(h, &S);
-    if (rc)
-      return rc;
+    if (sharded && h->start_level_override >= 0) {
+      S = h->start_level_override; // estimated by the caller from the all-reduced prefix histogram
+    } else {
+      rc = estimate_start_level(h, &S);
+      if (rc)
+        return rc;
+    }
     h->start_level = S;
     first_levels = S;
   }
@@ -555,7 +616,7 @@ run_batch(swgpu_tiler* h)
   u64* rem_key[2] = { h->keys[1].as<u64>(), h->wkey2.as<u64>() };
   u32* rem_idx[2] = { h->vals[1].as<u32>(), h->widx2.as<u32>() };
   int flip = 0;
-  for (int levels = first_levels; count > 0; ++levels) {
+  for (int levels = first_levels; count > 0 || spans_shards(h, levels); ++levels) {
     const int node_level = levels - 1;
     const LevelKind kind = level_kind(h, node_level);
     if (kind == KIND_REROOT || levels > 21)
@@ -563,6 +624,14 @@ run_batch(swgpu_tiler* h)
     const bool terminal = (kind == KIND_TERMINAL);
     if (!terminal && levels >= 21)
       return fail(h, SW_ERR_DEEP_REROOT, "child level exceeds MortonIndex64 capacity");
+    if (count == 0) { // nothing left on this GPU, but the other shards still need our (zero) counts
+      if (!terminal) {
+        rc = exchange_node_counts(h, in_key, 0, levels);
+        if (rc)
+          return rc;
+      }
+      continue;
+    }
     u64 n_sel = 0;
     rc = sweep_level(h, in_key, in_idx, count, levels, /*allow_take_all=*/true, terminal, rem_key[flip],
                      rem_idx[flip], 0u, &n_sel, false, 0);
@@ -589,6 +658,10 @@ run_finalize(swgpu_tiler* h)
   if (h->prm.tiling != SW_FAST || h->finalized)
     return SW_OK;
   const int S = h->start_level;
+  if (h->chunks.empty()) { // empty shard
+    h->finalized = true;
+    return SW_OK;
+  }
   // input of the first reconstruct level: the chunk of the start nodes themselves
   size_t src = 0; // chunks[0] has levels == S
   for (int lv = S - 1; lv >= 0; --lv) {
@@ -672,7 +745,8 @@ swgpu_destroy(swgpu_handle h)
   DevBuf* bufs[] = { &h->xyz_own,    &h->keys[0],   &h->keys[1],       &h->vals[0],     &h->vals[1],  &h->wkey2,
                      &h->widx2,      &h->hist,      &h->sort_status,   &h->scalars,     &h->pos_sorted, &h->out_key,
                      &h->out_idx,    &h->node_start, &h->tile_rank0,   &h->sel,         &h->scan_status, &h->node_index,
-                     &h->node_first, &h->bins,      &h->ids_tmp };
+                     &h->node_first, &h->bins,      &h->ids_tmp,     &h->dense_counts, &h->node_gcount,
+                     &h->part_tile_counts, &h->part_send_counts };
   for (DevBuf* b : bufs)
     b->release();
   free_min_distance_scratch(h->md);
@@ -760,6 +834,17 @@ swgpu_result_size(swgpu_handle h, uint64_t* n_nodes, uint64_t* n_point_ids)
   return SW_OK;
 }
 
+// node-major ids: sorted position -> original index (-> global id when this handle tiles a shard)
+static void
+compose_output_ids(swgpu_tiler* h, u32* out_device)
+{
+  if (h->global_ids)
+    launch_compose_ids_mapped(h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->global_ids, h->out_count, out_device,
+                              h->stream);
+  else
+    launch_compose_ids(h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, out_device, h->stream);
+}
+
 static int
 fill_node_table(swgpu_tiler* h, sw_node* nodes)
 {
@@ -792,7 +877,7 @@ swgpu_get_nodes_device_ids(swgpu_handle h, sw_node* nodes, uint32_t* point_ids_d
     return fail(h, SW_ERR_STATE, "no batch has been indexed");
   cudaSetDevice(h->device);
   if (point_ids_device && h->out_count) {
-    launch_compose_ids(h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, point_ids_device, h->stream);
+    compose_output_ids(h, point_ids_device);
     CK(cudaGetLastError());
   }
   return fill_node_table(h, nodes);
@@ -808,7 +893,7 @@ swgpu_get_nodes(swgpu_handle h, sw_node* nodes, uint32_t* point_ids)
   cudaSetDevice(h->device);
   if (point_ids && h->out_count) {
     CK(h->ids_tmp.ensure(h->out_count * 4));
-    launch_compose_ids(h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, h->ids_tmp.as<u32>(), h->stream);
+    compose_output_ids(h, h->ids_tmp.as<u32>());
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(point_ids, h->ids_tmp.p, h->out_count * 4, cudaMemcpyDeviceToHost, h->stream));
   }
@@ -912,6 +997,130 @@ swgpu_sort_keys_device(swgpu_handle h, uint64_t* keys_device, uint64_t n, uint32
                     h->sort_status.as<u32>(), h->d_tickets() + 8, h->stream);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
+  return SW_OK;
+}
+
+int
+swgpu_prefix_histogram_device(swgpu_handle h, const uint64_t* keys_device, uint64_t n, uint32_t* bins_device)
+{
+  if (!h || !bins_device || (n && !keys_device))
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  launch_prefix_histogram(reinterpret_cast<const u64*>(keys_device), n, bins_device, h->stream);
+  CK(cudaGetLastError());
+  return SW_OK;
+}
+
+int
+swgpu_estimate_start_level(const uint32_t* bins_host, uint32_t concurrency, int32_t* level)
+{
+  if (!bins_host || !level)
+    return SW_ERR_INVALID_ARGUMENT;
+  std::vector<u64> prefix(262145, 0);
+  for (u32 b = 0; b < 262144u; ++b)
+    prefix[b + 1] = prefix[b] + bins_host[b];
+  *level = start_level_from_prefix_counts([&](u32 b, u32 group) -> u64 { return prefix[b + group] - prefix[b]; },
+                                          concurrency ? concurrency : 1u);
+  return SW_OK;
+}
+
+int
+swgpu_choose_splitters(const uint32_t* bins_host, uint32_t n_ranks, uint32_t shard_levels, uint32_t* first_prefix)
+{
+  if (!bins_host || !first_prefix || n_ranks == 0 || n_ranks > SWGPU_MAX_RANKS || shard_levels == 0 || shard_levels > 6)
+    return SW_ERR_INVALID_ARGUMENT;
+  const u32 group = 1u << (3 * (6 - shard_levels)); // level-5 prefixes per shard-level subtree
+  const u32 n_groups = 262144u / group;
+  std::vector<u64> cum(n_groups + 1, 0);
+  for (u32 g = 0; g < n_groups; ++g) {
+    u64 c = 0;
+    for (u32 b = 0; b < group; ++b)
+      c += bins_host[g * group + b];
+    cum[g + 1] = cum[g] + c;
+  }
+  const u64 total = cum[n_groups];
+  first_prefix[0] = 0;
+  u32 g = 0;
+  for (u32 r = 1; r < n_ranks; ++r) {
+    // boundary whose cumulative count is closest to r/n_ranks of the points, never moving backwards
+    const double target = (double)total * r / n_ranks;
+    while (g < n_groups && (double)cum[g + 1] <= target)
+      ++g;
+    u32 pick = g;
+    if (g < n_groups && (double)cum[g + 1] - target < target - (double)cum[g])
+      pick = g + 1;
+    if (pick * group < first_prefix[r - 1])
+      pick = first_prefix[r - 1] / group;
+    first_prefix[r] = pick * group;
+  }
+  first_prefix[n_ranks] = 262144u;
+  return SW_OK;
+}
+
+int
+swgpu_max_shard_levels(swgpu_handle h, uint32_t* shard_levels)
+{
+  if (!h || !shard_levels)
+    return SW_ERR_INVALID_ARGUMENT;
+  int depth = 6;
+  switch (h->prm.sampling) {
+    case SW_RANDOM_GRID:
+    case SW_GRID_CENTER:
+      // root node cells are prefixes of cand(-1) + 1 levels; deeper nodes use deeper cells
+      depth = std::min(6, cand_level_sampler(h, -1) + 1);
+      break;
+    case SW_JITTERED: { // root grid: log2(cells) levels (Sampling.h:621-660)
+      const double perfect = root_extent_x(h) / (double)h->prm.spacing_at_root;
+      const uint32_t cells = prev_pow2_u32(static_cast<uint32_t>(perfect));
+      depth = std::min(6, cells ? (int)std::log2(cells) : 0);
+      break;
+    }
+    default: // MIN_DISTANCE: no cell structure; nodes above the shard depth are sampled per shard
+      depth = 6;
+      break;
+  }
+  *shard_levels = (uint32_t)std::max(depth, 0);
+  return SW_OK;
+}
+
+int
+swgpu_partition_device(swgpu_handle h, const uint64_t* keys_device, const double* xyz_device, uint64_t n,
+                       const uint32_t* first_prefix, uint32_t n_ranks, uint32_t id_base, double* out_xyz_device,
+                       uint32_t* out_id_device, uint64_t* send_counts_host)
+{
+  if (!h || !first_prefix || !send_counts_host || n_ranks == 0 || n_ranks > SWGPU_MAX_RANKS ||
+      (n && (!keys_device || !xyz_device || !out_xyz_device || !out_id_device)))
+    return SW_ERR_INVALID_ARGUMENT;
+  if (n >= (1ull << 32))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "a partition is limited to 2^32 - 1 points per GPU");
+  cudaSetDevice(h->device);
+  CK(h->part_tile_counts.ensure(partition_tiles(n) * SW_MAX_RANKS * 4));
+  CK(h->part_send_counts.ensure(SW_MAX_RANKS * 8));
+  launch_partition_by_splitters(reinterpret_cast<const u64*>(keys_device), xyz_device, n, first_prefix, n_ranks, id_base,
+                                h->part_tile_counts.as<u32>(), h->part_send_counts.as<u64>(), out_xyz_device,
+                                out_id_device, h->stream);
+  CK(cudaGetLastError());
+  u64 counts[SW_MAX_RANKS];
+  CK(cudaMemcpyAsync(counts, h->part_send_counts.p, SW_MAX_RANKS * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (u32 r = 0; r < n_ranks; ++r)
+    send_counts_host[r] = counts[r];
+  return SW_OK;
+}
+
+int
+swgpu_set_shard(swgpu_handle h, uint32_t shard_levels, int32_t start_level, swgpu_allreduce_u32_fn allreduce,
+                void* allreduce_ctx, const uint32_t* global_ids_device)
+{
+  if (!h || shard_levels > 6)
+    return SW_ERR_INVALID_ARGUMENT;
+  if (shard_levels && h->prm.max_points_per_node >= (1ull << 28))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "sharded tiling needs max_points_per_node < 2^28");
+  h->shard_levels = shard_levels;
+  h->start_level_override = shard_levels ? start_level : -1;
+  h->allreduce = shard_levels ? allreduce : nullptr;
+  h->allreduce_ctx = allreduce_ctx;
+  h->global_ids = shard_levels ? reinterpret_cast<const u32*>(global_ids_device) : nullptr;
   return SW_OK;
 }
 

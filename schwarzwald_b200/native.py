@@ -71,7 +71,8 @@ SYMBOLS = [
 
 
 def library_path() -> str:
-    return os.path.join(HERE, "libswgpu.so")
+    # SWGPU_LIB selects an alternative build of the SAME library (kernel tuning experiments)
+    return os.environ.get("SWGPU_LIB") or os.path.join(HERE, "libswgpu.so")
 
 
 def load_library():
