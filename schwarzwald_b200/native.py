@@ -46,6 +46,11 @@ class SwgpuStats(C.Structure):
     ]
 
 
+# swgpu_allreduce_u32_fn: int (*)(void* ctx, uint32_t* device_counters, uint64_t count, void* cuda_stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
+MAX_RANKS = 16
+PREFIX_BINS = 262144
+
 # every symbol include/swgpu.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("swgpu_create", C.c_int, [C.POINTER(SwParams), C.c_int, C.POINTER(C.c_void_p)]),
@@ -65,6 +70,13 @@ SYMBOLS = [
     ("swgpu_gather_attribute_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     ("swgpu_morton_encode_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     ("swgpu_sort_keys_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    ("swgpu_prefix_histogram_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    ("swgpu_estimate_start_level", C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]),
+    ("swgpu_choose_splitters", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    ("swgpu_max_shard_levels", C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    ("swgpu_partition_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
+                                         C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("swgpu_set_shard", C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, ALLREDUCE_FN, C.c_void_p, C.c_void_p]),
     ("swgpu_enable_timing", C.c_int, [C.c_void_p, C.c_int]),
     ("swgpu_get_stats", C.c_int, [C.c_void_p, C.POINTER(SwgpuStats)]),
 ]
