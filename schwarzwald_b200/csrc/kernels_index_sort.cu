@@ -179,6 +179,7 @@ launch_key_histogram(const u64* keys, u64 n, u32* hist, cudaStream_t stream)
 #ifndef RS_MATCH_MODE
 #define RS_MATCH_MODE 2 /* 0 = __match_any_sync, 1 = eight ballots, 2 = shared-memory atomicOr */
 #endif
+#define RS_LOOK 8 /* look-back descriptors fetched per round trip */
 #ifndef RS_MIN_CTAS
 #define RS_MIN_CTAS 4 /* CTAs per SM the register allocation is capped for */
 #endif
@@ -394,16 +395,27 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
     u32 prev = 0;
     if (tile != 0) {
       u32* my_status = status + (size_t)tile * RS_RADIX + d;
-      const u32* look = my_status - RS_RADIX;
-      while (true) {
-        u32 s;
-        do {
-          s = ld_relaxed_u32(look);
-        } while ((s >> 30) == 0);
-        prev += s & RS_VAL_MASK;
-        if ((s >> 30) == 2)
-          break;
-        look -= RS_RADIX;
+      // RS_LOOK predecessors are fetched per round trip (their descriptors were published before
+      // their ranking started, so they are almost always present): ~9 dependent L2 latencies
+      // become ~2
+      int t = (int)tile - 1;
+      bool done = false;
+      while (!done) {
+        u32 sv[RS_LOOK];
+#pragma unroll
+        for (int k = 0; k < RS_LOOK; ++k)
+          sv[k] = (t - k >= 0) ? ld_relaxed_u32(status + (size_t)(t - k) * RS_RADIX + d) : RS_FLAG_PFX;
+#pragma unroll
+        for (int k = 0; k < RS_LOOK; ++k) {
+          if (!done) {
+            u32 v = sv[k];
+            while ((v >> 30) == 0)
+              v = ld_relaxed_u32(status + (size_t)(t - k) * RS_RADIX + d);
+            prev += v & RS_VAL_MASK;
+            done = (v >> 30) == 2;
+          }
+        }
+        t -= RS_LOOK;
       }
       st_relaxed_u32(my_status, RS_FLAG_PFX | ((prev + my_count) & RS_VAL_MASK));
     }

@@ -185,6 +185,7 @@ level_compact_kernel(SwLevelArgs a, u64* __restrict__ n_selected, u64* __restric
   // ---- phase 2: node rank -> take-all decision -> selection flags ------------------------------
   u32 node_rank[SWP_ITEMS];
   u32 smask[SWP_ITEMS];
+  u32 take_bits = 0; // per item: this lane's element belongs to a take-all node
   u32 wsel = 0;
   {
     u32 run = a.tile_rank0[tile] + hexcl; // heads before this item
@@ -201,6 +202,7 @@ level_compact_kernel(SwLevelArgs a, u64* __restrict__ n_selected, u64* __restric
           const u32 cnt = node_point_count(a.node_start, a.node_gcount, node_rank[j]);
           take = (u64)cnt <= a.max_points_per_node;
         }
+        take_bits |= (take && !a.force_all ? 1u : 0u) << j;
         if (take)
           sel = true;
         else if (a.sampling == SW_RANDOM_GRID)
@@ -241,7 +243,8 @@ level_compact_kernel(SwLevelArgs a, u64* __restrict__ n_selected, u64* __restric
       }
       if ((nmask[j] >> lane) & 1u) {
         a.node_index[a.node_base + node_rank[j]] = key[j] >> a.node_shift;
-        a.node_first[a.node_base + node_rank[j]] = a.out_offset + srank;
+        // bit 63 = SW_NODE_TAKE_ALL (decoded by the host when it builds the node table)
+        a.node_first[a.node_base + node_rank[j]] = (a.out_offset + srank) | ((u64)((take_bits >> j) & 1u) << 63);
       }
     }
     run += __popc(smask[j]);

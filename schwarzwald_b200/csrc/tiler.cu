@@ -859,9 +859,10 @@ fill_node_table(swgpu_tiler* h, sw_node* nodes)
       sw_node& nd = nodes[c.node_base + k];
       nd.index = index[c.node_base + k];
       nd.levels = (uint32_t)c.levels;
-      nd.flags = c.flags;
-      nd.first = first[c.node_base + k];
-      const u64 end = (k + 1 < c.n_nodes) ? first[c.node_base + k + 1] : (c.out_offset + c.count);
+      const u64 fmask = ~(1ull << 63); // bit 63 of node_first = take-all marker of the compaction kernel
+      nd.flags = c.flags | ((first[c.node_base + k] >> 63) ? SW_NODE_TAKE_ALL : 0u);
+      nd.first = first[c.node_base + k] & fmask;
+      const u64 end = (k + 1 < c.n_nodes) ? (first[c.node_base + k + 1] & fmask) : (c.out_offset + c.count);
       nd.count = end - nd.first;
     }
   }

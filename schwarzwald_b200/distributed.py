@@ -1,0 +1,356 @@
+"""Multi-GPU tiling: one process (or thread) per GPU, every GPU owns whole Morton-prefix subtrees.
+
+The reference is a single process; its unit of independent work is the octree node — one taskflow
+task per start node (tiling/TilingAlgorithms.cpp:1314-1351) and per >= 100 000-point child
+(:499-561).  Sharding the points by the leading octree levels of their Morton key keeps that unit
+intact, so every GPU runs the unchanged single-GPU pipeline on its subtrees:
+
+  1. local Morton keys                         swgpu_morton_encode_device  (index_point, clamps in place)
+  2. level-5 prefix histogram, summed          swgpu_prefix_histogram_device + all-reduce (1 MiB)
+  3. global FAST start level + splitters       swgpu_estimate_start_level / swgpu_choose_splitters
+  4. stable partition by destination           swgpu_partition_device
+  5. all-to-all of (xyz 24 B, id 4 B)          NCCL over NVLink (torch.distributed.all_to_all_single)
+  6. single-GPU pipeline on the received points; nodes above the shard depth get their take-all
+     decision from all-reduced counts (the hook passed to swgpu_set_shard)
+
+Results: every rank reports its nodes with GLOBAL point ids.  Nodes with fewer than `shard_levels`
+levels span ranks; their parts concatenated in rank order (= Morton order) are the node
+(`merge_results`).  RANDOM_GRID / GRID_CENTER / JITTERED are bit-identical to a single-GPU run:
+a sampling cell never spans shards (swgpu_max_shard_levels).  MIN_DISTANCE is exact for every node
+that lies inside one shard; nodes above the shard depth are sampled per shard (relaxed across the
+shard faces) — see DESIGN.md.
+
+The communicator is an object with: rank, world, all_reduce_sum(tensor) in place,
+all_to_all_rows(send, send_counts) -> (recv, recv_counts).  `TorchDistComm` wraps
+torch.distributed (NCCL on GPUs, gloo in the CPU tests), `ThreadComm` runs several virtual ranks
+as threads on ONE GPU (parity tests on a single-GPU box).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import native
+from .tiler import GpuTiler, TileResult, NODE_DTYPE, SwgpuError
+
+PREFIX_BINS = native.PREFIX_BINS
+
+
+# --------------------------------------------------------------------------------------------------
+# communicators
+# --------------------------------------------------------------------------------------------------
+class TorchDistComm:
+    """torch.distributed process group: NCCL all-reduce / all-to-all over NVLink on GPUs."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def all_reduce_sum(self, t):
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+
+    def all_to_all_rows(self, send, send_counts):
+        """send: tensor whose rows are ordered by destination; returns (recv, recv_counts)."""
+        import torch
+        sc = torch.tensor(list(send_counts), dtype=torch.int64, device=send.device)
+        rc = torch.empty_like(sc)
+        self._dist.all_to_all_single(rc, sc, group=self.group)
+        recv_counts = [int(x) for x in rc.cpu().tolist()]
+        recv = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        self._dist.all_to_all_single(recv, send, output_split_sizes=recv_counts,
+                                     input_split_sizes=[int(x) for x in send_counts], group=self.group)
+        return recv, recv_counts
+
+
+class ThreadComm:
+    """Virtual ranks = threads of one process sharing one device (or the CPU).  Test plumbing."""
+
+    class _Shared:
+        def __init__(self, world):
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.slots = [None] * world
+
+    def __init__(self, shared, rank):
+        self.shared, self.rank, self.world = shared, rank, shared.world
+
+    @classmethod
+    def create(cls, world):
+        shared = cls._Shared(world)
+        return [cls(shared, r) for r in range(world)]
+
+    def _sync(self, t):
+        if t.is_cuda:
+            import torch
+            torch.cuda.synchronize(t.device)
+
+    def all_reduce_sum(self, t):
+        sh = self.shared
+        self._sync(t)
+        sh.slots[self.rank] = t
+        sh.barrier.wait()
+        total = sh.slots[0].clone()
+        for r in range(1, self.world):
+            total += sh.slots[r]
+        self._sync(t)
+        sh.barrier.wait()  # everybody has read every input
+        t.copy_(total)
+        self._sync(t)
+        sh.barrier.wait()
+
+    def all_to_all_rows(self, send, send_counts):
+        import torch
+        sh = self.shared
+        self._sync(send)
+        sh.slots[self.rank] = (send, list(int(x) for x in send_counts))
+        sh.barrier.wait()
+        parts, recv_counts = [], []
+        for r in range(self.world):
+            buf, counts = sh.slots[r]
+            off = sum(counts[:self.rank])
+            parts.append(buf[off:off + counts[self.rank]])
+            recv_counts.append(counts[self.rank])
+        recv = torch.cat(parts, dim=0) if parts else send[:0].clone()
+        self._sync(recv)
+        sh.barrier.wait()
+        return recv, recv_counts
+
+
+# --------------------------------------------------------------------------------------------------
+# host-side pieces (pure functions over the library's host entry points; CPU-testable)
+# --------------------------------------------------------------------------------------------------
+def estimate_start_level(global_bins, concurrency):
+    """estimate_start_node_level_in_octree (TilingAlgorithms.cpp:1473-1535) on global prefix counts."""
+    lib = native.load_library()
+    bins = np.ascontiguousarray(global_bins, dtype=np.uint32)
+    assert bins.size == PREFIX_BINS
+    out = C.c_int32()
+    rc = lib.swgpu_estimate_start_level(C.c_void_p(bins.ctypes.data), int(concurrency), C.byref(out))
+    if rc:
+        raise SwgpuError(rc, "swgpu_estimate_start_level")
+    return out.value
+
+
+def choose_splitters(global_bins, n_ranks, shard_levels):
+    """first_prefix[r]..first_prefix[r+1] = level-5 prefixes owned by rank r."""
+    lib = native.load_library()
+    bins = np.ascontiguousarray(global_bins, dtype=np.uint32)
+    assert bins.size == PREFIX_BINS
+    out = np.zeros(n_ranks + 1, np.uint32)
+    rc = lib.swgpu_choose_splitters(C.c_void_p(bins.ctypes.data), int(n_ranks), int(shard_levels),
+                                    C.c_void_p(out.ctypes.data))
+    if rc:
+        raise SwgpuError(rc, "swgpu_choose_splitters")
+    return out
+
+
+def merge_results(parts):
+    """Concatenates the per-rank results (rank order) into one TileResult: nodes that span ranks
+    are joined, ids in rank order = Morton order."""
+    order = {}
+    for r, res in enumerate(parts):
+        for row in res.nodes:
+            key = (int(row["levels"]), int(row["index"]))
+            order.setdefault(key, []).append((r, int(row["first"]), int(row["count"]), int(row["flags"])))
+    nodes = np.zeros(len(order), NODE_DTYPE)
+    chunks, first = [], 0
+    for i, key in enumerate(sorted(order)):
+        cnt, flags = 0, 0
+        for r, f, c, fl in order[key]:
+            chunks.append(parts[r].ids[f:f + c])
+            cnt += c
+            flags |= fl
+        nodes[i] = (key[1], key[0], flags, first, cnt)
+        first += cnt
+    ids = np.concatenate(chunks) if chunks else np.zeros(0, np.uint32)
+    start = max((p.start_level for p in parts), default=-1)
+    return TileResult(nodes, ids, start)
+
+
+# --------------------------------------------------------------------------------------------------
+# the sharded tiler
+# --------------------------------------------------------------------------------------------------
+class ShardedTiler:
+    """TilingAlgorithmBase-shaped front end for one rank of a multi-GPU run.
+
+    build_execution_graph(xyz) takes this rank's slice of the batch as a CUDA tensor (n_local, 3)
+    float64; global point ids are id_base + local index (id_base defaults to the exclusive prefix
+    of the per-rank point counts)."""
+
+    def __init__(self, sampling, tiling, bounds_min, bounds_max, spacing_at_root, max_points_per_node=20000,
+                 max_depth=100, concurrency=8, device=0, comm=None, shard_levels=None):
+        import torch
+        self._torch = torch
+        self.comm = comm if comm is not None else TorchDistComm()
+        self.device = torch.device("cuda", device)
+        self.tiler = GpuTiler(sampling, tiling, bounds_min, bounds_max, spacing_at_root,
+                              max_points_per_node=max_points_per_node, max_depth=max_depth, concurrency=concurrency,
+                              device=device)
+        self.sampling, self.tiling, self.concurrency = sampling, tiling, int(concurrency)
+        lib = self.tiler._lib
+        m = C.c_uint32()
+        self.tiler._check(lib.swgpu_max_shard_levels(self.tiler._h, C.byref(m)))
+        self.max_shard_levels = int(m.value)
+        self.shard_levels = min(int(shard_levels), self.max_shard_levels) if shard_levels else self.max_shard_levels
+        if self.shard_levels < 1:
+            raise ValueError("spacing too coarse to shard: a sampling cell would span GPUs")
+        # device scratch owned here (torch tensors): histogram, node-count exchange buffer
+        self._bins = torch.zeros(PREFIX_BINS, dtype=torch.int32, device=self.device)
+        self._hook = native.ALLREDUCE_FN(self._allreduce_hook)  # keep the callback object alive
+        self._keep = {}
+        self.last = {}
+
+    # -- plumbing -----------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_handle):
+        self.tiler.set_stream(cuda_stream_handle)
+
+    def enable_timing(self, on=True):
+        self.tiler.enable_timing(on)
+
+    def close(self):
+        self.tiler.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _allreduce_hook(self, ctx, ptr, count, stream):
+        """swgpu_allreduce_u32_fn: sums `count` u32 device counters over the ranks, in place."""
+        try:
+            torch = self._torch
+            view = _DeviceArray(ptr, int(count))
+            t = torch.as_tensor(view, device=self.device)
+            self.comm.all_reduce_sum(t)
+            return 0
+        except Exception:  # never let an exception cross the C boundary
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    # -- the two calls of TilingAlgorithmBase --------------------------------------------------------
+    def build_execution_graph(self, xyz, id_base=None):
+        torch = self._torch
+        t, lib, comm = self.tiler, self.tiler._lib, self.comm
+        n = xyz.numel() // 3
+        assert xyz.is_cuda and xyz.dtype == torch.float64 and xyz.is_contiguous()
+        # 1. keys of the local slice (clamps outliers in place, like index_point)
+        keys = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        t.morton_encode_device(xyz.data_ptr(), n, keys.data_ptr())
+        # 2. global level-5 prefix histogram (+ point counts per rank for the id bases)
+        self._bins.zero_()
+        t._check(lib.swgpu_prefix_histogram_device(t._h, C.c_void_p(keys.data_ptr()), n,
+                                                   C.c_void_p(self._bins.data_ptr())))
+        comm.all_reduce_sum(self._bins)
+        counts = torch.zeros(comm.world, dtype=torch.int64, device=self.device)
+        counts[comm.rank] = n
+        comm.all_reduce_sum(counts)
+        counts = counts.cpu().numpy()
+        n_global = int(counts.sum())
+        if id_base is None:
+            id_base = int(counts[:comm.rank].sum())
+        if n_global >= 2 ** 32:
+            raise ValueError("global point ids are 32 bit: at most 2^32 - 1 points per batch")
+        bins = self._bins.cpu().numpy().view(np.uint32)
+        # reference behaviour on degenerate batches (TilingAlgorithms.cpp:253-259, Parallel.h:181-186)
+        if n_global == 0:
+            raise SwgpuError(7, "tile_internal_node: Got zero points to tile @ node r")
+        if self.tiling == "FAST" and n_global < self.concurrency:
+            raise SwgpuError(9, "Can't scatter a range that has less than 'scatter_factor' elements!")
+        # 3. start level (FAST) and splitters
+        start_level = estimate_start_level(bins, self.concurrency) if self.tiling == "FAST" else -1
+        first_prefix = choose_splitters(bins, comm.world, self.shard_levels)
+        # 4. stable partition into the send buffer
+        send_xyz = torch.empty((max(n, 1), 3), dtype=torch.float64, device=self.device)
+        send_ids = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        send_counts = np.zeros(comm.world, np.uint64)
+        t._check(lib.swgpu_partition_device(t._h, C.c_void_p(keys.data_ptr()), C.c_void_p(xyz.data_ptr()), n,
+                                            C.c_void_p(first_prefix.ctypes.data), comm.world, int(id_base),
+                                            C.c_void_p(send_xyz.data_ptr()), C.c_void_p(send_ids.data_ptr()),
+                                            C.c_void_p(send_counts.ctypes.data)))
+        del keys
+        # 5. the exchange: every GPU receives whole subtrees, sources in rank order
+        sc = [int(x) for x in send_counts]
+        recv_xyz, recv_counts = comm.all_to_all_rows(send_xyz[:n], sc)
+        recv_ids, _ = comm.all_to_all_rows(send_ids[:n], sc)
+        del send_xyz, send_ids
+        m = int(recv_xyz.shape[0])
+        # 6. the single-GPU pipeline on the shard
+        t._check(lib.swgpu_set_shard(t._h, self.shard_levels, int(start_level), self._hook, None,
+                                     C.c_void_p(recv_ids.data_ptr() if m else 0)))
+        self._keep = {"xyz": recv_xyz, "ids": recv_ids}
+        t._check(lib.swgpu_index_batch_device(t._h, C.c_void_p(recv_xyz.data_ptr() if m else 0), m))
+        self.last = {"n_local": n, "n_shard": m, "n_global": n_global, "start_level": start_level,
+                     "first_prefix": first_prefix, "send_counts": sc, "recv_counts": recv_counts,
+                     "bytes_sent_off_gpu": int(sum(c for r, c in enumerate(sc) if r != comm.rank)) * 28}
+        return n
+
+    def finalize(self):
+        self.tiler.finalize()
+
+    # -- results ------------------------------------------------------------------------------------
+    def result(self, **kw):
+        """This rank's nodes with global point ids (spanning nodes: this rank's part)."""
+        return self.tiler.result(**kw)
+
+    def result_size(self):
+        return self.tiler.result_size()
+
+    def stats(self):
+        return self.tiler.stats()
+
+    def start_level(self):
+        return self.tiler.start_level()
+
+    def shard_positions(self):
+        """The received (shard-resident) positions and their global ids."""
+        return self._keep.get("xyz"), self._keep.get("ids")
+
+
+class _DeviceArray:
+    """__cuda_array_interface__ view of `count` int32 at a raw device pointer (no copy)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def tile_with_virtual_ranks(world, xyz_parts, sampling, tiling, bounds_min, bounds_max, spacing_at_root, device=0,
+                            **kw):
+    """Runs `world` virtual ranks as threads on one GPU (ThreadComm) and returns the per-rank
+    TileResults plus the per-rank bookkeeping.  Used by the single-GPU parity tests."""
+    import torch
+    comms = ThreadComm.create(world)
+    results, infos, errors = [None] * world, [None] * world, [None] * world
+
+    def work(r):
+        try:
+            torch.cuda.set_device(device)
+            with ShardedTiler(sampling, tiling, bounds_min, bounds_max, spacing_at_root, device=device,
+                              comm=comms[r], **kw) as st:
+                st.build_execution_graph(xyz_parts[r])
+                st.finalize()
+                results[r] = st.result()
+                infos[r] = dict(st.last)
+        except BaseException as e:  # noqa: BLE001 - reported to the caller
+            errors[r] = e
+            comms[r].shared.barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for e in errors:
+        if e is not None and not isinstance(e, threading.BrokenBarrierError):
+            raise e
+    for e in errors:
+        if e is not None:
+            raise e
+    return results, infos

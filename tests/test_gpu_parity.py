@@ -58,7 +58,7 @@ def assert_same(want, clamped, got, host, keys, order):
     wt, wi = want.canonical()
     gt, gi = got.canonical()
     assert np.array_equal(wt[:, :3], gt[:, :3]), "node table (levels, index, count) differs"
-    assert np.array_equal(wt[:, 3] & 6, gt[:, 3] & 6), "node flags (terminal / reconstructed) differ"
+    assert np.array_equal(wt[:, 3] & 7, gt[:, 3] & 7), "node flags (take-all / terminal / reconstructed) differ"
     assert np.array_equal(wi, gi), "node contents differ"
 
 
