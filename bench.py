@@ -242,6 +242,13 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
+    phase_ms = None
+    if world > 1:  # one extra, untimed step with per-phase events (index / exchange / tile)
+        tiler.profile = True
+        step()
+        phase_ms = {k: round(v, 3) for k, v in tiler.last["phase_ms"].items()}
+        phase_ms["bytes_sent_off_gpu"] = tiler.last["bytes_sent_off_gpu"]
+        tiler.profile = False
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -303,6 +310,7 @@ def main():
                                     "frac": total_bytes / (ms_per_step * 1e-3) / 1e9 / peak}},
         "stage_ms": {k: stats[k] for k in ("ms_index", "ms_sort", "ms_gather", "ms_sample", "ms_total")},
         "gpu_launches": int(launches),
+        "shuffle_phase_ms": phase_ms,
         "clocks": clocks,
     }
     if e2e is not None:

@@ -25,16 +25,10 @@
 __global__ void __launch_bounds__(256)
 prefix_histogram_kernel(const u64* __restrict__ keys, u64 n, u32* __restrict__ bins)
 {
-  const u32 lane = threadIdx.x & 31;
-  for (u64 base = ((u64)blockIdx.x * 256 + (threadIdx.x & ~31u)); base < n; base += (u64)gridDim.x * 256) {
-    const u64 i = base + lane;
-    const bool ok = i < n;
-    const u32 b = ok ? (u32)((keys[i] & SW_KEY_MASK) >> 45) : 0xFFFFFFFFu;
-    // neighbouring input points often share a prefix (scan lines): aggregate equal bins per warp
-    const u32 peers = __match_any_sync(0xffffffffu, b);
-    if (ok && (peers & lanemask_lt()) == 0)
-      atomicAdd(&bins[b], (u32)__popc(peers));
-  }
+  // one L2 reduction per key (no return value); __match_any_sync pre-aggregation costs more than it
+  // saves on B200 (~60 SM-cycles per warp instruction)
+  for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256)
+    atomicAdd(&bins[(u32)((keys[i] & SW_KEY_MASK) >> 45)], 1u);
 }
 
 void
@@ -176,7 +170,8 @@ partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict_
     dest[j] = (i < n) ? dest_of(keys[i], sp) : 0xFFu;
 #pragma unroll
     for (u32 r = 0; r < SW_MAX_RANKS; ++r)
-      cnt[r] += __popc(__ballot_sync(0xffffffffu, dest[j] == r));
+      if (r < sp.n_ranks) // warp-uniform: a ballot costs ~2.6 SM-cycles, skip the unused ranks
+        cnt[r] += __popc(__ballot_sync(0xffffffffu, dest[j] == r));
   }
   if (lane < SW_MAX_RANKS) {
     u32 mine = 0;
@@ -206,10 +201,12 @@ partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict_
     u64 pos = 0;
 #pragma unroll
     for (u32 r = 0; r < SW_MAX_RANKS; ++r) {
-      const u32 m = __ballot_sync(0xffffffffu, dest[j] == r);
-      if (dest[j] == r)
-        pos = s_base[r] + run[r] + __popc(m & lt);
-      run[r] += __popc(m);
+      if (r < sp.n_ranks) {
+        const u32 m = __ballot_sync(0xffffffffu, dest[j] == r);
+        if (dest[j] == r)
+          pos = s_base[r] + run[r] + __popc(m & lt);
+        run[r] += __popc(m);
+      }
     }
     if (i < n) {
       const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];

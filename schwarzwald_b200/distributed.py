@@ -54,13 +54,23 @@ class TorchDistComm:
     def all_reduce_sum(self, t):
         self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
 
-    def all_to_all_rows(self, send, send_counts):
-        """send: tensor whose rows are ordered by destination; returns (recv, recv_counts)."""
+    def all_gather(self, t):
+        """returns a (world, *t.shape) tensor holding every rank's `t`."""
         import torch
-        sc = torch.tensor(list(send_counts), dtype=torch.int64, device=send.device)
-        rc = torch.empty_like(sc)
-        self._dist.all_to_all_single(rc, sc, group=self.group)
-        recv_counts = [int(x) for x in rc.cpu().tolist()]
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self._dist.all_gather_into_tensor(out, t, group=self.group)
+        return out
+
+    def all_to_all_rows(self, send, send_counts, recv_counts=None):
+        """send: tensor whose rows are ordered by destination; returns (recv, recv_counts).
+        recv_counts, when the caller already knows them, saves the count exchange and its sync."""
+        import torch
+        if recv_counts is None:
+            sc = torch.tensor(list(send_counts), dtype=torch.int64, device=send.device)
+            rc = torch.empty_like(sc)
+            self._dist.all_to_all_single(rc, sc, group=self.group)
+            recv_counts = [int(x) for x in rc.cpu().tolist()]
+        recv_counts = [int(x) for x in recv_counts]
         recv = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
         self._dist.all_to_all_single(recv, send, output_split_sizes=recv_counts,
                                      input_split_sizes=[int(x) for x in send_counts], group=self.group)
@@ -103,7 +113,18 @@ class ThreadComm:
         self._sync(t)
         sh.barrier.wait()
 
-    def all_to_all_rows(self, send, send_counts):
+    def all_gather(self, t):
+        import torch
+        sh = self.shared
+        self._sync(t)
+        sh.slots[self.rank] = t
+        sh.barrier.wait()
+        out = torch.stack([sh.slots[r] for r in range(self.world)], dim=0)
+        self._sync(out)
+        sh.barrier.wait()
+        return out
+
+    def all_to_all_rows(self, send, send_counts, recv_counts=None):
         import torch
         sh = self.shared
         self._sync(send)
@@ -203,7 +224,9 @@ class ShardedTiler:
         self._bins = torch.zeros(PREFIX_BINS, dtype=torch.int32, device=self.device)
         self._hook = native.ALLREDUCE_FN(self._allreduce_hook)  # keep the callback object alive
         self._keep = {}
+        self._views = {}
         self.last = {}
+        self.profile = False  # True: per-phase CUDA-event times in self.last["phase_ms"] (adds a sync)
 
     # -- plumbing -----------------------------------------------------------------------------------
     def set_stream(self, cuda_stream_handle):
@@ -224,9 +247,11 @@ class ShardedTiler:
     def _allreduce_hook(self, ctx, ptr, count, stream):
         """swgpu_allreduce_u32_fn: sums `count` u32 device counters over the ranks, in place."""
         try:
-            torch = self._torch
-            view = _DeviceArray(ptr, int(count))
-            t = torch.as_tensor(view, device=self.device)
+            key = (int(ptr), int(count))
+            t = self._views.get(key)
+            if t is None:  # the library's counter buffer is stable: wrap it once, no copy
+                t = self._torch.as_tensor(_DeviceArray(ptr, int(count)), device=self.device)
+                self._views[key] = t
             self.comm.all_reduce_sum(t)
             return 0
         except Exception:  # never let an exception cross the C boundary
@@ -240,32 +265,48 @@ class ShardedTiler:
         t, lib, comm = self.tiler, self.tiler._lib, self.comm
         n = xyz.numel() // 3
         assert xyz.is_cuda and xyz.dtype == torch.float64 and xyz.is_contiguous()
+        marks = []
+
+        def mark(name):
+            if self.profile:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(torch.cuda.current_stream())
+                marks.append((name, ev))
+
+        mark("start")
         # 1. keys of the local slice (clamps outliers in place, like index_point)
         keys = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
         t.morton_encode_device(xyz.data_ptr(), n, keys.data_ptr())
-        # 2. global level-5 prefix histogram (+ point counts per rank for the id bases)
+        mark("encode")
+        # 2. level-5 prefix histogram of the local slice; ONE all-gather gives every rank all
+        #    histograms: their sum is the global histogram (start level, splitters) and, cut at the
+        #    splitters, the complete send/recv count matrix — no further count exchange or sync
         self._bins.zero_()
         t._check(lib.swgpu_prefix_histogram_device(t._h, C.c_void_p(keys.data_ptr()), n,
                                                    C.c_void_p(self._bins.data_ptr())))
-        comm.all_reduce_sum(self._bins)
-        counts = torch.zeros(comm.world, dtype=torch.int64, device=self.device)
-        counts[comm.rank] = n
-        comm.all_reduce_sum(counts)
-        counts = counts.cpu().numpy()
-        n_global = int(counts.sum())
-        if id_base is None:
-            id_base = int(counts[:comm.rank].sum())
+        all_bins = comm.all_gather(self._bins)  # (world, 8^6) int32, stays on the device
+        bins = all_bins.sum(dim=0, dtype=torch.int32).cpu().numpy().view(np.uint32)  # global histogram
+        mark("histogram+allgather")
+        # 3. start level (FAST) and splitters from the global histogram (host, ~0.3 ms)
+        n_global = int(bins.sum(dtype=np.int64))
         if n_global >= 2 ** 32:
             raise ValueError("global point ids are 32 bit: at most 2^32 - 1 points per batch")
-        bins = self._bins.cpu().numpy().view(np.uint32)
         # reference behaviour on degenerate batches (TilingAlgorithms.cpp:253-259, Parallel.h:181-186)
         if n_global == 0:
             raise SwgpuError(7, "tile_internal_node: Got zero points to tile @ node r")
         if self.tiling == "FAST" and n_global < self.concurrency:
             raise SwgpuError(9, "Can't scatter a range that has less than 'scatter_factor' elements!")
-        # 3. start level (FAST) and splitters
         start_level = estimate_start_level(bins, self.concurrency) if self.tiling == "FAST" else -1
         first_prefix = choose_splitters(bins, comm.world, self.shard_levels)
+        # send/recv count matrix [source, destination]: per-rank histograms cut at the splitters
+        cum = torch.zeros((comm.world, PREFIX_BINS + 1), dtype=torch.int64, device=all_bins.device)
+        torch.cumsum(all_bins, dim=1, dtype=torch.int64, out=cum[:, 1:])
+        cuts = torch.from_numpy(first_prefix.astype(np.int64)).to(all_bins.device)
+        count_matrix = torch.diff(cum[:, cuts], dim=1).cpu().numpy()
+        counts = count_matrix.sum(axis=1)
+        assert int(counts[comm.rank]) == n
+        if id_base is None:
+            id_base = int(counts[:comm.rank].sum())
         # 4. stable partition into the send buffer
         send_xyz = torch.empty((max(n, 1), 3), dtype=torch.float64, device=self.device)
         send_ids = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
@@ -275,18 +316,28 @@ class ShardedTiler:
                                             C.c_void_p(send_xyz.data_ptr()), C.c_void_p(send_ids.data_ptr()),
                                             C.c_void_p(send_counts.ctypes.data)))
         del keys
+        mark("partition")
         # 5. the exchange: every GPU receives whole subtrees, sources in rank order
-        sc = [int(x) for x in send_counts]
-        recv_xyz, recv_counts = comm.all_to_all_rows(send_xyz[:n], sc)
-        recv_ids, _ = comm.all_to_all_rows(send_ids[:n], sc)
+        sc = [int(x) for x in count_matrix[comm.rank]]
+        assert sc == [int(x) for x in send_counts], "partition and histogram disagree"
+        rc = [int(x) for x in count_matrix[:, comm.rank]]
+        recv_xyz, recv_counts = comm.all_to_all_rows(send_xyz[:n], sc, rc)
+        recv_ids, _ = comm.all_to_all_rows(send_ids[:n], sc, rc)
         del send_xyz, send_ids
         m = int(recv_xyz.shape[0])
+        mark("all_to_all")
         # 6. the single-GPU pipeline on the shard
         t._check(lib.swgpu_set_shard(t._h, self.shard_levels, int(start_level), self._hook, None,
                                      C.c_void_p(recv_ids.data_ptr() if m else 0)))
         self._keep = {"xyz": recv_xyz, "ids": recv_ids}
         t._check(lib.swgpu_index_batch_device(t._h, C.c_void_p(recv_xyz.data_ptr() if m else 0), m))
-        self.last = {"n_local": n, "n_shard": m, "n_global": n_global, "start_level": start_level,
+        mark("tile")
+        phases = {}
+        if self.profile:
+            torch.cuda.synchronize(self.device)
+            for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+                phases[name] = e0.elapsed_time(e1)
+        self.last = {"phase_ms": phases, "n_local": n, "n_shard": m, "n_global": n_global, "start_level": start_level,
                      "first_prefix": first_prefix, "send_counts": sc, "recv_counts": recv_counts,
                      "bytes_sent_off_gpu": int(sum(c for r, c in enumerate(sc) if r != comm.rank)) * 28}
         return n
