@@ -1,0 +1,159 @@
+// swgpu_tiler.hpp — header-only C++17 RAII layer over the C ABI (include/swgpu.h).
+//
+// This is the host-side mirror of the reference's tiler interfaces for code that is compiled
+// C++ (the reference itself): strategy names as the CLI spells them
+// (core/tiling/Sampling.h:774-791, core/process/Tiler.cpp:189-198), TilerMetaParameters-shaped
+// construction (core/process/Tiler.h:64-75), build_execution_graph / finalize
+// (core/tiling/TilingAlgorithms.h:70-116), Potree node names (TilingAlgorithms.cpp:139),
+// node bounds by the halving recurrence (core/tiling/OctreeAlgorithms.cpp:3-18) and the reference's
+// error behaviour: every failure is a std::runtime_error carrying the library's message.
+// It depends on nothing but the C ABI; TilingAlgorithmGPU.h (next to this file) plugs it into the
+// reference's TilingAlgorithmBase.
+#pragma once
+
+#include "../../include/swgpu.h"
+
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace swgpu {
+
+struct Error : std::runtime_error
+{
+  Error(int code_, const std::string& what)
+    : std::runtime_error(what)
+    , code(code_)
+  {}
+  int code;
+};
+
+inline sw_sampling
+sampling_from_name(const std::string& name)
+{
+  if (name == "RANDOM_GRID")
+    return SW_RANDOM_GRID;
+  if (name == "GRID_CENTER")
+    return SW_GRID_CENTER;
+  if (name == "MIN_DISTANCE")
+    return SW_MIN_DISTANCE;
+  if (name == "JITTERED")
+    return SW_JITTERED;
+  throw Error(SW_ERR_INVALID_ARGUMENT, "Unrecognized sampling strategy " + name);
+}
+
+inline sw_tiling
+tiling_from_name(const std::string& name)
+{
+  if (name == "ACCURATE")
+    return SW_ACCURATE;
+  if (name == "FAST")
+    return SW_FAST;
+  throw Error(SW_ERR_INVALID_ARGUMENT, "Unrecognized tiling strategy " + name);
+}
+
+// "r" + one octant digit per level, octant = x<<2 | y<<1 | z (TilingAlgorithms.cpp:139)
+inline std::string
+node_name(uint64_t index, uint32_t levels)
+{
+  std::string name = "r";
+  for (uint32_t l = 0; l < levels; ++l)
+    name.push_back(static_cast<char>('0' + ((index >> (3 * (levels - 1 - l))) & 7)));
+  return name;
+}
+
+// get_bounds_from_node_index: iterate get_octant_bounds from the root (OctreeAlgorithms.cpp:3-18,
+// 64-72); the recurrence, not a closed form, so the doubles match the reference bit for bit.
+inline void
+node_bounds(uint64_t index, uint32_t levels, const double root_min[3], const double root_max[3], double out_min[3],
+            double out_max[3])
+{
+  for (int a = 0; a < 3; ++a) {
+    out_min[a] = root_min[a];
+    out_max[a] = root_max[a];
+  }
+  for (uint32_t l = 0; l < levels; ++l) {
+    const uint32_t octant = static_cast<uint32_t>((index >> (3 * (levels - 1 - l))) & 7);
+    const uint32_t bit[3] = { (octant >> 2) & 1u, (octant >> 1) & 1u, octant & 1u };
+    for (int a = 0; a < 3; ++a) {
+      const double half = (out_max[a] - out_min[a]) / 2;
+      if (bit[a])
+        out_min[a] = out_min[a] + half;
+      out_max[a] = out_min[a] + half;
+    }
+  }
+}
+
+class Tiler
+{
+public:
+  Tiler(sw_sampling sampling, sw_tiling tiling, float spacing_at_root, uint32_t max_depth, uint64_t max_points_per_node,
+        const double bounds_min[3], const double bounds_max[3], uint32_t num_indexing_threads, int device = 0)
+  {
+    _params.sampling = sampling;
+    _params.tiling = tiling;
+    _params.spacing_at_root = spacing_at_root;
+    _params.max_depth = max_depth;
+    _params.max_points_per_node = max_points_per_node;
+    for (int a = 0; a < 3; ++a) {
+      _params.bounds_min[a] = bounds_min[a];
+      _params.bounds_max[a] = bounds_max[a];
+    }
+    _params.concurrency = num_indexing_threads;
+    _params.reserved = 0;
+    const int rc = swgpu_create(&_params, device, &_handle);
+    if (rc != SW_OK)
+      throw Error(rc,
+                  rc == SW_ERR_CUDA ? "swgpu_create: no usable CUDA device (there is no CPU fallback)"
+                                    : "swgpu_create: invalid tiler parameters");
+  }
+  ~Tiler() { swgpu_destroy(_handle); }
+  Tiler(const Tiler&) = delete;
+  Tiler& operator=(const Tiler&) = delete;
+
+  // build_execution_graph for one batch: xyz = PointBuffer::positions() (AoS doubles); outliers are
+  // clamped in place exactly as index_point does (OctreeAlgorithms.h:156-170)
+  void index_batch(double* xyz_host, uint64_t n) { check(swgpu_index_batch(_handle, xyz_host, n)); }
+  void finalize() { check(swgpu_finalize(_handle)); }
+
+  struct Result
+  {
+    std::vector<sw_node> nodes;
+    std::vector<uint32_t> point_ids; // node-major, Morton order inside a node
+  };
+
+  Result result()
+  {
+    uint64_t n_nodes = 0, n_ids = 0;
+    check(swgpu_result_size(_handle, &n_nodes, &n_ids));
+    Result r;
+    r.nodes.resize(n_nodes);
+    r.point_ids.resize(n_ids);
+    check(swgpu_get_nodes(_handle, r.nodes.data(), r.point_ids.data()));
+    return r;
+  }
+
+  int32_t start_level()
+  {
+    int32_t s = -1;
+    check(swgpu_get_start_level(_handle, &s));
+    return s;
+  }
+
+  const sw_params& params() const { return _params; }
+  swgpu_handle handle() const { return _handle; }
+
+private:
+  void check(int rc)
+  {
+    if (rc != SW_OK)
+      throw Error(rc, swgpu_last_error(_handle));
+  }
+
+  sw_params _params{};
+  swgpu_handle _handle = nullptr;
+};
+
+} // namespace swgpu
