@@ -18,10 +18,7 @@
 // atomic ticket so that the decoupled look-back chains are dead-lock free.
 #include "swgpu_internal.cuh"
 
-#define SWP_THREADS 256
 #define SWP_WARPS (SWP_THREADS / 32)
-#define SWP_ITEMS 8
-static_assert(SWP_THREADS * SWP_ITEMS == SW_SWEEP_TILE, "tile geometry");
 
 size_t
 sweep_tiles(u64 count)
@@ -142,17 +139,96 @@ launch_node_rle(const u64* keys, u64 count, int node_shift, u32* node_start, u32
 // =============================================================================================
 // K5 + K6 + K8  take-all decision, RANDOM_GRID selection, stable two-way compaction
 // =============================================================================================
-__global__ void __launch_bounds__(SWP_THREADS)
-level_compact_kernel(SwLevelArgs a, u64* __restrict__ n_selected, u64* __restrict__ status, u32* __restrict__ ticket)
+// Two passes without any inter-CTA dependency.  A single-pass compaction needs a decoupled
+// look-back chain; measured on B200 (tools/microbench/scan_chain.cu) the chain costs 3x the
+// streaming time of the same kernel (0.49 ms vs 0.15 ms per 100 M keys, independent of tile size
+// and window width), so reading the keys twice is the cheaper design:
+//
+//   level_count_kernel    [read 8 B/pt]  per element: node rank, take-all decision, selection
+//                         flag; stores the flags as one bit per element, the number of selected
+//                         points per tile and - for the points that stay - the point count of
+//                         every child node (one atomic per run of equal child inside a warp)
+//   level_scan_kernel     (one block) exclusive scan of the per-tile counts; exclusive scan of the
+//                         child counts = node boundaries of the NEXT level, so no pass over the
+//                         points is needed to find them (the reference does 8 linear scans per
+//                         node, partition_points_into_child_octants, OctreeAlgorithms.h:240-265)
+//   level_scatter_kernel  [read 12, write 12 B/pt]  moves selected points to the output chunk and
+//                         the rest to the remainder list, both in order; node table rows
+//
+// Element position inside a tile is warp-striped (item_pos) in all three.
+__device__ __forceinline__ void
+warp_totals_exclusive2(u32 a_total, u32 b_total, u32 warp, u32 lane, u32* s_a, u32* s_b, u32& a_excl, u32& b_excl)
 {
-  __shared__ u32 s_slot;
+  if (lane == 0) {
+    s_a[warp] = a_total;
+    s_b[warp] = b_total;
+  }
+  __syncthreads();
+  u32 ea = 0, eb = 0;
+#pragma unroll
+  for (int w = 0; w < SWP_WARPS; ++w) {
+    ea += (w < (int)warp) ? s_a[w] : 0u;
+    eb += (w < (int)warp) ? s_b[w] : 0u;
+  }
+  a_excl = ea;
+  b_excl = eb;
+}
+
+// tile_rank0[t] = number of node heads before the first element of tile t
+__global__ void __launch_bounds__(256)
+tile_rank0_kernel(const u32* __restrict__ node_start, u32 n_nodes, u32 n_tiles, u32* __restrict__ tile_rank0)
+{
+  const u32 t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= n_tiles)
+    return;
+  const u64 base = (u64)t * SW_SWEEP_TILE;
+  u32 lo = 0, hi = n_nodes; // first node whose start is >= base
+  while (lo < hi) {
+    const u32 mid = (lo + hi) >> 1;
+    if ((u64)node_start[mid] < base)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  tile_rank0[t] = lo;
+}
+
+void
+launch_tile_rank0(const u32* node_start, u32 n_nodes, u64 count, u32* tile_rank0, cudaStream_t stream)
+{
+  const u32 tiles = (u32)sweep_tiles(count);
+  tile_rank0_kernel<<<(tiles + 255) / 256, 256, 0, stream>>>(node_start, n_nodes, tiles, tile_rank0);
+}
+
+// the root node: one node holding every point
+__global__ void
+root_node_kernel(u32* node_start, u32 count)
+{
+  node_start[0] = 0;
+  node_start[1] = count;
+}
+
+void
+launch_root_node(u32* node_start, u64 count, cudaStream_t stream)
+{
+  root_node_kernel<<<1, 1, 0, stream>>>(node_start, (u32)count);
+}
+
+#define CHILD_WINDOW 256
+__global__ void __launch_bounds__(SWP_THREADS)
+level_count_kernel(SwLevelArgs a)
+{
   __shared__ u32 s_w[SWP_WARPS];
-  __shared__ u32 s_w2[SWP_WARPS];
-  __shared__ u64 s_prefix;
+  __shared__ u32 s_sel;
+  __shared__ u32 s_child[CHILD_WINDOW]; // child counters of the first CHILD_WINDOW slots touched by the tile
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const u32 tile = take_ticket(ticket, &s_slot);
+  const u32 tile = blockIdx.x;
   const u64 base = (u64)tile * SW_SWEEP_TILE;
   const u32 lt = lanemask_lt();
+  if (threadIdx.x == 0)
+    s_sel = 0;
+  for (u32 i = threadIdx.x; i < CHILD_WINDOW; i += SWP_THREADS)
+    s_child[i] = 0;
 
   // ---- phase 1: keys, node heads, cell heads ---------------------------------------------------
   u64 key[SWP_ITEMS];
@@ -182,82 +258,239 @@ level_compact_kernel(SwLevelArgs a, u64* __restrict__ n_selected, u64* __restric
   u32 heads_total;
   const u32 hexcl = warp_totals_exclusive(wheads, warp, lane, s_w, heads_total);
 
-  // ---- phase 2: node rank -> take-all decision -> selection flags ------------------------------
-  u32 node_rank[SWP_ITEMS];
-  u32 smask[SWP_ITEMS];
-  u32 take_bits = 0; // per item: this lane's element belongs to a take-all node
+  // ---- phase 2: node rank -> take-all decision -> selection flags, child counts -------------------
   u32 wsel = 0;
-  {
-    u32 run = a.tile_rank0[tile] + hexcl; // heads before this item
+  const u32 rank0 = a.tile_rank0[tile];
+  u32 run = rank0 + hexcl; // heads before this item
+  const bool count_children = a.child_count != nullptr;
+  // the tile's first element belongs to node rank0 - 1 (or rank0 when it is a head): slots of the
+  // tile start at or after slot_base; big nodes put a whole tile into one or two slots, so the
+  // global atomics shrink to a few per tile
+  const u32 slot_base = (rank0 ? rank0 - 1u : 0u) * 8u;
+  const int child_shift = a.node_shift - 3;
 #pragma unroll
-    for (int j = 0; j < SWP_ITEMS; ++j) {
-      const u64 i = base + item_pos(warp, lane, j);
-      const u32 incl = run + __popc(nmask[j] & (lt | (1u << lane)));
-      node_rank[j] = incl - 1;
-      run += __popc(nmask[j]);
-      bool sel = false;
-      if (i < a.count) {
-        bool take = a.force_all != 0;
-        if (!take && a.allow_take_all) {
-          const u32 cnt = node_point_count(a.node_start, a.node_gcount, node_rank[j]);
-          take = (u64)cnt <= a.max_points_per_node;
-        }
-        take_bits |= (take && !a.force_all ? 1u : 0u) << j;
-        if (take)
-          sel = true;
-        else if (a.sampling == SW_RANDOM_GRID)
-          sel = (cmask[j] >> lane) & 1u; // first point of each cell run (Sampling.h:253-284)
-        else
-          sel = a.sel[i] == 1;
+  for (int j = 0; j < SWP_ITEMS; ++j) {
+    const u64 i = base + item_pos(warp, lane, j);
+    const u32 node_rank = run + __popc(nmask[j] & (lt | (1u << lane))) - 1;
+    run += __popc(nmask[j]);
+    bool sel = false;
+    const bool valid = i < a.count;
+    if (valid) {
+      bool take = a.force_all != 0;
+      if (!take && a.allow_take_all) {
+        const u32 cnt = node_point_count(a.node_start, a.node_gcount, node_rank);
+        take = (u64)cnt <= a.max_points_per_node;
       }
-      smask[j] = __ballot_sync(0xffffffffu, sel);
-      wsel += __popc(smask[j]);
+      if (take)
+        sel = true;
+      else if (a.sampling == SW_RANDOM_GRID)
+        sel = (cmask[j] >> lane) & 1u; // first point of each cell run (Sampling.h:253-284)
+      else
+        sel = a.sel[i] == 1;
+    }
+    const u32 smask = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0)
+      a.selbits[((size_t)tile * SWP_WARPS + warp) * SWP_ITEMS + j] = smask;
+    wsel += __popc(smask);
+    if (count_children) {
+      // points that stay go to child (node_rank, octant); keys are sorted, so equal children are
+      // runs of lanes: one atomic per run
+      const u32 rem = __ballot_sync(0xffffffffu, valid && !sel);
+      const u32 slot = node_rank * 8u + (u32)((key[j] >> child_shift) & 7u);
+      const u32 prev_slot = __shfl_up_sync(0xffffffffu, slot, 1);
+      const u32 heads = __ballot_sync(0xffffffffu, lane == 0 || slot != prev_slot);
+      if ((heads >> lane) & 1u) {
+        const u32 above = heads & ~((2u << lane) - 1u); // heads in higher lanes (2u << 31 wraps to 0)
+        const u32 end_mask = above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu;
+        const u32 c = __popc(rem & end_mask & ~lt);
+        if (c) {
+          if (slot - slot_base < CHILD_WINDOW)
+            atomicAdd(&s_child[slot - slot_base], c);
+          else
+            atomicAdd(&a.child_count[slot], c);
+        }
+      }
     }
   }
-  u32 sel_total;
-  const u32 sexcl = warp_totals_exclusive(wsel, warp, lane, s_w2, sel_total);
-  if (warp == 0) {
-    const u64 p = lookback_exclusive(status, tile, (u64)sel_total);
-    if (lane == 0)
-      s_prefix = p;
+  if (lane == 0 && wsel)
+    atomicAdd(&s_sel, wsel);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    a.tile_sel[tile] = s_sel;
+  if (count_children)
+    for (u32 i = threadIdx.x; i < CHILD_WINDOW; i += SWP_THREADS) {
+      const u32 c = s_child[i];
+      if (c)
+        atomicAdd(&a.child_count[slot_base + i], c);
+    }
+}
+
+// One block.  (A) exclusive scan of tile_sel in place, total -> *n_selected.  (B) child counts ->
+// node_start of the next level (start position in the remainder list of every non-empty child,
+// plus the sentinel) and *n_nodes_next.
+#define SCAN_THREADS 1024
+__global__ void __launch_bounds__(SCAN_THREADS)
+level_scan_kernel(u32* __restrict__ tile_sel, u32 n_tiles, u64* __restrict__ n_selected,
+                  const u32* __restrict__ child_count, u32 n_slots, u32* __restrict__ next_node_start,
+                  u32* __restrict__ n_nodes_next)
+{
+  __shared__ u32 s_wa[32], s_wb[32];
+  __shared__ u32 s_carry_a, s_carry_b;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    s_carry_a = 0;
+    s_carry_b = 0;
   }
   __syncthreads();
-  const u64 sel_prefix = s_prefix;
-  if (threadIdx.x == 0 && base + SW_SWEEP_TILE >= a.count)
-    *n_selected = sel_prefix + sel_total;
+  // ---- (A) ----
+  for (u32 t0 = 0; t0 < n_tiles; t0 += SCAN_THREADS) {
+    const u32 t = t0 + threadIdx.x;
+    const u32 v = (t < n_tiles) ? tile_sel[t] : 0u;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (u32)o)
+        incl += up;
+    }
+    if (lane == 31)
+      s_wa[warp] = incl;
+    __syncthreads();
+    u32 wofs = 0;
+    for (u32 w = 0; w < warp; ++w)
+      wofs += s_wa[w];
+    const u32 carry = s_carry_a;
+    if (t < n_tiles)
+      tile_sel[t] = carry + wofs + incl - v;
+    __syncthreads();
+    if (threadIdx.x == SCAN_THREADS - 1)
+      s_carry_a = carry + wofs + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    *n_selected = s_carry_a;
+  // ---- (B) ----
+  if (!child_count)
+    return;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    s_carry_a = 0;
+  __syncthreads();
+  for (u32 t0 = 0; t0 < n_slots; t0 += SCAN_THREADS) {
+    const u32 t = t0 + threadIdx.x;
+    const u32 v = (t < n_slots) ? child_count[t] : 0u;
+    const u32 f = v ? 1u : 0u;
+    u32 ia = v, ib = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 ua = __shfl_up_sync(0xffffffffu, ia, o);
+      const u32 ub = __shfl_up_sync(0xffffffffu, ib, o);
+      if (lane >= (u32)o) {
+        ia += ua;
+        ib += ub;
+      }
+    }
+    if (lane == 31) {
+      s_wa[warp] = ia;
+      s_wb[warp] = ib;
+    }
+    __syncthreads();
+    u32 oa = 0, ob = 0;
+    for (u32 w = 0; w < warp; ++w) {
+      oa += s_wa[w];
+      ob += s_wb[w];
+    }
+    const u32 ca = s_carry_a, cb = s_carry_b;
+    if (f)
+      next_node_start[cb + ob + ib - 1] = ca + oa + ia - v;
+    __syncthreads();
+    if (threadIdx.x == SCAN_THREADS - 1) {
+      s_carry_a = ca + oa + ia;
+      s_carry_b = cb + ob + ib;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    next_node_start[s_carry_b] = s_carry_a; // sentinel = points that stay
+    *n_nodes_next = s_carry_b;
+  }
+}
 
-  // ---- phase 3: scatter ------------------------------------------------------------------------
-  u64 run = sel_prefix + sexcl; // selected before this item
+__global__ void __launch_bounds__(SWP_THREADS)
+level_scatter_kernel(SwLevelArgs a)
+{
+  __shared__ u32 s_w[SWP_WARPS];
+  __shared__ u32 s_w2[SWP_WARPS];
+  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 tile = blockIdx.x;
+  const u64 base = (u64)tile * SW_SWEEP_TILE;
+  const u32 lt = lanemask_lt();
+
+  u64 key[SWP_ITEMS];
+  u32 idx[SWP_ITEMS];
+  u32 nmask[SWP_ITEMS];
+  u32 smask[SWP_ITEMS];
+  u32 wheads = 0, wsel = 0;
+#pragma unroll
+  for (int j = 0; j < SWP_ITEMS; ++j) {
+    const u64 i = base + item_pos(warp, lane, j);
+    bool nh = false;
+    key[j] = 0;
+    idx[j] = 0;
+    if (i < a.count) {
+      const u64 k = a.in_key[i] & SW_KEY_MASK;
+      key[j] = k;
+      idx[j] = a.in_idx ? a.in_idx[i] : (u32)i;
+      nh = (i == 0) || ((k >> a.node_shift) != ((a.in_key[i - 1] & SW_KEY_MASK) >> a.node_shift));
+    }
+    nmask[j] = __ballot_sync(0xffffffffu, nh);
+    smask[j] = a.selbits[((size_t)tile * SWP_WARPS + warp) * SWP_ITEMS + j];
+    wheads += __popc(nmask[j]);
+    wsel += __popc(smask[j]);
+  }
+  u32 hexcl, sexcl;
+  warp_totals_exclusive2(wheads, wsel, warp, lane, s_w, s_w2, hexcl, sexcl);
+
+  u64 srun = (u64)a.tile_sel[tile] + sexcl; // selected before this item (tile_sel holds the exclusive scan)
+  u32 hrun = a.tile_rank0[tile] + hexcl;    // node heads before this item
 #pragma unroll
   for (int j = 0; j < SWP_ITEMS; ++j) {
     const u64 i = base + item_pos(warp, lane, j);
     if (i < a.count) {
-      const u64 srank = run + __popc(smask[j] & lt);
-      const u32 idx = a.in_idx ? a.in_idx[i] : (u32)i;
+      const u64 srank = srun + __popc(smask[j] & lt);
       if ((smask[j] >> lane) & 1u) {
         a.out_key[a.out_offset + srank] = key[j];
-        a.out_idx[a.out_offset + srank] = idx;
+        a.out_idx[a.out_offset + srank] = idx[j];
       } else if (a.rem_key) {
         a.rem_key[i - srank] = key[j];
-        a.rem_idx[i - srank] = idx;
+        a.rem_idx[i - srank] = idx[j];
       }
       if ((nmask[j] >> lane) & 1u) {
-        a.node_index[a.node_base + node_rank[j]] = key[j] >> a.node_shift;
+        const u32 node_rank = hrun + __popc(nmask[j] & lt);
+        bool take = false;
+        if (!a.force_all && a.allow_take_all)
+          take = (u64)node_point_count(a.node_start, a.node_gcount, node_rank) <= a.max_points_per_node;
+        a.node_index[a.node_base + node_rank] = key[j] >> a.node_shift;
         // bit 63 = SW_NODE_TAKE_ALL (decoded by the host when it builds the node table)
-        a.node_first[a.node_base + node_rank[j]] = (a.out_offset + srank) | ((u64)((take_bits >> j) & 1u) << 63);
+        a.node_first[a.node_base + node_rank] = (a.out_offset + srank) | ((u64)(take ? 1u : 0u) << 63);
       }
     }
-    run += __popc(smask[j]);
+    srun += __popc(smask[j]);
+    hrun += __popc(nmask[j]);
   }
 }
 
 void
-launch_level_compact(const SwLevelArgs& a, u64* n_selected, u64* status, u32* ticket, cudaStream_t stream)
+launch_level_compact(const SwLevelArgs& a, u64* n_selected, u32 n_child_slots, u32* next_node_start, u32* n_nodes_next,
+                     cudaStream_t stream)
 {
-  const size_t tiles = sweep_tiles(a.count);
-  cudaMemsetAsync(status, 0, tiles * sizeof(u64), stream);
-  cudaMemsetAsync(ticket, 0, sizeof(u32), stream);
-  level_compact_kernel<<<(u32)tiles, SWP_THREADS, 0, stream>>>(a, n_selected, status, ticket);
+  const u32 tiles = (u32)sweep_tiles(a.count);
+  if (a.child_count)
+    cudaMemsetAsync(a.child_count, 0, (size_t)n_child_slots * sizeof(u32), stream);
+  level_count_kernel<<<tiles, SWP_THREADS, 0, stream>>>(a);
+  level_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(a.tile_sel, tiles, n_selected, a.child_count, n_child_slots,
+                                                    next_node_start, n_nodes_next);
+  level_scatter_kernel<<<tiles, SWP_THREADS, 0, stream>>>(a);
 }
 
 // =============================================================================================

@@ -41,7 +41,11 @@ void launch_compose_ids(const u32* perm, const u32* idx, u64 n, u32* out, cudaSt
 void launch_level5_bins(const u64* sorted_keys, u64 n, u32* bin_start /* 262145 */, cudaStream_t stream);
 
 // ---- sampling sweep (kernels_sampling.cu) -----------------------------------------------------
-#define SW_SWEEP_TILE 2048 /* elements per tile of the rle / select / compact kernels */
+#ifndef SWP_THREADS
+#define SWP_THREADS 256
+#endif
+#define SWP_ITEMS 8
+#define SW_SWEEP_TILE (SWP_THREADS * SWP_ITEMS) /* elements per tile of the rle / select / compact kernels */
 
 struct SwLevelArgs
 {
@@ -64,6 +68,10 @@ struct SwLevelArgs
   const u32* node_gcount; // optional: global (all-shard) point count per node rank, nullptr = local run length
   // optional per-element selection flags (argmin / min-distance strategies)
   const unsigned char* sel;
+  // scratch of the two-pass compaction
+  u32* selbits;     // one bit per element: sweep_tiles * SW_SWEEP_TILE / 32 words
+  u32* tile_sel;    // per tile: selected points (count pass), then their exclusive scan
+  u32* child_count; // 8 * n_nodes counters of the points that stay, per child node; nullptr = not needed
   // outputs
   u64* out_key;
   u32* out_idx;
@@ -81,8 +89,15 @@ size_t sweep_tiles(u64 count);
 // run-length encode nodes: node_start[], tile_rank0[], *n_nodes.  `status` >= sweep_tiles u64.
 void launch_node_rle(const u64* keys, u64 count, int node_shift, u32* node_start, u32* tile_rank0, u32* n_nodes,
                      u64* status, u32* ticket, cudaStream_t stream);
-// stable two-way compaction of one level; *n_selected receives the number of selected points
-void launch_level_compact(const SwLevelArgs& a, u64* n_selected, u64* status, u32* ticket, cudaStream_t stream);
+// node boundaries that do not need a pass over the points
+void launch_root_node(u32* node_start, u64 count, cudaStream_t stream);
+void launch_tile_rank0(const u32* node_start, u32 n_nodes, u64 count, u32* tile_rank0, cudaStream_t stream);
+// Stable two-way compaction of one level (count pass, scan, scatter pass).  *n_selected receives the
+// number of selected points.  With a.child_count != nullptr the node boundaries of the next level
+// are written to next_node_start (n_child_slots = 8 * nodes of this level) and their number to
+// *n_nodes_next.
+void launch_level_compact(const SwLevelArgs& a, u64* n_selected, u32 n_child_slots, u32* next_node_start,
+                          u32* n_nodes_next, cudaStream_t stream);
 
 struct SwArgminArgs
 {

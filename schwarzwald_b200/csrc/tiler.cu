@@ -82,7 +82,7 @@ struct HostScalars
   u32 n_nodes;
   u32 n_clamped;
   u32 error_flag;
-  u32 changed;
+  u32 n_nodes_next;
   u64 n_selected;
   u32 scratch[16]; // pinned scratch for the min-distance driver (starts at u32 index 8... see below)
 };
@@ -119,7 +119,8 @@ struct swgpu_tiler
   DevBuf pos_sorted;
   DevBuf out_key, out_idx;
   u64 out_count = 0;
-  DevBuf node_start, tile_rank0, sel, scan_status;
+  DevBuf node_start, node_start_next, tile_rank0, sel, scan_status;
+  DevBuf selbits, tile_sel, child_count;
   DevBuf node_index, node_first;
   u64 node_count = 0;
   DevBuf bins;
@@ -147,7 +148,7 @@ struct swgpu_tiler
   u32* d_n_nodes() { return scalars.as<u32>() + 0; }
   u32* d_n_clamped() { return scalars.as<u32>() + 1; }
   u32* d_error() { return scalars.as<u32>() + 2; }
-  u32* d_changed() { return scalars.as<u32>() + 3; }
+  u32* d_n_nodes_next() { return scalars.as<u32>() + 3; }
   u64* d_n_selected() { return reinterpret_cast<u64*>(scalars.as<u32>() + 4); }
   u32* d_tickets() { return scalars.as<u32>() + 8; } // 16 u32
   u32* d_md_ncells() { return scalars.as<u32>() + 24; }
@@ -271,6 +272,9 @@ ensure_batch_buffers(swgpu_tiler* h, u64 n)
   CK(h->hist.ensure(8 * 256 * 4));
   CK(h->sort_status.ensure(sort_status_words(n) * 4));
   CK(h->node_start.ensure((nn + 1) * 4));
+  CK(h->node_start_next.ensure((nn + 1) * 4));
+  CK(h->selbits.ensure(sweep_tiles(n) * (SW_SWEEP_TILE / 32) * 4));
+  CK(h->tile_sel.ensure(sweep_tiles(n) * 4));
   CK(h->tile_rank0.ensure(sweep_tiles(n) * 4));
   CK(h->scan_status.ensure(sweep_tiles(n) * 8 * 5));
   CK(h->bins.ensure(262145 * 4));
@@ -324,7 +328,7 @@ exchange_node_counts(swgpu_tiler* h, const u64* in_key, u32 n_nodes, int levels)
 int
 sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int levels, bool allow_take_all,
             bool force_all, u64* rem_key, u32* rem_idx, u32 chunk_flags, u64* n_selected_out, bool input_in_out_buffers,
-            u64 input_out_offset)
+            u64 input_out_offset, bool nodes_known, u32 n_nodes_known, u32* n_nodes_next_out)
 {
   const int node_level = levels - 1;
   const int node_shift = shift_for_levels(levels);
@@ -338,14 +342,22 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
     in_idx = h->out_idx.as<u32>() + input_out_offset;
   }
 
-  launch_node_rle(in_key, count, node_shift, h->node_start.as<u32>(), h->tile_rank0.as<u32>(), h->d_n_nodes(),
-                  h->scan_status.as<u64>(), h->d_tickets(), s);
-  h->stats.kernel_launches += 1;
-  h->stats.bytes_sample += 8 * count;
-  int rc = sync_scalars(h);
-  if (rc)
-    return rc;
-  const u32 n_nodes = h->h_scalars->n_nodes;
+  // node boundaries: known from the previous level's child counts, else found by a pass over the keys
+  int rc = SW_OK;
+  u32 n_nodes = n_nodes_known;
+  if (nodes_known) {
+    launch_tile_rank0(h->node_start.as<u32>(), n_nodes, count, h->tile_rank0.as<u32>(), s);
+    h->stats.kernel_launches += 1;
+  } else {
+    launch_node_rle(in_key, count, node_shift, h->node_start.as<u32>(), h->tile_rank0.as<u32>(), h->d_n_nodes(),
+                    h->scan_status.as<u64>(), h->d_tickets(), s);
+    h->stats.kernel_launches += 1;
+    h->stats.bytes_sample += 8 * count;
+    rc = sync_scalars(h);
+    if (rc)
+      return rc;
+    n_nodes = h->h_scalars->n_nodes;
+  }
   CK(h->node_index.ensure((h->node_count + n_nodes) * 8, s, h->node_count * 8));
   CK(h->node_first.ensure((h->node_count + n_nodes + 1) * 8, s, h->node_count * 8));
 
@@ -476,8 +488,20 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
   a.node_first = h->node_first.as<u64>();
   a.node_base = h->node_count;
   a.levels = levels;
-  launch_level_compact(a, h->d_n_selected(), h->scan_status.as<u64>(), h->d_tickets(), s);
-  h->stats.kernel_launches += 1;
+  CK(h->selbits.ensure(sweep_tiles(count) * (SW_SWEEP_TILE / 32) * 4));
+  CK(h->tile_sel.ensure(sweep_tiles(count) * 4));
+  a.selbits = h->selbits.as<u32>();
+  a.tile_sel = h->tile_sel.as<u32>();
+  // the points that stay are counted per child node: that IS the node table of the next level
+  const bool want_children = rem_key != nullptr && !force_all && levels < 21;
+  const u32 n_child_slots = want_children ? 8u * n_nodes : 0u;
+  a.child_count = nullptr;
+  if (want_children) {
+    CK(h->child_count.ensure((size_t)n_child_slots * 4));
+    a.child_count = h->child_count.as<u32>();
+  }
+  launch_level_compact(a, h->d_n_selected(), n_child_slots, h->node_start_next.as<u32>(), h->d_n_nodes_next(), s);
+  h->stats.kernel_launches += 3;
   rc = sync_scalars(h);
   if (rc)
     return rc;
@@ -488,7 +512,12 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
                   ? "Grids smaller than 16x16 are not supported currently!"
                   : "Node is too small to be sampled with ImprovedPoissonSampling!");
   const u64 n_sel = h->h_scalars->n_selected;
-  h->stats.bytes_sample += (8 + (in_idx ? 4 : 0)) * count + 12 * n_sel + (rem_key ? 12 * (count - n_sel) : 0);
+  // count pass: keys; scatter pass: keys + ids in, (key, id) out
+  h->stats.bytes_sample += (16 + (in_idx ? 4 : 0)) * count + 12 * n_sel + (rem_key ? 12 * (count - n_sel) : 0);
+  if (n_nodes_next_out)
+    *n_nodes_next_out = want_children ? h->h_scalars->n_nodes_next : 0u;
+  if (want_children) // the next level reads its node boundaries from node_start
+    std::swap(h->node_start, h->node_start_next);
   h->stats.sweep_points += count;
 
   Chunk c{};
@@ -616,6 +645,15 @@ run_batch(swgpu_tiler* h)
   u64* rem_key[2] = { h->keys[1].as<u64>(), h->wkey2.as<u64>() };
   u32* rem_idx[2] = { h->vals[1].as<u32>(), h->widx2.as<u32>() };
   int flip = 0;
+  // node boundaries of the first level: the root is one node; FAST's start nodes are found by one
+  // run-length pass over the sorted keys; every later level gets them from the child counts
+  bool nodes_known = false;
+  u32 n_nodes_known = 0;
+  if (first_levels == 0 && count > 0) {
+    launch_root_node(h->node_start.as<u32>(), count, s);
+    nodes_known = true;
+    n_nodes_known = 1;
+  }
   for (int levels = first_levels; count > 0 || spans_shards(h, levels); ++levels) {
     const int node_level = levels - 1;
     const LevelKind kind = level_kind(h, node_level);
@@ -633,8 +671,9 @@ run_batch(swgpu_tiler* h)
       continue;
     }
     u64 n_sel = 0;
+    u32 n_nodes_next = 0;
     rc = sweep_level(h, in_key, in_idx, count, levels, /*allow_take_all=*/true, terminal, rem_key[flip],
-                     rem_idx[flip], 0u, &n_sel, false, 0);
+                     rem_idx[flip], 0u, &n_sel, false, 0, nodes_known, n_nodes_known, &n_nodes_next);
     if (rc)
       return rc;
     h->stats.n_levels += 1;
@@ -642,6 +681,8 @@ run_batch(swgpu_tiler* h)
     in_idx = rem_idx[flip];
     flip ^= 1;
     count -= n_sel;
+    nodes_known = true;
+    n_nodes_known = n_nodes_next;
   }
   record(h, 4);
   CK(cudaGetLastError());
@@ -668,7 +709,7 @@ run_finalize(swgpu_tiler* h)
     const Chunk in = h->chunks[src];
     u64 n_sel = 0;
     const int rc = sweep_level(h, nullptr, nullptr, in.count, lv, /*allow_take_all=*/false, false, nullptr, nullptr,
-                               SW_NODE_RECONSTRUCTED, &n_sel, true, in.out_offset);
+                               SW_NODE_RECONSTRUCTED, &n_sel, true, in.out_offset, false, 0, nullptr);
     if (rc)
       return rc;
     h->stats.n_reconstruct_levels += 1;
@@ -744,7 +785,7 @@ swgpu_destroy(swgpu_handle h)
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = { &h->xyz_own,    &h->keys[0],   &h->keys[1],       &h->vals[0],     &h->vals[1],  &h->wkey2,
                      &h->widx2,      &h->hist,      &h->sort_status,   &h->scalars,     &h->pos_sorted, &h->out_key,
-                     &h->out_idx,    &h->node_start, &h->tile_rank0,   &h->sel,         &h->scan_status, &h->node_index,
+                     &h->out_idx,    &h->node_start, &h->node_start_next, &h->selbits, &h->tile_sel, &h->child_count, &h->tile_rank0,   &h->sel,         &h->scan_status, &h->node_index,
                      &h->node_first, &h->bins,      &h->ids_tmp,     &h->dense_counts, &h->node_gcount,
                      &h->part_tile_counts, &h->part_send_counts };
   for (DevBuf* b : bufs)
