@@ -480,6 +480,84 @@ level_scatter_kernel(SwLevelArgs a)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// node tables that come from per-node data instead of a pass over the points
+// ---------------------------------------------------------------------------------------------
+// One block: stable compaction of the entries with flag != 0: out[rank] = value, out[total] = sentinel.
+template<typename Flag, typename Value>
+__device__ __forceinline__ void
+block_compact(u32 n, Flag flag_of, Value value_of, u32* __restrict__ out, u32 sentinel, u32* __restrict__ n_out)
+{
+  __shared__ u32 s_wf[32];
+  __shared__ u32 s_carry;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0)
+    s_carry = 0;
+  __syncthreads();
+  for (u32 t0 = 0; t0 < n; t0 += SCAN_THREADS) {
+    const u32 t = t0 + threadIdx.x;
+    const u32 f = (t < n && flag_of(t)) ? 1u : 0u;
+    const u32 m = __ballot_sync(0xffffffffu, f);
+    if (lane == 0)
+      s_wf[warp] = __popc(m);
+    __syncthreads();
+    u32 wofs = 0, tot = 0;
+    for (u32 w = 0; w < SCAN_THREADS / 32; ++w) {
+      wofs += (w < warp) ? s_wf[w] : 0u;
+      tot += s_wf[w];
+    }
+    const u32 carry = s_carry;
+    if (f)
+      out[carry + wofs + __popc(m & lanemask_lt())] = value_of(t);
+    __syncthreads();
+    if (threadIdx.x == 0)
+      s_carry = carry + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[s_carry] = sentinel;
+    *n_out = s_carry;
+  }
+}
+
+// FAST start nodes (split_indexed_points_into_subranges, TilingAlgorithms.cpp:1537-1578): the
+// non-empty prefixes of S levels, from the level-5 bin boundaries of the sorted keys.
+__global__ void __launch_bounds__(SCAN_THREADS)
+start_nodes_kernel(const u32* __restrict__ bin_start, int start_levels, u32 count, u32* __restrict__ node_start,
+                   u32* __restrict__ n_nodes)
+{
+  const u32 group = 1u << (3 * (6 - start_levels));
+  const u32 n_groups = 262144u / group;
+  block_compact(
+    n_groups, [&](u32 g) { return bin_start[(g + 1) * group] > bin_start[g * group]; },
+    [&](u32 g) { return bin_start[g * group]; }, node_start, count, n_nodes);
+}
+
+// Reconstruct (reconstruct_single_node, TilingAlgorithms.cpp:1661-1715): the input of a parent is
+// the concatenation of its children's stored points = a run of child nodes in the previous chunk.
+__global__ void __launch_bounds__(SCAN_THREADS)
+parent_nodes_kernel(const u64* __restrict__ child_index, const u64* __restrict__ child_first, u32 n_children,
+                    u64 chunk_offset, u32 chunk_count, u32* __restrict__ node_start, u32* __restrict__ n_nodes)
+{
+  block_compact(
+    n_children, [&](u32 c) { return c == 0 || (child_index[c] >> 3) != (child_index[c - 1] >> 3); },
+    [&](u32 c) { return (u32)((child_first[c] & ~(1ull << 63)) - chunk_offset); }, node_start, chunk_count, n_nodes);
+}
+
+void
+launch_start_nodes(const u32* bin_start, int start_levels, u64 count, u32* node_start, u32* n_nodes, cudaStream_t stream)
+{
+  start_nodes_kernel<<<1, SCAN_THREADS, 0, stream>>>(bin_start, start_levels, (u32)count, node_start, n_nodes);
+}
+
+void
+launch_parent_nodes(const u64* child_index, const u64* child_first, u32 n_children, u64 chunk_offset, u64 chunk_count,
+                    u32* node_start, u32* n_nodes, cudaStream_t stream)
+{
+  parent_nodes_kernel<<<1, SCAN_THREADS, 0, stream>>>(child_index, child_first, n_children, chunk_offset,
+                                                       (u32)chunk_count, node_start, n_nodes);
+}
+
 void
 launch_level_compact(const SwLevelArgs& a, u64* n_selected, u32 n_child_slots, u32* next_node_start, u32* n_nodes_next,
                      cudaStream_t stream)

@@ -91,6 +91,12 @@ void launch_node_rle(const u64* keys, u64 count, int node_shift, u32* node_start
                      u64* status, u32* ticket, cudaStream_t stream);
 // node boundaries that do not need a pass over the points
 void launch_root_node(u32* node_start, u64 count, cudaStream_t stream);
+// FAST start nodes from the level-5 bin boundaries (launch_level5_bins) of the sorted keys
+void launch_start_nodes(const u32* bin_start, int start_levels, u64 count, u32* node_start, u32* n_nodes,
+                        cudaStream_t stream);
+// reconstruct: parent nodes = runs of children (index >> 3) in the previous output chunk
+void launch_parent_nodes(const u64* child_index, const u64* child_first, u32 n_children, u64 chunk_offset,
+                         u64 chunk_count, u32* node_start, u32* n_nodes, cudaStream_t stream);
 void launch_tile_rank0(const u32* node_start, u32 n_nodes, u64 count, u32* tile_rank0, cudaStream_t stream);
 // Stable two-way compaction of one level (count pass, scan, scatter pass).  *n_selected receives the
 // number of selected points.  With a.child_count != nullptr the node boundaries of the next level

@@ -629,6 +629,8 @@ run_batch(swgpu_tiler* h)
     int S = 0;
     if (sharded && h->start_level_override >= 0) {
       S = h->start_level_override; // estimated by the caller from the all-reduced prefix histogram
+      launch_level5_bins(h->keys[0].as<u64>(), h->n, h->bins.as<u32>(), h->stream); // start nodes below
+      h->stats.kernel_launches += 1;
     } else {
       rc = estimate_start_level(h, &S);
       if (rc)
@@ -653,6 +655,14 @@ run_batch(swgpu_tiler* h)
     launch_root_node(h->node_start.as<u32>(), count, s);
     nodes_known = true;
     n_nodes_known = 1;
+  } else if (count > 0) {
+    launch_start_nodes(h->bins.as<u32>(), first_levels, count, h->node_start.as<u32>(), h->d_n_nodes(), s);
+    h->stats.kernel_launches += 1;
+    rc = sync_scalars(h);
+    if (rc)
+      return rc;
+    nodes_known = true;
+    n_nodes_known = h->h_scalars->n_nodes;
   }
   for (int levels = first_levels; count > 0 || spans_shards(h, levels); ++levels) {
     const int node_level = levels - 1;
@@ -708,8 +718,15 @@ run_finalize(swgpu_tiler* h)
   for (int lv = S - 1; lv >= 0; --lv) {
     const Chunk in = h->chunks[src];
     u64 n_sel = 0;
-    const int rc = sweep_level(h, nullptr, nullptr, in.count, lv, /*allow_take_all=*/false, false, nullptr, nullptr,
-                               SW_NODE_RECONSTRUCTED, &n_sel, true, in.out_offset, false, 0, nullptr);
+    launch_parent_nodes(h->node_index.as<u64>() + in.node_base, h->node_first.as<u64>() + in.node_base, in.n_nodes,
+                        in.out_offset, in.count, h->node_start.as<u32>(), h->d_n_nodes(), h->stream);
+    h->stats.kernel_launches += 1;
+    int rc = sync_scalars(h);
+    if (rc)
+      return rc;
+    const u32 n_parents = h->h_scalars->n_nodes;
+    rc = sweep_level(h, nullptr, nullptr, in.count, lv, /*allow_take_all=*/false, false, nullptr, nullptr,
+                     SW_NODE_RECONSTRUCTED, &n_sel, true, in.out_offset, true, n_parents, nullptr);
     if (rc)
       return rc;
     h->stats.n_reconstruct_levels += 1;
