@@ -214,115 +214,203 @@ launch_root_node(u32* node_start, u64 count, cudaStream_t stream)
   root_node_kernel<<<1, 1, 0, stream>>>(node_start, (u32)count);
 }
 
+// ---- blocked tile layout of the count / scatter kernels -----------------------------------------
+// Thread t owns the 8 consecutive elements [8t, 8t + 8) of its tile, so node / cell heads, selection
+// bits and child runs are thread-local bit operations and the warp-wide collectives (a ballot costs
+// ~2.6 SM-cycles, a popc ~2.3 on B200) are needed once per 256 elements instead of once per 32.
+// Global loads and stores stay coalesced: tiles are transposed through shared memory, padded by one
+// slot per 8 so that the 72-byte thread stride is conflict-free.
+#define BLK_ITEMS 8
+#define BLK_PAD(p) ((p) + ((p) >> 3))
+#define BLK_SLOTS (SW_SWEEP_TILE + SW_SWEEP_TILE / 8)
+static_assert(SWP_ITEMS == BLK_ITEMS, "blocked layout assumes 8 elements per thread");
+
+// keys of the tile into registers (blocked) + the key before the thread's first element
+__device__ __forceinline__ void
+load_keys_blocked(const u64* __restrict__ in_key, u64 base, u64 count, u64* s_k, u64* s_prev, u64 k[BLK_ITEMS], u64& prev)
+{
+  const u32 tid = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < BLK_ITEMS; ++j) {
+    const u32 p = j * SWP_THREADS + tid;
+    const u64 i = base + p;
+    s_k[BLK_PAD(p)] = (i < count) ? (in_key[i] & SW_KEY_MASK) : ~0ull;
+  }
+  if (tid == 0)
+    *s_prev = base ? (in_key[base - 1] & SW_KEY_MASK) : 0ull;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < BLK_ITEMS; ++j)
+    k[j] = s_k[9 * tid + j];
+  prev = tid ? s_k[9 * tid - 2] : *s_prev; // BLK_PAD(8 * tid - 1)
+}
+
+// head bits of the thread's elements: bit j set = element j starts a new run of (key >> shift)
+__device__ __forceinline__ u32
+head_bits(const u64 k[BLK_ITEMS], u64 prev, int shift, bool first_of_list)
+{
+  u32 bits = first_of_list ? 1u : (((k[0] >> shift) != (prev >> shift)) ? 1u : 0u);
+#pragma unroll
+  for (int j = 1; j < BLK_ITEMS; ++j)
+    bits |= (((k[j] >> shift) != (k[j - 1] >> shift)) ? 1u : 0u) << j;
+  return bits;
+}
+
+// exclusive block scan of a packed pair of counters (each total < 2^16); returns the block total
+__device__ __forceinline__ u32
+block_scan_packed(u32 v, u32* s_w, u32& excl)
+{
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (u32)o)
+      incl += up;
+  }
+  if (lane == 31)
+    s_w[warp] = incl;
+  __syncthreads();
+  u32 wofs = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < SWP_WARPS; ++w) {
+    const u32 x = s_w[w];
+    wofs += (w < (int)warp) ? x : 0u;
+    tot += x;
+  }
+  excl = wofs + incl - v;
+  return tot;
+}
+
 #define CHILD_WINDOW 256
 __global__ void __launch_bounds__(SWP_THREADS)
 level_count_kernel(SwLevelArgs a)
 {
+  __shared__ u64 s_k[BLK_SLOTS];
+  __shared__ u64 s_prev;
   __shared__ u32 s_w[SWP_WARPS];
-  __shared__ u32 s_sel;
+  __shared__ u32 s_w2[SWP_WARPS];
   __shared__ u32 s_child[CHILD_WINDOW]; // child counters of the first CHILD_WINDOW slots touched by the tile
-  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 tid = threadIdx.x, lane = tid & 31;
   const u32 tile = blockIdx.x;
   const u64 base = (u64)tile * SW_SWEEP_TILE;
-  const u32 lt = lanemask_lt();
-  if (threadIdx.x == 0)
-    s_sel = 0;
-  for (u32 i = threadIdx.x; i < CHILD_WINDOW; i += SWP_THREADS)
+  const u64 e0 = base + 8ull * tid;
+  for (u32 i = tid; i < CHILD_WINDOW; i += SWP_THREADS)
     s_child[i] = 0;
 
-  // ---- phase 1: keys, node heads, cell heads ---------------------------------------------------
-  u64 key[SWP_ITEMS];
-  u32 nmask[SWP_ITEMS];
-  u32 cmask[SWP_ITEMS];
-  u32 wheads = 0;
-#pragma unroll
-  for (int j = 0; j < SWP_ITEMS; ++j) {
-    const u64 i = base + item_pos(warp, lane, j);
-    bool nh = false, ch = false;
-    key[j] = 0;
-    if (i < a.count) {
-      const u64 k = a.in_key[i] & SW_KEY_MASK;
-      key[j] = k;
-      if (i == 0) {
-        nh = ch = true;
-      } else {
-        const u64 pk = a.in_key[i - 1] & SW_KEY_MASK;
-        nh = (k >> a.node_shift) != (pk >> a.node_shift);
-        ch = nh || ((k >> a.cell_shift) != (pk >> a.cell_shift));
-      }
-    }
-    nmask[j] = __ballot_sync(0xffffffffu, nh);
-    cmask[j] = __ballot_sync(0xffffffffu, ch);
-    wheads += __popc(nmask[j]);
-  }
-  u32 heads_total;
-  const u32 hexcl = warp_totals_exclusive(wheads, warp, lane, s_w, heads_total);
+  u64 k[BLK_ITEMS];
+  u64 prev;
+  load_keys_blocked(a.in_key, base, a.count, s_k, &s_prev, k, prev);
+  const u32 nvalid = e0 >= a.count ? 0u : (a.count - e0 < 8 ? (u32)(a.count - e0) : 8u);
+  const u32 valid = (1u << nvalid) - 1u;
 
-  // ---- phase 2: node rank -> take-all decision -> selection flags, child counts -------------------
-  u32 wsel = 0;
+  // ---- node heads, cell heads --------------------------------------------------------------------
+  const u32 nh = head_bits(k, prev, a.node_shift, e0 == 0) & valid;
+  const u32 ch = (head_bits(k, prev, a.cell_shift, e0 == 0) | nh) & valid;
+  u32 hexcl;
+  block_scan_packed(__popc(nh), s_w, hexcl);
+
+  // ---- node rank -> take-all decision -> selection bits ----------------------------------------------
   const u32 rank0 = a.tile_rank0[tile];
-  u32 run = rank0 + hexcl; // heads before this item
-  const bool count_children = a.child_count != nullptr;
-  // the tile's first element belongs to node rank0 - 1 (or rank0 when it is a head): slots of the
-  // tile start at or after slot_base; big nodes put a whole tile into one or two slots, so the
-  // global atomics shrink to a few per tile
-  const u32 slot_base = (rank0 ? rank0 - 1u : 0u) * 8u;
+  u32 rank = rank0 + hexcl - 1u; // node of the element before my first one (0xFFFFFFFF: none yet)
+  bool take = a.force_all != 0;
+  if (!take && a.allow_take_all && nvalid && !(nh & 1u))
+    take = (u64)node_point_count(a.node_start, a.node_gcount, rank) <= a.max_points_per_node;
+  u32 other = 0; // strategy flags of the 8 elements (one byte each in a.sel)
+  if (a.sampling != SW_RANDOM_GRID && !a.force_all && nvalid) {
+    if (nvalid == 8) {
+      const u64 bytes = *reinterpret_cast<const u64*>(a.sel + e0);
+#pragma unroll
+      for (int j = 0; j < BLK_ITEMS; ++j)
+        other |= (((bytes >> (8 * j)) & 0xFFu) == 1u ? 1u : 0u) << j;
+    } else {
+      for (u32 j = 0; j < nvalid; ++j)
+        other |= (a.sel[e0 + j] == 1 ? 1u : 0u) << j;
+    }
+  }
+  const u32 pick = (a.sampling == SW_RANDOM_GRID) ? ch : other; // Sampling.h:253-284: first point of each cell run
+  u32 sel = 0;
+  u32 slot0 = 0;          // child slot of my first element
+  bool one_slot = true;   // all my elements fall into the same child of the same node
   const int child_shift = a.node_shift - 3;
 #pragma unroll
-  for (int j = 0; j < SWP_ITEMS; ++j) {
-    const u64 i = base + item_pos(warp, lane, j);
-    const u32 node_rank = run + __popc(nmask[j] & (lt | (1u << lane))) - 1;
-    run += __popc(nmask[j]);
-    bool sel = false;
-    const bool valid = i < a.count;
-    if (valid) {
-      bool take = a.force_all != 0;
-      if (!take && a.allow_take_all) {
-        const u32 cnt = node_point_count(a.node_start, a.node_gcount, node_rank);
-        take = (u64)cnt <= a.max_points_per_node;
-      }
-      if (take)
-        sel = true;
-      else if (a.sampling == SW_RANDOM_GRID)
-        sel = (cmask[j] >> lane) & 1u; // first point of each cell run (Sampling.h:253-284)
-      else
-        sel = a.sel[i] == 1;
+  for (int j = 0; j < BLK_ITEMS; ++j) {
+    if ((nh >> j) & 1u) {
+      ++rank;
+      if (!a.force_all && a.allow_take_all)
+        take = (u64)node_point_count(a.node_start, a.node_gcount, rank) <= a.max_points_per_node;
     }
-    const u32 smask = __ballot_sync(0xffffffffu, sel);
-    if (lane == 0)
-      a.selbits[((size_t)tile * SWP_WARPS + warp) * SWP_ITEMS + j] = smask;
-    wsel += __popc(smask);
-    if (count_children) {
-      // points that stay go to child (node_rank, octant); keys are sorted, so equal children are
-      // runs of lanes: one atomic per run
-      const u32 rem = __ballot_sync(0xffffffffu, valid && !sel);
-      const u32 slot = node_rank * 8u + (u32)((key[j] >> child_shift) & 7u);
-      const u32 prev_slot = __shfl_up_sync(0xffffffffu, slot, 1);
-      const u32 heads = __ballot_sync(0xffffffffu, lane == 0 || slot != prev_slot);
-      if ((heads >> lane) & 1u) {
-        const u32 above = heads & ~((2u << lane) - 1u); // heads in higher lanes (2u << 31 wraps to 0)
-        const u32 end_mask = above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu;
-        const u32 c = __popc(rem & end_mask & ~lt);
-        if (c) {
-          if (slot - slot_base < CHILD_WINDOW)
-            atomicAdd(&s_child[slot - slot_base], c);
-          else
-            atomicAdd(&a.child_count[slot], c);
-        }
-      }
+    sel |= ((take ? 1u : ((pick >> j) & 1u)) << j);
+    if (a.child_count) {
+      const u32 slot = rank * 8u + (u32)((k[j] >> child_shift) & 7u);
+      if (j == 0)
+        slot0 = slot;
+      else if (((valid >> j) & 1u) && slot != slot0)
+        one_slot = false;
     }
   }
-  if (lane == 0 && wsel)
-    atomicAdd(&s_sel, wsel);
-  __syncthreads();
-  if (threadIdx.x == 0)
-    a.tile_sel[tile] = s_sel;
-  if (count_children)
-    for (u32 i = threadIdx.x; i < CHILD_WINDOW; i += SWP_THREADS) {
+  sel &= valid;
+  reinterpret_cast<unsigned char*>(a.selbits)[(size_t)tile * SWP_THREADS + tid] = (unsigned char)sel;
+
+  // ---- selected points of the tile ---------------------------------------------------------------------
+  u32 sexcl;
+  const u32 tile_selected = block_scan_packed(__popc(sel), s_w2, sexcl);
+  if (tid == 0)
+    a.tile_sel[tile] = tile_selected;
+
+  // ---- points that stay, counted per child node ----------------------------------------------------------
+  if (a.child_count) {
+    const u32 slot_base = (rank0 ? rank0 - 1u : 0u) * 8u; // slots of this tile start here or later
+    const u32 rem = valid & ~sel;
+    const u32 lead_slot = __shfl_sync(0xffffffffu, slot0, 0);
+    const bool uniform = __all_sync(0xffffffffu, nvalid == 0 || (one_slot && slot0 == lead_slot));
+    if (uniform) { // the whole warp (256 points) lies in one child: one atomic
+      u32 c = __popc(rem);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0 && c) {
+        if (lead_slot - slot_base < CHILD_WINDOW)
+          atomicAdd(&s_child[lead_slot - slot_base], c);
+        else
+          atomicAdd(&a.child_count[lead_slot], c);
+      }
+    } else { // runs of equal child inside the thread
+      u32 r2 = rank0 + hexcl - 1u;
+      u32 cur = 0xFFFFFFFFu, cnt = 0;
+#pragma unroll
+      for (int j = 0; j < BLK_ITEMS; ++j) {
+        if ((nh >> j) & 1u)
+          ++r2;
+        if ((rem >> j) & 1u) {
+          const u32 slot = r2 * 8u + (u32)((k[j] >> child_shift) & 7u);
+          if (slot != cur) {
+            if (cnt) {
+              if (cur - slot_base < CHILD_WINDOW)
+                atomicAdd(&s_child[cur - slot_base], cnt);
+              else
+                atomicAdd(&a.child_count[cur], cnt);
+            }
+            cur = slot;
+            cnt = 0;
+          }
+          ++cnt;
+        }
+      }
+      if (cnt) {
+        if (cur - slot_base < CHILD_WINDOW)
+          atomicAdd(&s_child[cur - slot_base], cnt);
+        else
+          atomicAdd(&a.child_count[cur], cnt);
+      }
+    }
+    __syncthreads();
+    for (u32 i = tid; i < CHILD_WINDOW; i += SWP_THREADS) {
       const u32 c = s_child[i];
       if (c)
         atomicAdd(&a.child_count[slot_base + i], c);
     }
+  }
 }
 
 // One block.  (A) exclusive scan of tile_sel in place, total -> *n_selected.  (B) child counts ->
@@ -419,64 +507,81 @@ level_scan_kernel(u32* __restrict__ tile_sel, u32 n_tiles, u64* __restrict__ n_s
 __global__ void __launch_bounds__(SWP_THREADS)
 level_scatter_kernel(SwLevelArgs a)
 {
+  __shared__ u64 s_k[BLK_SLOTS];
+  __shared__ u32 s_i[BLK_SLOTS];
+  __shared__ u64 s_prev;
   __shared__ u32 s_w[SWP_WARPS];
-  __shared__ u32 s_w2[SWP_WARPS];
-  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 tid = threadIdx.x;
   const u32 tile = blockIdx.x;
   const u64 base = (u64)tile * SW_SWEEP_TILE;
-  const u32 lt = lanemask_lt();
+  const u64 e0 = base + 8ull * tid;
+  const u32 tile_valid = (a.count - base) < SW_SWEEP_TILE ? (u32)(a.count - base) : SW_SWEEP_TILE;
 
-  u64 key[SWP_ITEMS];
-  u32 idx[SWP_ITEMS];
-  u32 nmask[SWP_ITEMS];
-  u32 smask[SWP_ITEMS];
-  u32 wheads = 0, wsel = 0;
+  // ---- load: keys and ids, coalesced, transposed to the blocked layout ----------------------------------
+  if (a.in_idx) {
 #pragma unroll
-  for (int j = 0; j < SWP_ITEMS; ++j) {
-    const u64 i = base + item_pos(warp, lane, j);
-    bool nh = false;
-    key[j] = 0;
-    idx[j] = 0;
-    if (i < a.count) {
-      const u64 k = a.in_key[i] & SW_KEY_MASK;
-      key[j] = k;
-      idx[j] = a.in_idx ? a.in_idx[i] : (u32)i;
-      nh = (i == 0) || ((k >> a.node_shift) != ((a.in_key[i - 1] & SW_KEY_MASK) >> a.node_shift));
+    for (int j = 0; j < BLK_ITEMS; ++j) {
+      const u32 p = j * SWP_THREADS + tid;
+      s_i[BLK_PAD(p)] = (p < tile_valid) ? a.in_idx[base + p] : 0u;
     }
-    nmask[j] = __ballot_sync(0xffffffffu, nh);
-    smask[j] = a.selbits[((size_t)tile * SWP_WARPS + warp) * SWP_ITEMS + j];
-    wheads += __popc(nmask[j]);
-    wsel += __popc(smask[j]);
   }
-  u32 hexcl, sexcl;
-  warp_totals_exclusive2(wheads, wsel, warp, lane, s_w, s_w2, hexcl, sexcl);
-
-  u64 srun = (u64)a.tile_sel[tile] + sexcl; // selected before this item (tile_sel holds the exclusive scan)
-  u32 hrun = a.tile_rank0[tile] + hexcl;    // node heads before this item
+  u64 k[BLK_ITEMS];
+  u64 prev;
+  load_keys_blocked(a.in_key, base, a.count, s_k, &s_prev, k, prev);
+  u32 idx[BLK_ITEMS];
 #pragma unroll
-  for (int j = 0; j < SWP_ITEMS; ++j) {
-    const u64 i = base + item_pos(warp, lane, j);
-    if (i < a.count) {
-      const u64 srank = srun + __popc(smask[j] & lt);
-      if ((smask[j] >> lane) & 1u) {
-        a.out_key[a.out_offset + srank] = key[j];
-        a.out_idx[a.out_offset + srank] = idx[j];
-      } else if (a.rem_key) {
-        a.rem_key[i - srank] = key[j];
-        a.rem_idx[i - srank] = idx[j];
-      }
-      if ((nmask[j] >> lane) & 1u) {
-        const u32 node_rank = hrun + __popc(nmask[j] & lt);
+  for (int j = 0; j < BLK_ITEMS; ++j)
+    idx[j] = a.in_idx ? s_i[9 * tid + j] : (u32)(e0 + j);
+  const u32 nvalid = e0 >= a.count ? 0u : (a.count - e0 < 8 ? (u32)(a.count - e0) : 8u);
+  const u32 valid = (1u << nvalid) - 1u;
+  const u32 nh = head_bits(k, prev, a.node_shift, e0 == 0) & valid;
+  const u32 sel = reinterpret_cast<const unsigned char*>(a.selbits)[(size_t)tile * SWP_THREADS + tid];
+
+  // ---- ranks inside the tile: node heads and selected points before my first element ----------------------
+  u32 excl;
+  const u32 tot = block_scan_packed((__popc(nh) << 16) | __popc(sel), s_w, excl); // also: s_k / s_i are free now
+  const u32 hexcl = excl >> 16, sexcl = excl & 0xFFFFu;
+  const u32 tile_selected = tot & 0xFFFFu;
+  const u64 tile_off = a.tile_sel[tile]; // selected before this tile (exclusive scan)
+
+  // ---- node table rows (from registers) and staging in output order -----------------------------------------
+  u32 rank = a.tile_rank0[tile] + hexcl - 1u;
+#pragma unroll
+  for (int j = 0; j < BLK_ITEMS; ++j) {
+    if ((valid >> j) & 1u) {
+      const u32 sbefore = sexcl + __popc(sel & ((1u << j) - 1u));
+      if ((nh >> j) & 1u) {
+        ++rank;
         bool take = false;
         if (!a.force_all && a.allow_take_all)
-          take = (u64)node_point_count(a.node_start, a.node_gcount, node_rank) <= a.max_points_per_node;
-        a.node_index[a.node_base + node_rank] = key[j] >> a.node_shift;
+          take = (u64)node_point_count(a.node_start, a.node_gcount, rank) <= a.max_points_per_node;
+        a.node_index[a.node_base + rank] = k[j] >> a.node_shift;
         // bit 63 = SW_NODE_TAKE_ALL (decoded by the host when it builds the node table)
-        a.node_first[a.node_base + node_rank] = (a.out_offset + srank) | ((u64)(take ? 1u : 0u) << 63);
+        a.node_first[a.node_base + rank] = (a.out_offset + tile_off + sbefore) | ((u64)(take ? 1u : 0u) << 63);
       }
+      // selected points first, then the points that stay, both in input order
+      const u32 p = ((sel >> j) & 1u) ? sbefore : tile_selected + (8u * tid + j - sbefore);
+      s_k[BLK_PAD(p)] = k[j];
+      s_i[BLK_PAD(p)] = idx[j];
     }
-    srun += __popc(smask[j]);
-    hrun += __popc(nmask[j]);
+  }
+  __syncthreads();
+
+  // ---- coalesced copy-out: one contiguous range of the output chunk, one of the remainder list -------------
+  u64* const out_key = a.out_key + a.out_offset + tile_off;
+  u32* const out_idx = a.out_idx + a.out_offset + tile_off;
+  const u64 rem_base = base - tile_off;
+#pragma unroll
+  for (int m = 0; m < BLK_ITEMS; ++m) {
+    const u32 q = m * SWP_THREADS + tid;
+    if (q < tile_selected) {
+      out_key[q] = s_k[BLK_PAD(q)];
+      out_idx[q] = s_i[BLK_PAD(q)];
+    } else if (q < tile_valid && a.rem_key) {
+      const u32 r = q - tile_selected;
+      a.rem_key[rem_base + r] = s_k[BLK_PAD(q)];
+      a.rem_idx[rem_base + r] = s_i[BLK_PAD(q)];
+    }
   }
 }
 
