@@ -129,6 +129,17 @@ int swgpu_max_shard_levels(swgpu_handle h, uint32_t* shard_levels);
 int swgpu_partition_device(swgpu_handle h, const uint64_t* keys_device, const double* xyz_device, uint64_t n,
                            const uint32_t* first_prefix, uint32_t n_ranks, uint32_t id_base, double* out_xyz_device,
                            uint32_t* out_id_device, uint64_t* send_counts_host);
+/* Partition + exchange in ONE kernel over peer memory: the same stable partition, written straight
+ * into the destinations' receive buffers.  peer_xyz_device[r] / peer_ids_device[r] are device
+ * pointers to rank r's receive buffers as mapped into THIS process (CUDA IPC / VMM peer mappings over
+ * NVLink; the local buffers for r == own rank); dst_offsets[r] is the first point of this source's
+ * block inside rank r's buffer (= points rank r receives from lower ranks; known from the all-gathered
+ * prefix histograms).  The caller orders the kernel against the peers (a barrier before, so that the
+ * receive buffers are free; one after, before anybody reads).  send_counts_host may be NULL. */
+int swgpu_partition_to_peers_device(swgpu_handle h, const uint64_t* keys_device, const double* xyz_device, uint64_t n,
+                                    const uint32_t* first_prefix, uint32_t n_ranks, uint32_t id_base,
+                                    void* const* peer_xyz_device, void* const* peer_ids_device,
+                                    const uint64_t* dst_offsets, uint64_t* send_counts_host);
 /* Marks the handle as tiling one shard.  start_level: FAST's global start level (-1 = estimate from
  * the local points); global_ids_device: id of every received point (returned by swgpu_get_nodes
  * instead of local indices; may be NULL).  shard_levels = 0 switches sharding off. */

@@ -245,15 +245,26 @@ load_keys_blocked(const u64* __restrict__ in_key, u64 base, u64 count, u64* s_k,
   prev = tid ? s_k[9 * tid - 2] : *s_prev; // BLK_PAD(8 * tid - 1)
 }
 
-// head bits of the thread's elements: bit j set = element j starts a new run of (key >> shift)
-__device__ __forceinline__ u32
-head_bits(const u64 k[BLK_ITEMS], u64 prev, int shift, bool first_of_list)
+// Head bits of the thread's elements: bit j of nh (ch) is set when element j starts a new run of
+// key >> node_shift (key >> cell_shift).  Prefixes differ iff the XOR of the keys has a bit at or
+// above the shift, so both tests share one XOR per element.
+__device__ __forceinline__ void
+head_bits2(const u64 k[BLK_ITEMS], u64 prev, int node_shift, int cell_shift, bool first_of_list, u32& nh, u32& ch)
 {
-  u32 bits = first_of_list ? 1u : (((k[0] >> shift) != (prev >> shift)) ? 1u : 0u);
+  const u64 nmask = ~0ull << node_shift, cmask = ~0ull << cell_shift; // shifts are <= 63
+  u32 n = 0, c = 0;
 #pragma unroll
-  for (int j = 1; j < BLK_ITEMS; ++j)
-    bits |= (((k[j] >> shift) != (k[j - 1] >> shift)) ? 1u : 0u) << j;
-  return bits;
+  for (int j = 0; j < BLK_ITEMS; ++j) {
+    const u64 x = k[j] ^ (j ? k[j - 1] : prev);
+    n |= ((x & nmask) ? 1u : 0u) << j;
+    c |= ((x & cmask) ? 1u : 0u) << j;
+  }
+  if (first_of_list) {
+    n |= 1u;
+    c |= 1u;
+  }
+  nh = n;
+  ch = c | n;
 }
 
 // exclusive block scan of a packed pair of counters (each total < 2^16); returns the block total
@@ -305,8 +316,10 @@ level_count_kernel(SwLevelArgs a)
   const u32 valid = (1u << nvalid) - 1u;
 
   // ---- node heads, cell heads --------------------------------------------------------------------
-  const u32 nh = head_bits(k, prev, a.node_shift, e0 == 0) & valid;
-  const u32 ch = (head_bits(k, prev, a.cell_shift, e0 == 0) | nh) & valid;
+  u32 nh, ch;
+  head_bits2(k, prev, a.node_shift, a.cell_shift, e0 == 0, nh, ch);
+  nh &= valid;
+  ch &= valid;
   u32 hexcl;
   block_scan_packed(__popc(nh), s_w, hexcl);
 
@@ -430,11 +443,17 @@ level_scan_kernel(u32* __restrict__ tile_sel, u32 n_tiles, u64* __restrict__ n_s
     s_carry_b = 0;
   }
   __syncthreads();
-  // ---- (A) ----
-  for (u32 t0 = 0; t0 < n_tiles; t0 += SCAN_THREADS) {
-    const u32 t = t0 + threadIdx.x;
-    const u32 v = (t < n_tiles) ? tile_sel[t] : 0u;
-    u32 incl = v;
+  // ---- (A) ---- (8 consecutive tiles per thread per iteration)
+  for (u32 t0 = 0; t0 < n_tiles; t0 += SCAN_THREADS * 8) {
+    const u32 t = t0 + threadIdx.x * 8;
+    u32 v[8];
+    u32 sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      v[q] = (t + q < n_tiles) ? tile_sel[t + q] : 0u;
+      sum += v[q];
+    }
+    u32 incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const u32 up = __shfl_up_sync(0xffffffffu, incl, o);
@@ -448,8 +467,13 @@ level_scan_kernel(u32* __restrict__ tile_sel, u32 n_tiles, u64* __restrict__ n_s
     for (u32 w = 0; w < warp; ++w)
       wofs += s_wa[w];
     const u32 carry = s_carry_a;
-    if (t < n_tiles)
-      tile_sel[t] = carry + wofs + incl - v;
+    u32 run = carry + wofs + incl - sum;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (t + q < n_tiles)
+        tile_sel[t + q] = run;
+      run += v[q];
+    }
     __syncthreads();
     if (threadIdx.x == SCAN_THREADS - 1)
       s_carry_a = carry + wofs + incl;
@@ -504,7 +528,7 @@ level_scan_kernel(u32* __restrict__ tile_sel, u32 n_tiles, u64* __restrict__ n_s
   }
 }
 
-__global__ void __launch_bounds__(SWP_THREADS)
+__global__ void __launch_bounds__(SWP_THREADS, 4)
 level_scatter_kernel(SwLevelArgs a)
 {
   __shared__ u64 s_k[BLK_SLOTS];
@@ -534,7 +558,9 @@ level_scatter_kernel(SwLevelArgs a)
     idx[j] = a.in_idx ? s_i[9 * tid + j] : (u32)(e0 + j);
   const u32 nvalid = e0 >= a.count ? 0u : (a.count - e0 < 8 ? (u32)(a.count - e0) : 8u);
   const u32 valid = (1u << nvalid) - 1u;
-  const u32 nh = head_bits(k, prev, a.node_shift, e0 == 0) & valid;
+  u32 nh, ch_unused;
+  head_bits2(k, prev, a.node_shift, a.node_shift, e0 == 0, nh, ch_unused);
+  nh &= valid;
   const u32 sel = reinterpret_cast<const unsigned char*>(a.selbits)[(size_t)tile * SWP_THREADS + tid];
 
   // ---- ranks inside the tile: node heads and selected points before my first element ----------------------

@@ -49,7 +49,7 @@ launch_prefix_histogram(const u64* keys, u64 n, u32* bins, cudaStream_t stream)
 // ---------------------------------------------------------------------------------------------
 #define PT_THREADS 256
 #define PT_WARPS 8
-#define PT_ITEMS 8
+#define PT_ITEMS 4
 #define PT_TILE (PT_THREADS * PT_ITEMS)
 
 struct SwSplitters
@@ -146,17 +146,33 @@ partition_scan_kernel(u32* __restrict__ tile_counts, u32 n_tiles, u64* __restric
     send_counts[d] = s_carry;
 }
 
-// Scatter: out position = dest_base[d] + tile offset + rank inside the tile (tile order = index
-// order, so the partition is stable).
+// Scatter.  Position of a point = base of (this source, destination d) + offset of the tile + rank
+// inside the tile (tile order = index order, so the partition is stable).  The tile is staged in
+// shared memory ordered by destination, then every destination's segment leaves as one contiguous,
+// coalesced write.  The destination bases are plain device pointers: slices of a local send buffer
+// (NCCL all-to-all follows) or PEER memory mapped over NVLink (partition + exchange in one kernel,
+// no send buffer, no collective on the data path).
+struct SwPartitionDst
+{
+  double* xyz[SW_MAX_RANKS]; // where this source's points for destination d start
+  u32* ids[SW_MAX_RANKS];
+};
+
 __global__ void __launch_bounds__(PT_THREADS)
 partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict__ xyz, u64 n, SwSplitters sp,
                          const u32* __restrict__ tile_offsets, const u64* __restrict__ send_counts, u32 id_base,
-                         double* __restrict__ out_xyz, u32* __restrict__ out_id)
+                         SwPartitionDst dst)
 {
+  __shared__ double s_x[3 * PT_TILE];
+  __shared__ u32 s_id[PT_TILE];
+  __shared__ unsigned char s_d[PT_TILE];
   __shared__ u32 s_wcnt[PT_WARPS][SW_MAX_RANKS];
-  __shared__ u64 s_base[SW_MAX_RANKS];
+  __shared__ u32 s_seg[SW_MAX_RANKS + 1]; // first staged position of every destination's segment
+  __shared__ double* s_gx[SW_MAX_RANKS];
+  __shared__ u32* s_gi[SW_MAX_RANKS];
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u64 base = (u64)blockIdx.x * PT_TILE;
+  const u32 tile_valid = (n - base) < PT_TILE ? (u32)(n - base) : PT_TILE;
   const u32 lt = lanemask_lt();
   // warp-striped: item j of a warp covers 32 consecutive points; a warp owns PT_ITEMS * 32 of them
   u32 dest[PT_ITEMS];
@@ -180,17 +196,31 @@ partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict_
       mine = (lane == r) ? cnt[r] : mine;
     s_wcnt[warp][lane] = mine;
   }
-  if (threadIdx.x < SW_MAX_RANKS) {
-    u64 b = 0;
-    for (u32 r = 0; r < threadIdx.x; ++r)
-      b += send_counts[r];
-    s_base[threadIdx.x] = b + tile_offsets[(u64)blockIdx.x * SW_MAX_RANKS + threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 run = 0;
+    u64 sent_before = 0; // local send buffer: destinations are laid out one after the other
+    for (u32 r = 0; r < SW_MAX_RANKS; ++r) {
+      s_seg[r] = run;
+      u32 tot = 0;
+      for (u32 w = 0; w < PT_WARPS; ++w)
+        tot += s_wcnt[w][r];
+      run += tot;
+      if (r < sp.n_ranks) {
+        const u64 off = sent_before + tile_offsets[(u64)blockIdx.x * SW_MAX_RANKS + r];
+        s_gx[r] = dst.xyz[r] + 3 * off;
+        s_gi[r] = dst.ids[r] + off;
+        if (send_counts)
+          sent_before += send_counts[r];
+      }
+    }
+    s_seg[SW_MAX_RANKS] = run;
   }
   __syncthreads();
-  u32 run[SW_MAX_RANKS]; // rank of the next point of this warp per destination, inside the tile
+  u32 run[SW_MAX_RANKS]; // staged position of the next point of this warp per destination
 #pragma unroll
   for (u32 r = 0; r < SW_MAX_RANKS; ++r) {
-    u32 o = 0;
+    u32 o = s_seg[r];
     for (u32 w = 0; w < warp; ++w)
       o += s_wcnt[w][r];
     run[r] = o;
@@ -198,23 +228,34 @@ partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict_
 #pragma unroll
   for (int j = 0; j < PT_ITEMS; ++j) {
     const u64 i = base + warp * (32 * PT_ITEMS) + j * 32 + lane;
-    u64 pos = 0;
+    u32 pos = 0;
 #pragma unroll
     for (u32 r = 0; r < SW_MAX_RANKS; ++r) {
       if (r < sp.n_ranks) {
         const u32 m = __ballot_sync(0xffffffffu, dest[j] == r);
         if (dest[j] == r)
-          pos = s_base[r] + run[r] + __popc(m & lt);
+          pos = run[r] + __popc(m & lt);
         run[r] += __popc(m);
       }
     }
     if (i < n) {
-      const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
-      out_xyz[3 * pos] = x;
-      out_xyz[3 * pos + 1] = y;
-      out_xyz[3 * pos + 2] = z;
-      out_id[pos] = id_base + (u32)i;
+      s_x[3 * pos] = xyz[3 * i];
+      s_x[3 * pos + 1] = xyz[3 * i + 1];
+      s_x[3 * pos + 2] = xyz[3 * i + 2];
+      s_id[pos] = id_base + (u32)i;
+      s_d[pos] = (unsigned char)dest[j];
     }
+  }
+  __syncthreads();
+  // copy-out: consecutive threads write consecutive doubles of a destination's segment
+  for (u32 e = threadIdx.x; e < 3 * tile_valid; e += PT_THREADS) {
+    const u32 q = e / 3, c = e - 3 * q;
+    const u32 d = s_d[q];
+    s_gx[d][3 * (q - s_seg[d]) + c] = s_x[e];
+  }
+  for (u32 q = threadIdx.x; q < tile_valid; q += PT_THREADS) {
+    const u32 d = s_d[q];
+    s_gi[d][q - s_seg[d]] = s_id[q];
   }
 }
 
@@ -225,24 +266,56 @@ partition_tiles(u64 n)
   return t ? t : 1;
 }
 
-void
-launch_partition_by_splitters(const u64* keys, const double* xyz, u64 n, const u32* first_prefix, u32 n_ranks,
-                              u32 id_base, u32* tile_counts, u64* send_counts, double* out_xyz, u32* out_id,
-                              cudaStream_t stream)
+static SwSplitters
+make_splitters(const u32* first_prefix, u32 n_ranks)
 {
   SwSplitters sp{};
   sp.n_ranks = n_ranks;
   for (u32 r = 0; r < SW_MAX_RANKS; ++r)
     sp.first_prefix[r] = r < n_ranks ? first_prefix[r] : 0xFFFFFFFFu;
+  return sp;
+}
+
+void
+launch_partition_by_splitters(const u64* keys, const double* xyz, u64 n, const u32* first_prefix, u32 n_ranks,
+                              u32 id_base, u32* tile_counts, u64* send_counts, double* out_xyz, u32* out_id,
+                              cudaStream_t stream)
+{
+  const SwSplitters sp = make_splitters(first_prefix, n_ranks);
   const u32 tiles = (u32)partition_tiles(n);
   if (n == 0) {
     cudaMemsetAsync(send_counts, 0, SW_MAX_RANKS * sizeof(u64), stream);
     return;
   }
+  SwPartitionDst dst{};
+  for (u32 r = 0; r < SW_MAX_RANKS; ++r) { // one send buffer: the kernel adds the per-destination prefix
+    dst.xyz[r] = out_xyz;
+    dst.ids[r] = out_id;
+  }
   partition_count_kernel<<<tiles, PT_THREADS, 0, stream>>>(keys, n, sp, tile_counts);
   partition_scan_kernel<<<SW_MAX_RANKS, 1024, 0, stream>>>(tile_counts, tiles, send_counts);
-  partition_scatter_kernel<<<tiles, PT_THREADS, 0, stream>>>(keys, xyz, n, sp, tile_counts, send_counts, id_base, out_xyz,
-                                                            out_id);
+  partition_scatter_kernel<<<tiles, PT_THREADS, 0, stream>>>(keys, xyz, n, sp, tile_counts, send_counts, id_base, dst);
+}
+
+void
+launch_partition_to_peers(const u64* keys, const double* xyz, u64 n, const u32* first_prefix, u32 n_ranks, u32 id_base,
+                          u32* tile_counts, u64* send_counts, double* const* peer_xyz, u32* const* peer_ids,
+                          const u64* dst_offsets, cudaStream_t stream)
+{
+  const SwSplitters sp = make_splitters(first_prefix, n_ranks);
+  const u32 tiles = (u32)partition_tiles(n);
+  if (n == 0) {
+    cudaMemsetAsync(send_counts, 0, SW_MAX_RANKS * sizeof(u64), stream);
+    return;
+  }
+  SwPartitionDst dst{};
+  for (u32 r = 0; r < n_ranks; ++r) { // this source's block inside destination r's receive buffer
+    dst.xyz[r] = peer_xyz[r] + 3 * dst_offsets[r];
+    dst.ids[r] = peer_ids[r] + dst_offsets[r];
+  }
+  partition_count_kernel<<<tiles, PT_THREADS, 0, stream>>>(keys, n, sp, tile_counts);
+  partition_scan_kernel<<<SW_MAX_RANKS, 1024, 0, stream>>>(tile_counts, tiles, send_counts);
+  partition_scatter_kernel<<<tiles, PT_THREADS, 0, stream>>>(keys, xyz, n, sp, tile_counts, nullptr, id_base, dst);
 }
 
 // ---------------------------------------------------------------------------------------------

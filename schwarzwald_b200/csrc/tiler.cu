@@ -1168,6 +1168,41 @@ swgpu_partition_device(swgpu_handle h, const uint64_t* keys_device, const double
 }
 
 int
+swgpu_partition_to_peers_device(swgpu_handle h, const uint64_t* keys_device, const double* xyz_device, uint64_t n,
+                                const uint32_t* first_prefix, uint32_t n_ranks, uint32_t id_base,
+                                void* const* peer_xyz_device, void* const* peer_ids_device, const uint64_t* dst_offsets,
+                                uint64_t* send_counts_host)
+{
+  if (!h || !first_prefix || !peer_xyz_device || !peer_ids_device || !dst_offsets || n_ranks == 0 ||
+      n_ranks > SWGPU_MAX_RANKS || (n && (!keys_device || !xyz_device)))
+    return SW_ERR_INVALID_ARGUMENT;
+  if (n >= (1ull << 32))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "a partition is limited to 2^32 - 1 points per GPU");
+  cudaSetDevice(h->device);
+  CK(h->part_tile_counts.ensure(partition_tiles(n) * SW_MAX_RANKS * 4));
+  CK(h->part_send_counts.ensure(SW_MAX_RANKS * 8));
+  double* px[SW_MAX_RANKS];
+  u32* pi[SW_MAX_RANKS];
+  u64 off[SW_MAX_RANKS];
+  for (u32 r = 0; r < n_ranks; ++r) {
+    px[r] = static_cast<double*>(peer_xyz_device[r]);
+    pi[r] = static_cast<u32*>(peer_ids_device[r]);
+    off[r] = dst_offsets[r];
+  }
+  launch_partition_to_peers(reinterpret_cast<const u64*>(keys_device), xyz_device, n, first_prefix, n_ranks, id_base,
+                            h->part_tile_counts.as<u32>(), h->part_send_counts.as<u64>(), px, pi, off, h->stream);
+  CK(cudaGetLastError());
+  if (send_counts_host) { // optional check value; costs a stream synchronisation
+    u64 counts[SW_MAX_RANKS];
+    CK(cudaMemcpyAsync(counts, h->part_send_counts.p, SW_MAX_RANKS * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (u32 r = 0; r < n_ranks; ++r)
+      send_counts_host[r] = counts[r];
+  }
+  return SW_OK;
+}
+
+int
 swgpu_set_shard(swgpu_handle h, uint32_t shard_levels, int32_t start_level, swgpu_allreduce_u32_fn allreduce,
                 void* allreduce_ctx, const uint32_t* global_ids_device)
 {

@@ -76,6 +76,8 @@ SYMBOLS = [
     ("swgpu_max_shard_levels", C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     ("swgpu_partition_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
                                          C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("swgpu_partition_to_peers_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
+                                                  C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swgpu_set_shard", C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, ALLREDUCE_FN, C.c_void_p, C.c_void_p]),
     ("swgpu_enable_timing", C.c_int, [C.c_void_p, C.c_int]),
     ("swgpu_get_stats", C.c_int, [C.c_void_p, C.POINTER(SwgpuStats)]),
