@@ -51,56 +51,109 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.
+
+    NVML is polled from a thread every ~2 ms (a bench step is ~10 ms, `nvidia-smi -lms` cannot start
+    that fast); `nvidia-smi --query-gpu` is the fallback when pynvml is unavailable."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bit masks (nvml.h)
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20,
+                   "hw_thermal_slowdown": 0x40}
 
     def __init__(self, device_index=0):
         self.device_index = device_index
-        self.proc = None
-        self.lines = []
+        self.samples = []  # (perf_counter, sm_mhz, reason bitmask)
+        self.sm_max = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.mode = None
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.device_index])
+            except (ValueError, IndexError):
+                pass
+        return self.device_index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self._sample_nvml()
         except Exception:
-            self.proc = None
+            self.mode = "smi"
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+    def _sample_nvml(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
         try:
-            self.proc.wait(timeout=5)
+            reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
         except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+            reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.samples.append((time.perf_counter(), sm, reasons))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self._nvml_index()), "--query-gpu=" + self.QUERY,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        if len(f) < 9:
+            return
+        mask = 0
+        for k, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if f[5 + k].lower().startswith("active"):
+                mask |= self.REASON_BITS[name]
+        self.samples.append((time.perf_counter(), float(f[1]), mask))
+        self.sm_max = float(f[2])
+
+    def _poll(self):
+        while not self.stop_flag.is_set():
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for k, name in enumerate(names):
-                if f[5 + k].lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                if self.mode == "nvml":
+                    self._sample_nvml()
+                    time.sleep(0.002)
+                else:
+                    self._sample_smi()
+            except Exception:
+                time.sleep(0.05)
+
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken in [t0, t1] (perf_counter times of the timed region)."""
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler not started"], "samples": 0}
+        self.stop_flag.set()
+        self.thread.join(timeout=15)
+        inside = [x for x in self.samples if (t0 is None or x[0] >= t0) and (t1 is None or x[0] <= t1)]
+        if not inside:
+            inside = self.samples
+        sm = sorted(x[1] for x in inside)
+        mask = 0
+        for x in inside:
+            mask |= x[2]
+        reasons = sorted(name for name, bit in self.REASON_BITS.items() if mask & bit)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(sm), "source": self.mode}
+
+
+def captured_traffic(n_points):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (same point count only)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        if int(t["points"]) == int(n_points):
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
 
 
 def cpu_reference_run(n_points, steps, warmup, full_points, bounds=None):
@@ -232,6 +285,7 @@ def main():
     sort_ms, launches = 0.0, 0
     stats = None
     barrier()
+    t_begin = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
@@ -240,7 +294,7 @@ def main():
         launches += stats["kernel_launches"]
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     phase_ms = None
     if world > 1:  # one extra, untimed step with per-phase events (index / exchange / tile)
@@ -303,7 +357,8 @@ def main():
                    "output_ids": int(stats["n_output_ids"]),
                    "l2": "inputs (2.4 GB positions, 0.8 GB keys) are far larger than the 126 MB L2"},
         "roofline": {"bound": "hbm", "kernel": "onesweep_pass_kernel (8 launches per step)", "achieved": achieved,
-                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": captured_traffic(n_local),
                      "algorithmic_bytes_per_launch": 24 * n_local,
                      "whole_step": {"algorithmic_bytes": int(total_bytes),
                                     "achieved": total_bytes / (ms_per_step * 1e-3) / 1e9,
