@@ -28,7 +28,10 @@ typedef enum sw_sampling {
   SW_RANDOM_GRID = 0,  /* RandomSortedGridSampling, Sampling.h:187-308 */
   SW_GRID_CENTER = 1,  /* GridCenterSampling,       Sampling.h:314-416 */
   SW_MIN_DISTANCE = 2, /* PoissonDiskSampling,      Sampling.h:421-471 */
-  SW_JITTERED = 3      /* JitteredSampling,         Sampling.h:598-759 */
+  SW_JITTERED = 3,     /* JitteredSampling,         Sampling.h:598-759 */
+  SW_MIN_DISTANCE_FAST = 4 /* AdaptivePoissonDiskSampling, Sampling.h:477-542, with the CLI's density
+                            * function (process/TilerProcess.cpp:500-508): every 4th point of a node is
+                            * analysed at the root, every 2nd at node level 0, every point below */
 } sw_sampling;
 
 typedef enum sw_tiling {

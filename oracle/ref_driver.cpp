@@ -61,6 +61,16 @@ make_strategy(int32_t sampling, size_t max_points)
       return PoissonDiskSampling{ max_points };
     case SW_JITTERED:
       return JitteredSampling{ max_points };
+    case SW_MIN_DISTANCE_FAST: /* the strategy object TilerProcess::make_sampling_strategy builds for
+                                  "MIN_DISTANCE_FAST" (process/TilerProcess.cpp:500-508; TilerProcess.cpp
+                                  itself needs boost/taskflow and is not compiled here) */
+      return AdaptivePoissonDiskSampling{ max_points, [](int32_t node_level) -> float {
+                                           if (node_level < 0)
+                                             return 0.25f;
+                                           if (node_level < 1)
+                                             return 0.5f;
+                                           return 1.f;
+                                         } };
   }
   throw swo::OracleError(SW_ERR_INVALID_ARGUMENT, "unknown sampling strategy");
 }

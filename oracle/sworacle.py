@@ -19,11 +19,11 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-RANDOM_GRID, GRID_CENTER, MIN_DISTANCE, JITTERED = 0, 1, 2, 3
+RANDOM_GRID, GRID_CENTER, MIN_DISTANCE, JITTERED, MIN_DISTANCE_FAST = 0, 1, 2, 3, 4
 ACCURATE, FAST = 0, 1
 TAKE_ALL_WHEN_COUNT_BELOW_MAX, ALWAYS_ADHERE = 0, 1
 
-SAMPLING_NAMES = {"RANDOM_GRID": 0, "GRID_CENTER": 1, "MIN_DISTANCE": 2, "JITTERED": 3}
+SAMPLING_NAMES = {"RANDOM_GRID": 0, "GRID_CENTER": 1, "MIN_DISTANCE": 2, "JITTERED": 3, "MIN_DISTANCE_FAST": 4}
 TILING_NAMES = {"ACCURATE": 0, "FAST": 1}
 
 

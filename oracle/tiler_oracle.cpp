@@ -280,6 +280,7 @@ struct RestatedPrims
       case SW_GRID_CENTER:
         return node_level_to_sample_from(node_level, root);
       case SW_MIN_DISTANCE:
+      case SW_MIN_DISTANCE_FAST:
         return node_level;
       case SW_JITTERED: {
         const double spacing_at_this_node = root.max_spacing / std::pow(2, node_level + 1);
@@ -331,6 +332,8 @@ struct RestatedPrims
         return sample_min_distance(begin, end, node_key, node_level, root_bounds, spacing_at_root);
       case SW_JITTERED:
         return sample_jittered(begin, end, node_key, node_level, root_bounds, spacing_at_root);
+      case SW_MIN_DISTANCE_FAST:
+        return sample_min_distance_fast(begin, end, node_key, node_level, root_bounds, spacing_at_root);
     }
     throw OracleError(SW_ERR_INVALID_ARGUMENT, "unknown sampling strategy");
   }
@@ -404,6 +407,44 @@ struct RestatedPrims
     std::vector<uint8_t> sel(cnt, 0);
     for (size_t i = 0; i < cnt; ++i)
       sel[i] = grid.add(xyz + 3 * static_cast<uint64_t>(begin[i].id)) ? 1 : 0;
+    return stable_partition_flags(begin, end, sel);
+  }
+
+  /* density_per_level of the MIN_DISTANCE_FAST strategy, process/TilerProcess.cpp:500-508 */
+  static float density_per_level(int32_t node_level)
+  {
+    if (node_level < 0)
+      return 0.25f;
+    if (node_level < 1)
+      return 0.5f;
+    return 1.f;
+  }
+
+  /* AdaptivePoissonDiskSampling::sample_points, Sampling.h:477-542: only every n-th point of the
+   * range is offered to the SparseGrid, the others are rejected outright */
+  size_t sample_min_distance_fast(IP* begin,
+                                  IP* end,
+                                  uint64_t node_key,
+                                  int32_t node_level,
+                                  const Box& root,
+                                  float spacing_at_root)
+  {
+    const size_t cnt = static_cast<size_t>(end - begin);
+    const double spacing_at_this_node = spacing_at_root / std::pow(2, node_level + 1);
+    const int cand = candidate_level_in_sampler(root, spacing_at_root, node_level);
+    if (cand == -1)
+      return 1; /* `return ++partition_point;` (Sampling.h:513-515) */
+    const Box nb = get_bounds_from_morton_index(node_key, root, static_cast<uint32_t>(node_level + 1));
+    SparseGridRestated grid(nb, static_cast<float>(spacing_at_this_node));
+    const uint32_t nth_point = static_cast<uint32_t>(std::round(1 / density_per_level(node_level)));
+    uint32_t point_counter = nth_point - 1; /* the first point is always analysed */
+    std::vector<uint8_t> sel(cnt, 0);
+    for (size_t i = 0; i < cnt; ++i) {
+      if (++point_counter == nth_point) {
+        point_counter = 0;
+        sel[i] = grid.add(xyz + 3 * static_cast<uint64_t>(begin[i].id)) ? 1 : 0;
+      }
+    }
     return stable_partition_flags(begin, end, sel);
   }
 

@@ -1214,6 +1214,10 @@ md_setup_kernel(SwMinDistArgs a, int cell_shift, const u32* __restrict__ cell_ti
         const u32 cnt = node_point_count(a.node_start, a.node_gcount, node_rank);
         active = (u64)cnt > a.max_points_per_node;
       }
+      // AdaptivePoissonDiskSampling: the counter starts at nth - 1, so positions 0, nth, 2 nth, ... of
+      // the node's range are analysed, every other point is rejected without touching the grid
+      if (a.nth_point > 1 && ((u32)i - a.node_start[node_rank]) % a.nth_point != 0)
+        active = false;
       cell_of[i] = cell_rank;
       state[i] = active ? MD_UNDECIDED : MD_REJECTED;
       cur_off[i] = 0;

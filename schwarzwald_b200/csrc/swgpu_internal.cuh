@@ -152,6 +152,7 @@ struct SwMinDistArgs
   const u32* node_gcount; // see SwLevelArgs
   int allow_take_all;
   u64 max_points_per_node;
+  u32 nth_point; // 1 = every point is analysed; n = only every n-th point of a node (MIN_DISTANCE_FAST)
 };
 
 struct SwMinDistScratch

@@ -223,6 +223,7 @@ required_depth(const swgpu_tiler* h, int node_level)
       return std::max(-1, static_cast<int>(std::floor(std::log2f(ratio))) - 1);
     }
     case SW_MIN_DISTANCE:
+    case SW_MIN_DISTANCE_FAST:
       return node_level;
     case SW_JITTERED: {
       const double spacing_at_this_node = h->prm.spacing_at_root / std::pow(2, node_level + 1);
@@ -390,7 +391,8 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
     int sampling = h->prm.sampling;
     // GridCenterSampling takes the first point when the candidate level is the root
     // (`return ++partition_point`, Sampling.h:346-348): same selection as RANDOM_GRID at level -1
-    if (sampling == SW_GRID_CENTER && cand < 0) {
+    // (AdaptivePoissonDiskSampling has the same early return, Sampling.h:513-515)
+    if ((sampling == SW_GRID_CENTER || sampling == SW_MIN_DISTANCE_FAST) && cand < 0) {
       sampling = SW_RANDOM_GRID;
       a.sampling = SW_RANDOM_GRID;
     }
@@ -432,7 +434,8 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
         a.sel = h->sel.as<unsigned char>();
         break;
       }
-      case SW_MIN_DISTANCE: {
+      case SW_MIN_DISTANCE:
+      case SW_MIN_DISTANCE_FAST: {
         SwMinDistArgs m{};
         m.in_key = in_key;
         m.in_idx = in_idx;
@@ -460,6 +463,11 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
         m.node_gcount = node_gcount;
         m.allow_take_all = allow_take_all ? 1 : 0;
         m.max_points_per_node = h->prm.max_points_per_node;
+        // MIN_DISTANCE_FAST analyses every n-th point of a node only: n = round(1 / density(level)) with
+        // the CLI's density function (process/TilerProcess.cpp:500-508; Sampling.h:525-539)
+        m.nth_point = 1;
+        if (sampling == SW_MIN_DISTANCE_FAST)
+          m.nth_point = node_level < 0 ? 4u : (node_level < 1 ? 2u : 1u);
         h->md.status = h->scan_status.as<u64>();
         h->md.ticket = h->d_tickets();
         h->md.h_pinned = h->h_scalars->scratch;
@@ -750,7 +758,7 @@ swgpu_create(const sw_params* params, int device, swgpu_handle* out)
   if (!params || !out)
     return SW_ERR_INVALID_ARGUMENT;
   *out = nullptr;
-  if (params->sampling < 0 || params->sampling > 3 || params->tiling < 0 || params->tiling > 1)
+  if (params->sampling < 0 || params->sampling > SW_MIN_DISTANCE_FAST || params->tiling < 0 || params->tiling > 1)
     return SW_ERR_INVALID_ARGUMENT;
   for (int a = 0; a < 3; ++a)
     if (!(params->bounds_max[a] > params->bounds_min[a]))

@@ -99,8 +99,10 @@ private:
           return SW_MIN_DISTANCE;
         else if constexpr (std::is_same_v<T, JitteredSampling>)
           return SW_JITTERED;
-        else
-          throw std::runtime_error{ "TilingAlgorithmGPU: MIN_DISTANCE_FAST is not implemented on the GPU" };
+        else // AdaptivePoissonDiskSampling: its density function is an opaque std::function; the only
+             // one the reference ever constructs is the CLI's (process/TilerProcess.cpp:500-508),
+             // which is what SW_MIN_DISTANCE_FAST implements
+          return SW_MIN_DISTANCE_FAST;
       },
       _sampling_strategy);
   }

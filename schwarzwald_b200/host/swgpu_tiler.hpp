@@ -41,6 +41,8 @@ sampling_from_name(const std::string& name)
     return SW_MIN_DISTANCE;
   if (name == "JITTERED")
     return SW_JITTERED;
+  if (name == "MIN_DISTANCE_FAST")
+    return SW_MIN_DISTANCE_FAST;
   throw Error(SW_ERR_INVALID_ARGUMENT, "Unrecognized sampling strategy " + name);
 }
 

@@ -20,8 +20,9 @@ import numpy as np
 from . import native
 
 RANDOM_GRID, GRID_CENTER, MIN_DISTANCE, JITTERED = "RANDOM_GRID", "GRID_CENTER", "MIN_DISTANCE", "JITTERED"
+MIN_DISTANCE_FAST = "MIN_DISTANCE_FAST"
 ACCURATE, FAST = "ACCURATE", "FAST"
-_SAMPLING = {RANDOM_GRID: 0, GRID_CENTER: 1, MIN_DISTANCE: 2, JITTERED: 3}
+_SAMPLING = {RANDOM_GRID: 0, GRID_CENTER: 1, MIN_DISTANCE: 2, JITTERED: 3, MIN_DISTANCE_FAST: 4}
 _TILING = {ACCURATE: 0, FAST: 1}
 
 NODE_TERMINAL = 2

@@ -22,6 +22,8 @@ CLOUDS = {
 }
 SAMPLINGS = ["RANDOM_GRID", "GRID_CENTER", "JITTERED", "MIN_DISTANCE"]
 TILINGS = ["ACCURATE", "FAST"]
+# strategies added after the first fixture set: appended so that earlier case numbers stay put
+LATER_SAMPLINGS = ["MIN_DISTANCE_FAST"]
 
 
 def case_input(cloud):
@@ -47,10 +49,11 @@ def main():
     from oracle import sworacle
     ref = sworacle.Oracle("ref")
     cases = []
-    for cloud in CLOUDS:
+    for group in (SAMPLINGS, LATER_SAMPLINGS):
+      for cloud in CLOUDS:
         xyz, bmin, bmax, spacing = case_input(cloud)
         for tiling in TILINGS:
-            for sampling in SAMPLINGS:
+            for sampling in group:
                 p = sworacle.make_params(sampling, tiling, spacing, bmin, bmax, max_points_per_node=700, concurrency=2)
                 res = ref.tile(p, xyz)
                 cases.append({"cloud": cloud, "sampling": sampling, "tiling": tiling, "max_points": 700,

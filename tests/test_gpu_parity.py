@@ -11,7 +11,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-SAMPLINGS = ["RANDOM_GRID", "GRID_CENTER", "JITTERED", "MIN_DISTANCE"]
+SAMPLINGS = ["RANDOM_GRID", "GRID_CENTER", "JITTERED", "MIN_DISTANCE", "MIN_DISTANCE_FAST"]
 TILINGS = ["ACCURATE", "FAST"]
 
 
@@ -75,7 +75,7 @@ def test_uniform_small(port_oracle, sampling, tiling):
 @pytest.mark.parametrize("sampling", SAMPLINGS)
 def test_terrain_medium(port_oracle, sampling, tiling):
     _torch_cuda()
-    n = 1_500_000 if sampling != "MIN_DISTANCE" else 600_000
+    n = 1_500_000 if not sampling.startswith("MIN_DISTANCE") else 600_000
     xyz = make_cloud("terrain", n, 2, side_m=2000.0)
     bmin, bmax, spacing = setup_case(xyz)
     assert_same(*run_both(port_oracle, xyz, sampling, tiling, bmin, bmax, spacing, 20000, 8))
@@ -305,7 +305,7 @@ def test_full_size_properties():
     assert len(np.unique(cells)) == len(cells)
 
 
-@pytest.mark.parametrize("case", range(16))
+@pytest.mark.parametrize("case", range(20))
 def test_gpu_equals_committed_reference_golden(case):
     """The CUDA path against tests/golden/tiler_golden.json — digests of results produced by the
     reference's own code (oracle/_ref, verbatim TUs) and committed, so this pin needs neither

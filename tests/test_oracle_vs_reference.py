@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SAMPLINGS = ["RANDOM_GRID", "GRID_CENTER", "JITTERED", "MIN_DISTANCE"]
+SAMPLINGS = ["RANDOM_GRID", "GRID_CENTER", "JITTERED", "MIN_DISTANCE", "MIN_DISTANCE_FAST"]
 
 
 def cloud(seed, n, scale, offset):
@@ -110,7 +110,7 @@ def load_golden():
     return json.load(open(path))
 
 
-@pytest.mark.parametrize("case", range(16))
+@pytest.mark.parametrize("case", range(20))
 def test_port_equals_committed_reference_golden(port_oracle, case):
     """Fixtures generated from oracle/_ref (the reference's own code) by tests/golden/make_golden.py."""
     import sys
