@@ -64,6 +64,33 @@ typedef struct sw_node {
   uint64_t count;
 } sw_node;
 
+/* LAS record -> PointBuffer position, as the reference's reader and tiler transformation compute it
+ * (SURVEY.md section 8 f2):
+ *   position_from_las_point, core/io/LASFile.cpp:79-94:
+ *       p = offset + X * scale;  p = std::min(header_max, std::max(header_min, p))
+ *   TilerProcess's point transformation, core/process/TilerProcess.cpp:552-559 (3DTILES output with an
+ *   identity SRS transform): p -= center; p = (double)(float)p     when shift_to_center != 0
+ * center = cubic_bounds.getCenter() = min + extent / 2 (core/math/AABB.h:70), computed by the caller. */
+typedef struct sw_las_transform {
+  double scale[3];      /* laszip_header::x/y/z_scale_factor */
+  double offset[3];     /* laszip_header::x/y/z_offset */
+  double header_min[3]; /* laszip_header::min_x/y/z */
+  double header_max[3]; /* laszip_header::max_x/y/z */
+  double center[3];     /* only read when shift_to_center != 0 */
+  int32_t shift_to_center;
+  int32_t reserved;
+} sw_las_transform;
+
+/* Header values LASPersistence::persist_points writes for one node (core/io/LASPersistence.h:119-131):
+ * offset = min = node bounds min, max = node bounds max, one scale for the three axes
+ * (compute_las_scale_from_bounds, core/io/LASPersistence.cpp:17-28). */
+typedef struct sw_las_node_header {
+  double offset[3];
+  double scale;
+  double max[3];
+  double reserved;
+} sw_las_node_header;
+
 /* error codes shared by swgpu_* and swo_* */
 #define SW_OK 0
 #define SW_ERR_INVALID_ARGUMENT 1

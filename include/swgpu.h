@@ -79,6 +79,35 @@ int swgpu_get_keys(swgpu_handle h, uint64_t* keys, uint32_t* order);
  * by original point index into node-major order on the device.  src/dst are device pointers. */
 int swgpu_gather_attribute_device(swgpu_handle h, const void* src_device, uint32_t width, void* dst_device);
 
+/*
+ * ---- LAS coordinates in ------------------------------------------------------
+ * build_execution_graph() for a batch that is still in LAS record form: `las_xyz` holds n x 3 int32
+ * (laszip_point::X, Y, Z).  The device computes the PointBuffer positions exactly as the reference's
+ * reader and point transformation do (sw_las_transform, include/sw_types.h: io/LASFile.cpp:79-94,
+ * process/TilerProcess.cpp:552-559) and indexes them in the same kernel: the host pass over every point
+ * and half of the host-to-device bytes disappear.  swgpu_get_positions returns those positions
+ * (n x 3 doubles, original point order, after index_point's clamping) for callers that still need them
+ * on the host; it works after any swgpu_index_batch* call.
+ */
+int swgpu_index_batch_las(swgpu_handle h, const int32_t* las_xyz_host, uint64_t n, const sw_las_transform* t);
+int swgpu_index_batch_las_device(swgpu_handle h, const int32_t* las_xyz_device, uint64_t n, const sw_las_transform* t);
+int swgpu_get_positions(swgpu_handle h, double* xyz_host);
+
+/*
+ * ---- Writer payloads ---------------------------------------------------------
+ * The position bytes the reference's writers store, for ALL nodes at once in the node-major order of
+ * swgpu_get_nodes (row i of the node table owns payload records [first, first + count)):
+ *   pnts  n_point_ids x 3 float32 = attributes::PositionAttribute (io/PNTSWriter.cpp:326-342)
+ *   las   n_point_ids x 3 int32 record coordinates + one sw_las_node_header per node table row
+ *         (io/LASPersistence.h:119-131,160-163; io/LASPersistence.cpp:17-28; quantisation of LASzip's
+ *         laszip_set_coordinates)
+ * The _device variants write to caller-owned device buffers (headers still go to the host).
+ */
+int swgpu_get_payload_pnts(swgpu_handle h, float* xyz_f32_host);
+int swgpu_get_payload_pnts_device(swgpu_handle h, float* xyz_f32_device);
+int swgpu_get_payload_las(swgpu_handle h, int32_t* xyz_i32_host, sw_las_node_header* headers_host);
+int swgpu_get_payload_las_device(swgpu_handle h, int32_t* xyz_i32_device, sw_las_node_header* headers_host);
+
 /* Stand-alone primitives (used by the parity tests and the multi-GPU shuffle). */
 /* index_point<21> over a device batch: keys_device receives n u64; xyz is clamped in place. */
 int swgpu_morton_encode_device(swgpu_handle h, double* xyz_device, uint64_t n, uint64_t* keys_device);

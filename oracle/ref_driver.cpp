@@ -14,6 +14,10 @@
  *   sample_points(SamplingStrategy&, ...)   tiling/Sampling.h:799-821 (all four strategies)
  *   required_morton_index_depth             tiling/Sampling.cpp:29-62
  *   expand_bits_by_3 / contract_bits_by_3   util/stuff.h:207-234
+ *   position_from_las_point                 io/LASFile.cpp:79-94
+ *   attributes::PositionAttribute           io/PNTSWriter.cpp:326-342,344-360
+ *   LASPersistence::persist_points<Iter>    io/LASPersistence.h:33-240 (+ compute_las_scale_from_bounds,
+ *                                           io/LASPersistence.cpp:17-28)
  * TilingAlgorithms.cpp needs taskflow/boost::hana/cista, which are not in this image, so the
  * control flow around these calls is the restatement in orchestrator.h.
  */
@@ -25,8 +29,23 @@
 #include "tiling/Sampling.h"
 #include "util/stuff.h"
 
+/* the reader's position conversion and the writers' position payloads,
+ * compiled verbatim as well (io/LASFile.cpp, io/LASPersistence.cpp, io/PNTSWriter.cpp) against the
+ * in-memory LASzip stand-in oracle/shim/laszip_api.h */
+#include "io/LASFile.h"
+#include "io/LASPersistence.h"
+#include "io/PNTSWriter.h"
+
 #include <cstring>
 #include <memory>
+
+/* util/Transformation.cpp needs PROJ and is not compiled; io/PNTSWriter.cpp references this one function
+ * from it in writePNTSFile (converter mode), which nothing here calls. */
+Vector3<double>
+setOriginToSmallestPoint(std::vector<Vector3<double>>&)
+{
+  throw std::logic_error("setOriginToSmallestPoint is not part of the tiler hot path");
+}
 
 namespace {
 
@@ -404,6 +423,113 @@ void
 swr_destroy(void* handle)
 {
   delete static_cast<Handle*>(handle);
+}
+
+/* ---- LAS input transform and writer payloads ------------------------- */
+
+void
+swr_las_positions(const int32_t* las, uint64_t n, const sw_las_transform* t, double* xyz)
+{
+  laszip_header header;
+  header.x_scale_factor = t->scale[0];
+  header.y_scale_factor = t->scale[1];
+  header.z_scale_factor = t->scale[2];
+  header.x_offset = t->offset[0];
+  header.y_offset = t->offset[1];
+  header.z_offset = t->offset[2];
+  header.min_x = t->header_min[0];
+  header.min_y = t->header_min[1];
+  header.min_z = t->header_min[2];
+  header.max_x = t->header_max[0];
+  header.max_y = t->header_max[1];
+  header.max_z = t->header_max[2];
+  const Vector3<double> center{ t->center[0], t->center[1], t->center[2] };
+  for (uint64_t i = 0; i < n; ++i) {
+    laszip_point point;
+    point.X = las[3 * i];
+    point.Y = las[3 * i + 1];
+    point.Z = las[3 * i + 2];
+    auto position = position_from_las_point(point, header); /* the reference's own function */
+    if (t->shift_to_center) {
+      /* the transformation TilerProcess registers on the point source (process/TilerProcess.cpp:552-559;
+       * that TU needs boost/taskflow and is not compiled here, so its four statements are spelled out) */
+      position -= center;
+      position.x = static_cast<float>(position.x);
+      position.y = static_cast<float>(position.y);
+      position.z = static_cast<float>(position.z);
+    }
+    xyz[3 * i] = position.x;
+    xyz[3 * i + 1] = position.y;
+    xyz[3 * i + 2] = position.z;
+  }
+}
+
+void
+swr_payload_pnts(const double* xyz, const uint32_t* ids, uint64_t n_ids, float* out)
+{
+  uint64_t n = 0;
+  for (uint64_t j = 0; j < n_ids; ++j)
+    n = std::max<uint64_t>(n, static_cast<uint64_t>(ids[j]) + 1);
+  RefPrims p(xyz, n, SW_RANDOM_GRID, 1);
+  std::vector<PointBuffer::PointReference> refs;
+  refs.reserve(n_ids);
+  for (uint64_t j = 0; j < n_ids; ++j)
+    refs.push_back(p.refs[ids[j]]);
+  attributes::PositionAttribute attribute;
+  attribute.extractFromPoints(gsl::span<PointBuffer::PointReference>(refs.data(), refs.size()));
+  const auto bytes = attribute.getBinaryDataRange();
+  std::memcpy(out, bytes.data(), bytes.size());
+}
+
+void
+swr_payload_las(const double* xyz, const uint32_t* ids, const sw_node* nodes, uint64_t n_nodes, const double* bmin,
+                const double* bmax, int32_t* out, sw_las_node_header* headers)
+{
+  uint64_t n = 0, n_ids = 0;
+  for (uint64_t r = 0; r < n_nodes; ++r)
+    n_ids = std::max<uint64_t>(n_ids, nodes[r].first + nodes[r].count);
+  for (uint64_t j = 0; j < n_ids; ++j)
+    n = std::max<uint64_t>(n, static_cast<uint64_t>(ids[j]) + 1);
+  RefPrims p(xyz, n, SW_RANDOM_GRID, 1);
+  PointAttributes attributes;
+  attributes.insert(PointAttribute::Position);
+  LASPersistence sink("swr", attributes, attributes, Compressed::No);
+  const AABB root = to_aabb(make_box(bmin, bmax));
+  for (uint64_t r = 0; r < n_nodes; ++r) {
+    AABB b = root;
+    for (uint32_t l = 0; l < nodes[r].levels; ++l) /* get_bounds_from_node_index, OctreeAlgorithms.cpp:64-72 */
+      b = get_octant_bounds(static_cast<uint8_t>((nodes[r].index >> (3 * (nodes[r].levels - 1 - l))) & 7), b);
+    if (headers) {
+      headers[r] = sw_las_node_header{};
+      headers[r].scale = compute_las_scale_from_bounds(b);
+    }
+    if (!nodes[r].count)
+      continue;
+    std::vector<PointBuffer::PointReference> refs;
+    for (uint64_t j = nodes[r].first; j < nodes[r].first + nodes[r].count; ++j)
+      refs.push_back(p.refs[ids[j]]);
+    const std::string name = "node" + std::to_string(r);
+    sink.persist_points(refs.begin(), refs.end(), b, name);
+    const auto it = laszip_shim::files().find("swr/" + name + ".las");
+    if (it == laszip_shim::files().end() || it->second.points.size() != nodes[r].count)
+      throw std::runtime_error("LASPersistence did not write node " + name);
+    const auto& file = it->second;
+    if (headers) { /* what persist_points stored in the LAS header */
+      headers[r].offset[0] = file.header.x_offset;
+      headers[r].offset[1] = file.header.y_offset;
+      headers[r].offset[2] = file.header.z_offset;
+      headers[r].max[0] = file.header.max_x;
+      headers[r].max[1] = file.header.max_y;
+      headers[r].max[2] = file.header.max_z;
+      headers[r].scale = file.header.x_scale_factor;
+    }
+    for (uint64_t k = 0; k < nodes[r].count; ++k) {
+      out[3 * (nodes[r].first + k)] = file.points[k].X;
+      out[3 * (nodes[r].first + k) + 1] = file.points[k].Y;
+      out[3 * (nodes[r].first + k) + 2] = file.points[k].Z;
+    }
+    laszip_shim::files().erase(it);
+  }
 }
 
 } /* extern "C" */

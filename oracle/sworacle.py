@@ -41,6 +41,32 @@ class SwParams(C.Structure):
     ]
 
 
+class SwLasTransform(C.Structure):
+    _fields_ = [
+        ("scale", C.c_double * 3),
+        ("offset", C.c_double * 3),
+        ("header_min", C.c_double * 3),
+        ("header_max", C.c_double * 3),
+        ("center", C.c_double * 3),
+        ("shift_to_center", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+def make_las_transform(scale, offset, header_min, header_max, center=None):
+    t = SwLasTransform()
+    for a in range(3):
+        t.scale[a] = float(scale[a])
+        t.offset[a] = float(offset[a])
+        t.header_min[a] = float(header_min[a])
+        t.header_max[a] = float(header_max[a])
+        t.center[a] = float(center[a]) if center is not None else 0.0
+    t.shift_to_center = 1 if center is not None else 0
+    return t
+
+
+LAS_HEADER_DTYPE = np.dtype([("offset", "<f8", 3), ("scale", "<f8"), ("max", "<f8", 3), ("reserved", "<f8")])
+
 NODE_DTYPE = np.dtype(
     [("index", "<u8"), ("levels", "<u4"), ("flags", "<u4"), ("first", "<u8"), ("count", "<u8")]
 )
@@ -141,6 +167,10 @@ class Oracle:
         f("duplicate_keys", C.c_uint64, [C.c_void_p])
         f("get_nodes", None, [C.c_void_p, C.c_void_p, C.c_void_p])
         f("get_keys", None, [C.c_void_p, C.c_void_p, C.c_void_p])
+        f("las_positions", None, [C.c_void_p, C.c_uint64, C.POINTER(SwLasTransform), C.c_void_p])
+        f("payload_pnts", None, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p])
+        f("payload_las", None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p])
         f("last_error", C.c_char_p, [C.c_void_p])
         f("destroy", None, [C.c_void_p])
 
@@ -213,6 +243,32 @@ class Oracle:
         if r < 0:
             raise RuntimeError("oracle sample_points failed with code %d" % -r)
         return int(r), ko, io
+
+    # --- LAS input transform and writer payloads ------------------
+    def las_positions(self, las_xyz, transform):
+        """position_from_las_point + the tiler's shift/float32 transformation -> (n,3) float64."""
+        las_xyz = np.ascontiguousarray(las_xyz, dtype=np.int32).reshape(-1, 3)
+        out = np.empty((len(las_xyz), 3), np.float64)
+        self._las_positions(las_xyz.ctypes.data, len(las_xyz), C.byref(transform), out.ctypes.data)
+        return out
+
+    def payload_pnts(self, xyz, ids):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        out = np.empty((len(ids), 3), np.float32)
+        self._payload_pnts(xyz.ctypes.data, ids.ctypes.data, len(ids), out.ctypes.data)
+        return out
+
+    def payload_las(self, xyz, ids, nodes, bounds):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        nodes = np.ascontiguousarray(nodes)
+        bmin, bmax = self._b(bounds)
+        out = np.zeros((len(ids), 3), np.int32)
+        headers = np.zeros(len(nodes), LAS_HEADER_DTYPE)
+        self._payload_las(xyz.ctypes.data, ids.ctypes.data, nodes.ctypes.data, len(nodes), bmin.ctypes.data,
+                          bmax.ctypes.data, out.ctypes.data, headers.ctypes.data)
+        return out, headers
 
     # --- whole batch --------------------------------------------------------------------------
     def tile(self, params: SwParams, xyz, return_clamped=False):

@@ -739,4 +739,85 @@ swo_destroy(void* handle)
   delete static_cast<Handle*>(handle);
 }
 
+/* ---- LAS input transform and writer payloads ------------------------- */
+
+/* position_from_las_point, core/io/LASFile.cpp:79-94, followed by the tiler's point transformation with
+ * an identity SRS transform, core/process/TilerProcess.cpp:552-559 */
+void
+swo_las_positions(const int32_t* las, uint64_t n, const sw_las_transform* t, double* xyz)
+{
+  for (uint64_t i = 0; i < n; ++i) {
+    for (int a = 0; a < 3; ++a) {
+      double p = t->offset[a] + las[3 * i + a] * t->scale[a];
+      p = std::min(t->header_max[a], std::max(t->header_min[a], p));
+      if (t->shift_to_center) {
+        p -= t->center[a];
+        p = static_cast<float>(p);
+      }
+      xyz[3 * i + a] = p;
+    }
+  }
+}
+
+/* attributes::PositionAttribute::extractFromPoints(span<PointReference>), core/io/PNTSWriter.cpp:326-342:
+ * the positions of the node's points, in the node's stored order, narrowed to float */
+void
+swo_payload_pnts(const double* xyz, const uint32_t* ids, uint64_t n_ids, float* out)
+{
+  for (uint64_t j = 0; j < n_ids; ++j)
+    for (int a = 0; a < 3; ++a)
+      out[3 * j + a] = static_cast<float>(xyz[3 * static_cast<uint64_t>(ids[j]) + a]);
+}
+
+/* compute_las_scale_from_bounds, core/io/LASPersistence.cpp:17-28 */
+static double
+las_scale_from_bounds(const Box& b)
+{
+  const double ex = b.max[0] - b.min[0], ey = b.max[1] - b.min[1], ez = b.max[2] - b.min[2];
+  const double bounds_diagonal = std::sqrt(ex * ex + ey * ey + ez * ez);
+  if (bounds_diagonal > 1000000)
+    return 0.01;
+  else if (bounds_diagonal > 100000)
+    return 0.001;
+  else if (bounds_diagonal > 1)
+    return 0.001;
+  return 0.0001;
+}
+
+/* LASzip (third-party, not vendored in /root/reference; the reference links the system liblaszip through
+ * laszip_api.h): laszip_set_coordinates stores I32_QUANTIZE((coordinate - offset) / scale_factor) with
+ * I32_QUANTIZE(n) = (n >= 0) ? (I32)(n + 0.5) : (I32)(n - 0.5)  (LASzip src/mydefs.hpp, laszip_dll.cpp). */
+static int32_t
+i32_quantize(double n)
+{
+  return (n >= 0) ? static_cast<int32_t>(n + 0.5) : static_cast<int32_t>(n - 0.5);
+}
+
+/* LASPersistence::persist_points, core/io/LASPersistence.h:119-131 (header: offset = min = bounds.min,
+ * max = bounds.max, one scale) and :160-163 (laszip_set_coordinates of every point), for every node of a
+ * node table; node bounds = get_bounds_from_node_index (OctreeAlgorithms.cpp:64-72). */
+void
+swo_payload_las(const double* xyz, const uint32_t* ids, const sw_node* nodes, uint64_t n_nodes, const double* bmin,
+                const double* bmax, int32_t* out, sw_las_node_header* headers)
+{
+  const Box root = make_box(bmin, bmax);
+  for (uint64_t r = 0; r < n_nodes; ++r) {
+    Box b = root;
+    for (uint32_t l = 0; l < nodes[r].levels; ++l)
+      b = get_octant_bounds(static_cast<uint8_t>((nodes[r].index >> (3 * (nodes[r].levels - 1 - l))) & 7), b);
+    const double scale = las_scale_from_bounds(b);
+    if (headers) {
+      for (int a = 0; a < 3; ++a) {
+        headers[r].offset[a] = b.min[a];
+        headers[r].max[a] = b.max[a];
+      }
+      headers[r].scale = scale;
+      headers[r].reserved = 0;
+    }
+    for (uint64_t j = nodes[r].first; j < nodes[r].first + nodes[r].count; ++j)
+      for (int a = 0; a < 3; ++a)
+        out[3 * j + a] = i32_quantize((xyz[3 * static_cast<uint64_t>(ids[j]) + a] - b.min[a]) / scale);
+  }
+}
+
 } /* extern "C" */

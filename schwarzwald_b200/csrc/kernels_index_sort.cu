@@ -168,6 +168,101 @@ launch_key_histogram(const u64* keys, u64 n, u32* hist, cudaStream_t stream)
   key_histogram_kernel<<<grid, MORTON_THREADS, 0, stream>>>(keys, n, hist);
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1-LAS    LAS record coordinates -> PointBuffer position -> index_point
+//   position_from_las_point              io/LASFile.cpp:79-94     offset + X * scale (two roundings),
+//                                                                 clamped into the LAS header bounds
+//   the tiler's point transformation     process/TilerProcess.cpp:552-559  shift to the centre of the
+//                                                                 cubic bounds, round to float32
+//   index_point<21>                      as K1
+// One host pass over every point (and half of the PCIe bytes: 12 instead of 24 per point) disappears;
+// the doubles the reference would hold in its PointBuffer are written to xyz_out for the sampling
+// kernels and the writers.  Each thread converts four records = three 16-byte loads.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double
+las_axis(int v, int a, const SwLasTransform& t)
+{
+  double p = t.offset[a] + (double)v * t.scale[a];
+  p = clamp_like_reference(p, t.hmin[a], t.hmax[a]);
+  if (t.shift) {
+    p = p - t.center[a];
+    p = (double)(float)p;
+  }
+  return p;
+}
+
+__device__ __forceinline__ u64
+las_one(int X, int Y, int Z, const SwLasTransform& t, const SwBounds& b, double* out, u32& clamped)
+{
+  double x = las_axis(X, 0, t), y = las_axis(Y, 1, t), z = las_axis(Z, 2, t);
+  clamped += (u32)index_one(x, y, z, b);
+  out[0] = x;
+  out[1] = y;
+  out[2] = z;
+  return morton_from_position(x, y, z, b);
+}
+
+__global__ void __launch_bounds__(MORTON_THREADS)
+las_encode_kernel(const int* __restrict__ las, u64 n, SwLasTransform t, SwBounds b, double* __restrict__ xyz_out,
+                  u64* __restrict__ keys, u32* __restrict__ hist, u32* __restrict__ n_clamped)
+{
+  __shared__ u32 s_hist[8 * 256];
+  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS)
+    s_hist[i] = 0;
+  __syncthreads();
+
+  const u64 n_quads = n >> 2;
+  u32 clamped = 0;
+  for (u64 q = (u64)blockIdx.x * MORTON_THREADS + threadIdx.x; q < n_quads; q += (u64)gridDim.x * MORTON_THREADS) {
+    const int4* p4 = reinterpret_cast<const int4*>(las) + 3 * q;
+    const int4 a = p4[0], c = p4[1], e = p4[2];
+    double o[12];
+    u64 k[4];
+    k[0] = las_one(a.x, a.y, a.z, t, b, o + 0, clamped);
+    k[1] = las_one(a.w, c.x, c.y, t, b, o + 3, clamped);
+    k[2] = las_one(c.z, c.w, e.x, t, b, o + 6, clamped);
+    k[3] = las_one(e.y, e.z, e.w, t, b, o + 9, clamped);
+    double2* d2 = reinterpret_cast<double2*>(xyz_out) + 6 * q;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      d2[i] = make_double2(o[2 * i], o[2 * i + 1]);
+    ulonglong2* k2 = reinterpret_cast<ulonglong2*>(keys) + 2 * q;
+    k2[0] = make_ulonglong2(k[0], k[1]);
+    k2[1] = make_ulonglong2(k[2], k[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      hist_add(s_hist, k[i]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (u32)(n & 3)) { // ragged tail: up to three records
+    const u64 i = (n & ~3ull) + threadIdx.x;
+    double o[3];
+    const u64 k = las_one(las[3 * i], las[3 * i + 1], las[3 * i + 2], t, b, o, clamped);
+    xyz_out[3 * i] = o[0];
+    xyz_out[3 * i + 1] = o[1];
+    xyz_out[3 * i + 2] = o[2];
+    keys[i] = k;
+    hist_add(s_hist, k);
+  }
+  if (clamped)
+    atomicAdd(n_clamped, clamped);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS) {
+    const u32 v = s_hist[i];
+    if (v)
+      atomicAdd(&hist[i], v);
+  }
+}
+
+void
+launch_las_encode(const int* las, u64 n, const SwLasTransform& t, const SwBounds& b, double* xyz_out, u64* keys,
+                  u32* hist, u32* n_clamped, cudaStream_t stream)
+{
+  if (n == 0)
+    return;
+  const int grid = persistent_grid((n + 3) / 4, MORTON_THREADS, 8);
+  las_encode_kernel<<<grid, MORTON_THREADS, 0, stream>>>(las, n, t, b, xyz_out, keys, hist, n_clamped);
+}
+
 // =============================================================================================
 // K2  onesweep LSD radix sort, 8-bit digits, u64 keys + u32 payload
 // =============================================================================================

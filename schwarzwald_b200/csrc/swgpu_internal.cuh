@@ -197,3 +197,30 @@ void launch_node_counts_from_dense(const u64* keys, const u32* node_start, u32 n
                                    const u32* dense, u32* gcount, cudaStream_t stream);
 // out[i] = map[perm[idx[i]]]
 void launch_compose_ids_mapped(const u32* perm, const u32* idx, const u32* map, u64 n, u32* out, cudaStream_t stream);
+
+// ---- LAS input transform (kernels_index_sort.cu) and writer payloads (kernels_payload.cu) ------------
+// device-side copy of sw_las_transform (include/sw_types.h)
+struct SwLasTransform
+{
+  double scale[3];
+  double offset[3];
+  double hmin[3];
+  double hmax[3];
+  double center[3];
+  int shift;
+};
+// K1-LAS: position_from_las_point (io/LASFile.cpp:79-94) + shift/float rounding
+// (process/TilerProcess.cpp:552-559) + index_point, fused; same outputs as launch_morton_encode plus
+// the positions themselves (xyz_out, n x 3 doubles)
+void launch_las_encode(const int* las, u64 n, const SwLasTransform& t, const SwBounds& b, double* xyz_out, u64* keys,
+                       u32* hist, u32* n_clamped, cudaStream_t stream);
+
+// PNTS payload: out[j] = (float) position of the j-th node-major point (io/PNTSWriter.cpp:326-342).
+// perm == nullptr: `xyz` is already in sorted order (indexed by out_idx directly).
+void launch_payload_pnts(const double* xyz, const u32* perm, const u32* out_idx, u64 n_out, float* out,
+                         cudaStream_t stream);
+// LAS payload: per node header offset = node bounds min, one scale per node; X = I32_QUANTIZE((p - offset) /
+// scale) (io/LASPersistence.h:119-131,160-163 + LASzip's laszip_set_coordinates).  node_first: first
+// output offset per node (bit 63 may carry a flag); node_hdr: 4 doubles per node (offset xyz, scale).
+void launch_payload_las(const double* xyz, const u32* perm, const u32* out_idx, u64 n_out, const u64* node_first,
+                        u32 n_nodes, const double* node_hdr, int* out, cudaStream_t stream);

@@ -113,6 +113,9 @@ struct swgpu_tiler
   u64 n_clamped = 0;
 
   DevBuf xyz_own;
+  const int* d_las = nullptr; // current batch arrives as LAS record coordinates (swgpu_index_batch_las*)
+  SwLasTransform las_t{};
+  DevBuf las_own, payload_tmp, node_hdr;
   DevBuf keys[2], vals[2];
   DevBuf wkey2, widx2;
   DevBuf hist, sort_status, scalars;
@@ -613,9 +616,15 @@ run_batch(swgpu_tiler* h)
   // K1 (every launcher is a no-op for an empty shard)
   CK(cudaMemsetAsync(h->hist.p, 0, 8 * 256 * 4, s));
   CK(cudaMemsetAsync(h->scalars.p, 0, 128, s));
-  launch_morton_encode(h->d_xyz, n, h->bounds, h->keys[0].as<u64>(), h->hist.as<u32>(), h->d_n_clamped(), s);
+  if (h->d_las) { // K1-LAS: 12 B record in, 24 B position + 8 B key out
+    launch_las_encode(h->d_las, n, h->las_t, h->bounds, h->d_xyz, h->keys[0].as<u64>(), h->hist.as<u32>(),
+                      h->d_n_clamped(), s);
+    h->stats.bytes_index = 44 * n;
+  } else {
+    launch_morton_encode(h->d_xyz, n, h->bounds, h->keys[0].as<u64>(), h->hist.as<u32>(), h->d_n_clamped(), s);
+    h->stats.bytes_index = 32 * n;
+  }
   h->stats.kernel_launches += 1;
-  h->stats.bytes_index = 32 * n;
   record(h, 1);
   // K2
   launch_radix_sort(h->keys[0].as<u64>(), h->keys[1].as<u64>(), h->vals[0].as<u32>(), h->vals[1].as<u32>(), n,
@@ -808,7 +817,7 @@ swgpu_destroy(swgpu_handle h)
     return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = { &h->xyz_own,    &h->keys[0],   &h->keys[1],       &h->vals[0],     &h->vals[1],  &h->wkey2,
+  DevBuf* bufs[] = { &h->las_own, &h->payload_tmp, &h->node_hdr, &h->xyz_own,    &h->keys[0],   &h->keys[1],       &h->vals[0],     &h->vals[1],  &h->wkey2,
                      &h->widx2,      &h->hist,      &h->sort_status,   &h->scalars,     &h->pos_sorted, &h->out_key,
                      &h->out_idx,    &h->node_start, &h->node_start_next, &h->selbits, &h->tile_sel, &h->child_count, &h->tile_rank0,   &h->sel,         &h->scan_status, &h->node_index,
                      &h->node_first, &h->bins,      &h->ids_tmp,     &h->dense_counts, &h->node_gcount,
@@ -854,6 +863,7 @@ swgpu_index_batch_device(swgpu_handle h, double* xyz_device, uint64_t n)
   if (!h || (!xyz_device && n))
     return SW_ERR_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
+  h->d_las = nullptr;
   h->d_xyz = xyz_device;
   h->n = n;
   return run_batch(h);
@@ -867,6 +877,7 @@ swgpu_index_batch(swgpu_handle h, double* xyz_host, uint64_t n)
   cudaSetDevice(h->device);
   CK(h->xyz_own.ensure(std::max<size_t>(n, 1) * 24));
   CK(cudaMemcpyAsync(h->xyz_own.p, xyz_host, n * 24, cudaMemcpyHostToDevice, h->stream));
+  h->d_las = nullptr;
   h->d_xyz = h->xyz_own.as<double>();
   h->n = n;
   const int rc = run_batch(h);
@@ -886,6 +897,60 @@ swgpu_finalize(swgpu_handle h)
     return SW_ERR_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
   return run_finalize(h);
+}
+
+static int
+set_las_transform(swgpu_tiler* h, const sw_las_transform* t)
+{
+  for (int a = 0; a < 3; ++a) {
+    h->las_t.scale[a] = t->scale[a];
+    h->las_t.offset[a] = t->offset[a];
+    h->las_t.hmin[a] = t->header_min[a];
+    h->las_t.hmax[a] = t->header_max[a];
+    h->las_t.center[a] = t->center[a];
+  }
+  h->las_t.shift = t->shift_to_center != 0;
+  return SW_OK;
+}
+
+int
+swgpu_index_batch_las_device(swgpu_handle h, const int32_t* las_xyz_device, uint64_t n, const sw_las_transform* t)
+{
+  if (!h || !t || (!las_xyz_device && n))
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  set_las_transform(h, t);
+  CK(h->xyz_own.ensure(std::max<size_t>(n, 1) * 24));
+  h->d_las = las_xyz_device;
+  h->d_xyz = h->xyz_own.as<double>();
+  h->n = n;
+  const int rc = run_batch(h);
+  h->d_las = nullptr; // the positions now live in xyz_own
+  return rc;
+}
+
+int
+swgpu_index_batch_las(swgpu_handle h, const int32_t* las_xyz_host, uint64_t n, const sw_las_transform* t)
+{
+  if (!h || !t || (!las_xyz_host && n))
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  CK(h->las_own.ensure(std::max<size_t>(n, 1) * 12));
+  CK(cudaMemcpyAsync(h->las_own.p, las_xyz_host, n * 12, cudaMemcpyHostToDevice, h->stream));
+  return swgpu_index_batch_las_device(h, h->las_own.as<int32_t>(), n, t);
+}
+
+int
+swgpu_get_positions(swgpu_handle h, double* xyz_host)
+{
+  if (!h || !xyz_host)
+    return SW_ERR_INVALID_ARGUMENT;
+  if (!h->batch_done)
+    return fail(h, SW_ERR_STATE, "no batch has been indexed");
+  cudaSetDevice(h->device);
+  CK(cudaMemcpyAsync(xyz_host, h->d_xyz, h->n * 24, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SW_OK;
 }
 
 int
@@ -967,6 +1032,142 @@ swgpu_get_nodes(swgpu_handle h, sw_node* nodes, uint32_t* point_ids)
   const int rc = fill_node_table(h, nodes);
   if (rc)
     return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return SW_OK;
+}
+
+// get_bounds_from_node_index: get_octant_bounds iterated from the root (tiling/OctreeAlgorithms.cpp:3-18,
+// 64-72); the recurrence, not a closed form, so the doubles match the reference bit for bit
+static void
+node_bounds_of(const swgpu_tiler* h, u64 index, u32 levels, double mn[3], double mx[3])
+{
+  for (int a = 0; a < 3; ++a) {
+    mn[a] = h->prm.bounds_min[a];
+    mx[a] = h->prm.bounds_max[a];
+  }
+  for (u32 l = 0; l < levels; ++l) {
+    const u32 octant = (u32)((index >> (3 * (levels - 1 - l))) & 7);
+    const u32 bit[3] = { (octant >> 2) & 1u, (octant >> 1) & 1u, octant & 1u };
+    for (int a = 0; a < 3; ++a) {
+      const double half = (mx[a] - mn[a]) / 2;
+      if (bit[a])
+        mn[a] = mn[a] + half;
+      mx[a] = mn[a] + half;
+    }
+  }
+}
+
+// compute_las_scale_from_bounds, io/LASPersistence.cpp:17-28
+static double
+las_scale_from_bounds(const double mn[3], const double mx[3])
+{
+  const double ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+  const double diagonal = std::sqrt(ex * ex + ey * ey + ez * ez); // Vector3::length, math/Vector3.h
+  if (diagonal > 1'000'000)
+    return 0.01;
+  else if (diagonal > 100'000)
+    return 0.001;
+  else if (diagonal > 1)
+    return 0.001;
+  return 0.0001;
+}
+
+static int
+payload_checks(swgpu_tiler* h)
+{
+  if (!h->batch_done)
+    return fail(h, SW_ERR_STATE, "no batch has been indexed");
+  if (!h->d_xyz && h->n)
+    return fail(h, SW_ERR_STATE, "the positions of the batch are gone");
+  return SW_OK;
+}
+
+int
+swgpu_get_payload_pnts_device(swgpu_handle h, float* xyz_f32_device)
+{
+  if (!h || !xyz_f32_device)
+    return SW_ERR_INVALID_ARGUMENT;
+  const int rc = payload_checks(h);
+  if (rc)
+    return rc;
+  cudaSetDevice(h->device);
+  launch_payload_pnts(h->d_xyz, h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, xyz_f32_device, h->stream);
+  CK(cudaGetLastError());
+  return SW_OK;
+}
+
+int
+swgpu_get_payload_pnts(swgpu_handle h, float* xyz_f32_host)
+{
+  if (!h || !xyz_f32_host)
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  CK(h->payload_tmp.ensure(std::max<u64>(h->out_count, 1) * 12));
+  const int rc = swgpu_get_payload_pnts_device(h, h->payload_tmp.as<float>());
+  if (rc)
+    return rc;
+  CK(cudaMemcpyAsync(xyz_f32_host, h->payload_tmp.p, h->out_count * 12, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SW_OK;
+}
+
+int
+swgpu_get_payload_las_device(swgpu_handle h, int32_t* xyz_i32_device, sw_las_node_header* headers_host)
+{
+  if (!h || !xyz_i32_device)
+    return SW_ERR_INVALID_ARGUMENT;
+  int rc = payload_checks(h);
+  if (rc)
+    return rc;
+  cudaSetDevice(h->device);
+  if (!h->node_count)
+    return SW_OK;
+  // per-node header values on the host (a few thousand nodes), then one kernel over all points
+  std::vector<u64> index(h->node_count);
+  CK(cudaMemcpyAsync(index.data(), h->node_index.p, h->node_count * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<double> hdr(h->node_count * 4);
+  for (const Chunk& c : h->chunks) {
+    for (u32 k = 0; k < c.n_nodes; ++k) {
+      const u64 row = c.node_base + k;
+      double mn[3], mx[3];
+      node_bounds_of(h, index[row], (u32)c.levels, mn, mx);
+      const double scale = las_scale_from_bounds(mn, mx);
+      hdr[4 * row + 0] = mn[0];
+      hdr[4 * row + 1] = mn[1];
+      hdr[4 * row + 2] = mn[2];
+      hdr[4 * row + 3] = scale;
+      if (headers_host) {
+        sw_las_node_header& o = headers_host[row];
+        for (int a = 0; a < 3; ++a) {
+          o.offset[a] = mn[a];
+          o.max[a] = mx[a];
+        }
+        o.scale = scale;
+        o.reserved = 0;
+      }
+    }
+  }
+  CK(h->node_hdr.ensure(h->node_count * 32));
+  CK(cudaMemcpyAsync(h->node_hdr.p, hdr.data(), h->node_count * 32, cudaMemcpyHostToDevice, h->stream));
+  launch_payload_las(h->d_xyz, h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, h->node_first.as<u64>(),
+                     (u32)h->node_count, h->node_hdr.as<double>(), xyz_i32_device, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream)); // hdr is a stack-owned staging vector
+  return SW_OK;
+}
+
+int
+swgpu_get_payload_las(swgpu_handle h, int32_t* xyz_i32_host, sw_las_node_header* headers_host)
+{
+  if (!h || !xyz_i32_host)
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  CK(h->payload_tmp.ensure(std::max<u64>(h->out_count, 1) * 12));
+  const int rc = swgpu_get_payload_las_device(h, h->payload_tmp.as<int32_t>(), headers_host);
+  if (rc)
+    return rc;
+  CK(cudaMemcpyAsync(xyz_i32_host, h->payload_tmp.p, h->out_count * 12, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return SW_OK;
 }

@@ -24,6 +24,20 @@ class SwParams(C.Structure):
     ]
 
 
+class SwLasTransform(C.Structure):
+    """sw_las_transform, include/sw_types.h (reference io/LASFile.cpp:79-94, process/TilerProcess.cpp:552-559)."""
+
+    _fields_ = [
+        ("scale", C.c_double * 3),
+        ("offset", C.c_double * 3),
+        ("header_min", C.c_double * 3),
+        ("header_max", C.c_double * 3),
+        ("center", C.c_double * 3),
+        ("shift_to_center", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 class SwgpuStats(C.Structure):
     _fields_ = [
         ("n_points", C.c_uint64),
@@ -60,6 +74,13 @@ SYMBOLS = [
     ("swgpu_reserve", C.c_int, [C.c_void_p, C.c_uint64]),
     ("swgpu_index_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     ("swgpu_index_batch_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    ("swgpu_index_batch_las", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(SwLasTransform)]),
+    ("swgpu_index_batch_las_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(SwLasTransform)]),
+    ("swgpu_get_positions", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("swgpu_get_payload_pnts", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("swgpu_get_payload_pnts_device", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("swgpu_get_payload_las", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("swgpu_get_payload_las_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swgpu_finalize", C.c_int, [C.c_void_p]),
     ("swgpu_result_size", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("swgpu_get_nodes", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -32,6 +32,25 @@ NODE_DTYPE = np.dtype(
     [("index", "<u8"), ("levels", "<u4"), ("flags", "<u4"), ("first", "<u8"), ("count", "<u8")])
 
 
+# sw_las_node_header, include/sw_types.h: what LASPersistence::persist_points writes into a node's LAS header
+LAS_HEADER_DTYPE = np.dtype([("offset", "<f8", 3), ("scale", "<f8"), ("max", "<f8", 3), ("reserved", "<f8")])
+
+
+def las_transform(scale, offset, header_min, header_max, center=None):
+    """sw_las_transform: LAS header scale/offset/bounds (position_from_las_point, io/LASFile.cpp:79-94) and,
+    when `center` is given, the shift-to-centre + float32 rounding of the 3DTILES pipeline
+    (process/TilerProcess.cpp:552-559; center = cubic_bounds.getCenter())."""
+    t = native.SwLasTransform()
+    for a in range(3):
+        t.scale[a] = float(scale[a])
+        t.offset[a] = float(offset[a])
+        t.header_min[a] = float(header_min[a])
+        t.header_max[a] = float(header_max[a])
+        t.center[a] = float(center[a]) if center is not None else 0.0
+    t.shift_to_center = 1 if center is not None else 0
+    return t
+
+
 class SwgpuError(RuntimeError):
     """Raised for every non-zero return code; the reference throws std::runtime_error instead."""
 
@@ -174,6 +193,29 @@ class GpuTiler:
             self._check(self._lib.swgpu_index_batch_device(self._h, C.c_void_p(points.data_ptr()), n))
         return n
 
+    def build_execution_graph_las(self, las_xyz, transform):
+        """One batch that is still in LAS record form: `las_xyz` host numpy (n,3) int32 (laszip_point X/Y/Z)
+        or a CUDA tensor of n*3 int32; `transform` from las_transform().  The positions are computed on
+        the device exactly as the reference's reader + point transformation compute them."""
+        if isinstance(las_xyz, np.ndarray):
+            if las_xyz.dtype != np.int32 or not las_xyz.flags["C_CONTIGUOUS"]:
+                raise ValueError("LAS coordinates must be C-contiguous int32")
+            n = las_xyz.size // 3
+            self._check(self._lib.swgpu_index_batch_las(self._h, C.c_void_p(las_xyz.ctypes.data), n, C.byref(transform)))
+        else:
+            n = las_xyz.numel() // 3
+            self._keepalive = las_xyz
+            self._check(self._lib.swgpu_index_batch_las_device(self._h, C.c_void_p(las_xyz.data_ptr()), n,
+                                                               C.byref(transform)))
+        self._n_last = n
+        return n
+
+    def positions(self, n):
+        """PointBuffer positions of the last batch (n x 3 float64, original order, after clamping)."""
+        out = np.empty((int(n), 3), np.float64)
+        self._check(self._lib.swgpu_get_positions(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
     def finalize(self):
         self._check(self._lib.swgpu_finalize(self._h))
 
@@ -204,6 +246,24 @@ class GpuTiler:
         ids = ids_out if ids_out is not None else np.empty(ni, np.uint32)
         self._check(self._lib.swgpu_get_nodes(self._h, C.c_void_p(nodes.ctypes.data), C.c_void_p(ids.ctypes.data)))
         return TileResult(nodes[:nn], ids[:ni], self.start_level())
+
+    # -- writer payloads (node-major, same order as result().ids) -----------------------------------
+    def payload_pnts(self, out=None):
+        """float32 positions as PNTSWriter's PositionAttribute stores them (io/PNTSWriter.cpp:326-342)."""
+        _, ni = self.result_size()
+        out = out if out is not None else np.empty((ni, 3), np.float32)
+        self._check(self._lib.swgpu_get_payload_pnts(self._h, C.c_void_p(out.ctypes.data)))
+        return out[:ni]
+
+    def payload_las(self, out=None):
+        """(int32 record coordinates, per-node LAS header values) as LASPersistence::persist_points writes
+        them (io/LASPersistence.h:119-131,160-163)."""
+        nn, ni = self.result_size()
+        out = out if out is not None else np.empty((ni, 3), np.int32)
+        headers = np.zeros(nn, LAS_HEADER_DTYPE)
+        self._check(self._lib.swgpu_get_payload_las(self._h, C.c_void_p(out.ctypes.data),
+                                                    C.c_void_p(headers.ctypes.data)))
+        return out[:ni], headers
 
     def result_device_ids(self, ids_device_ptr):
         nn, _ = self.result_size()
