@@ -18,6 +18,16 @@
 // =============================================================================================
 #define MORTON_THREADS 256
 
+// Radix of the sort (K2).  A MortonIndex64 has 63 significant bits: 9-bit digits sort it in 7 passes
+// instead of the 8 that 8-bit digits need (one read + one write of every pair less).  One thread per
+// digit value in K2, so a CTA has RS_RADIX threads.
+#ifndef RS_BITS
+#define RS_BITS 8
+#endif
+#define RS_RADIX (1 << RS_BITS)
+#define RS_PASSES ((63 + RS_BITS - 1) / RS_BITS)
+#define RS_DIGIT_MASK ((u32)(RS_RADIX - 1))
+
 __device__ __forceinline__ u64
 morton_from_position(double x, double y, double z, const SwBounds& b)
 {
@@ -62,8 +72,8 @@ __device__ __forceinline__ void
 hist_add(u32* s_hist, u64 key)
 {
 #pragma unroll
-  for (int p = 0; p < 8; ++p)
-    atomicAdd(&s_hist[p * 256 + (u32)((key >> (8 * p)) & 255)], 1u);
+  for (int p = 0; p < RS_PASSES; ++p)
+    atomicAdd(&s_hist[p * RS_RADIX + ((u32)(key >> (RS_BITS * p)) & RS_DIGIT_MASK)], 1u);
 }
 
 // Each thread indexes two consecutive points: 48 bytes = three 16-byte loads.
@@ -71,8 +81,8 @@ __global__ void __launch_bounds__(MORTON_THREADS)
 morton_encode_kernel(double* __restrict__ xyz, u64 n, SwBounds b, u64* __restrict__ keys, u32* __restrict__ hist,
                      u32* __restrict__ n_clamped)
 {
-  __shared__ u32 s_hist[8 * 256];
-  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS)
+  __shared__ u32 s_hist[RS_PASSES * RS_RADIX];
+  for (int i = threadIdx.x; i < RS_PASSES * RS_RADIX; i += MORTON_THREADS)
     s_hist[i] = 0;
   __syncthreads();
 
@@ -113,7 +123,7 @@ morton_encode_kernel(double* __restrict__ xyz, u64 n, SwBounds b, u64* __restric
   if (clamped)
     atomicAdd(n_clamped, clamped);
   __syncthreads();
-  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS) {
+  for (int i = threadIdx.x; i < RS_PASSES * RS_RADIX; i += MORTON_THREADS) {
     const u32 v = s_hist[i];
     if (v)
       atomicAdd(&hist[i], v);
@@ -123,14 +133,14 @@ morton_encode_kernel(double* __restrict__ xyz, u64 n, SwBounds b, u64* __restric
 __global__ void __launch_bounds__(MORTON_THREADS)
 key_histogram_kernel(const u64* __restrict__ keys, u64 n, u32* __restrict__ hist)
 {
-  __shared__ u32 s_hist[8 * 256];
-  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS)
+  __shared__ u32 s_hist[RS_PASSES * RS_RADIX];
+  for (int i = threadIdx.x; i < RS_PASSES * RS_RADIX; i += MORTON_THREADS)
     s_hist[i] = 0;
   __syncthreads();
   for (u64 i = (u64)blockIdx.x * MORTON_THREADS + threadIdx.x; i < n; i += (u64)gridDim.x * MORTON_THREADS)
     hist_add(s_hist, keys[i]);
   __syncthreads();
-  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS) {
+  for (int i = threadIdx.x; i < RS_PASSES * RS_RADIX; i += MORTON_THREADS) {
     const u32 v = s_hist[i];
     if (v)
       atomicAdd(&hist[i], v);
@@ -206,8 +216,8 @@ __global__ void __launch_bounds__(MORTON_THREADS)
 las_encode_kernel(const int* __restrict__ las, u64 n, SwLasTransform t, SwBounds b, double* __restrict__ xyz_out,
                   u64* __restrict__ keys, u32* __restrict__ hist, u32* __restrict__ n_clamped)
 {
-  __shared__ u32 s_hist[8 * 256];
-  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS)
+  __shared__ u32 s_hist[RS_PASSES * RS_RADIX];
+  for (int i = threadIdx.x; i < RS_PASSES * RS_RADIX; i += MORTON_THREADS)
     s_hist[i] = 0;
   __syncthreads();
 
@@ -246,7 +256,7 @@ las_encode_kernel(const int* __restrict__ las, u64 n, SwLasTransform t, SwBounds
   if (clamped)
     atomicAdd(n_clamped, clamped);
   __syncthreads();
-  for (int i = threadIdx.x; i < 8 * 256; i += MORTON_THREADS) {
+  for (int i = threadIdx.x; i < RS_PASSES * RS_RADIX; i += MORTON_THREADS) {
     const u32 v = s_hist[i];
     if (v)
       atomicAdd(&hist[i], v);
@@ -266,35 +276,37 @@ launch_las_encode(const int* las, u64 n, const SwLasTransform& t, const SwBounds
 // =============================================================================================
 // K2  onesweep LSD radix sort, 8-bit digits, u64 keys + u32 payload
 // =============================================================================================
-#define RS_THREADS 256
+#define RS_THREADS RS_RADIX
 #define RS_WARPS (RS_THREADS / 32)
+#ifndef RS_ITEMS
 #define RS_ITEMS 16
-#define RS_TILE (RS_THREADS * RS_ITEMS) // 4096 pairs per tile
-#define RS_RADIX 256
+#endif
+#define RS_TILE (RS_THREADS * RS_ITEMS) // pairs per tile: 4096 (8-bit digits) or 8192 (9-bit)
 #ifndef RS_MATCH_MODE
 #define RS_MATCH_MODE 2 /* 0 = __match_any_sync, 1 = eight ballots, 2 = shared-memory atomicOr */
 #endif
 #define RS_LOOK 8 /* look-back descriptors fetched per round trip */
 #ifndef RS_MIN_CTAS
-#define RS_MIN_CTAS 4 /* CTAs per SM the register allocation is capped for */
+#define RS_MIN_CTAS (1024 / RS_THREADS) /* CTAs per SM the register allocation is capped for: 32 warps per SM */
 #endif
 
 #define RS_FLAG_AGG (1u << 30)
 #define RS_FLAG_PFX (2u << 30)
 #define RS_VAL_MASK ((1u << 30) - 1)
 
-// exclusive scan of the 8 x 256 histogram rows, in place (one block, one row per warp)
+// exclusive scan of the RS_PASSES x RS_RADIX histogram rows, in place (one block, one row per warp)
 __global__ void
 digit_base_kernel(u32* __restrict__ hist)
 {
+  constexpr int PER_LANE = RS_RADIX / 32;
   const int row = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  u32* h = hist + row * 256;
-  u32 v[8];
+  u32* h = hist + row * RS_RADIX;
+  u32 v[PER_LANE];
   u32 sum = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    v[i] = h[lane * 8 + i];
+  for (int i = 0; i < PER_LANE; ++i) {
+    v[i] = h[lane * PER_LANE + i];
     sum += v[i];
   }
   u32 incl = sum;
@@ -306,8 +318,8 @@ digit_base_kernel(u32* __restrict__ hist)
   }
   u32 run = incl - sum;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h[lane * 8 + i] = run;
+  for (int i = 0; i < PER_LANE; ++i) {
+    h[lane * PER_LANE + i] = run;
     run += v[i];
   }
 }
@@ -330,7 +342,7 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
                      u32* __restrict__ vals_out, u32 n, const u32* __restrict__ digit_base, u32* __restrict__ status,
                      u32* __restrict__ ticket)
 {
-  constexpr int SHIFT = 8 * PASS;
+  constexpr int SHIFT = RS_BITS * PASS;
   extern __shared__ __align__(16) unsigned char smem[];
   u64* s_keys = reinterpret_cast<u64*>(smem);               // RS_TILE * 8
   u32* s_vals = reinterpret_cast<u32*>(smem + RS_TILE * 8); // RS_TILE * 4
@@ -375,7 +387,7 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
   uint2* my_tab = s_tab + warp * RS_RADIX;
 #pragma unroll
   for (int j = 0; j < RS_ITEMS; ++j)
-    atomicAdd(&my_tab[(u32)(key[j] >> SHIFT) & 255u].y, 1u);
+    atomicAdd(&my_tab[(u32)(key[j] >> SHIFT) & RS_DIGIT_MASK].y, 1u);
   __syncthreads();
 
   u32 my_excl;  // tile-local exclusive offset of digit `tid`
@@ -430,7 +442,7 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
     const u32 lane_bit = 1u << lane;
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
-      uint2* e = &my_tab[(u32)(key[j] >> SHIFT) & 255u];
+      uint2* e = &my_tab[(u32)(key[j] >> SHIFT) & RS_DIGIT_MASK];
       atomicOr(&e->x, lane_bit);
       __syncwarp();
       const uint2 v = *e; // .x = group, .y = first free rank
@@ -444,7 +456,7 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
 #else
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
-      const u32 d = (u32)(key[j] >> SHIFT) & 255u;
+      const u32 d = (u32)(key[j] >> SHIFT) & RS_DIGIT_MASK;
 #if RS_MATCH_MODE == 1
       u32 peers = 0xffffffffu;
 #pragma unroll
@@ -528,7 +540,7 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
     for (int k = 0; k < RS_ITEMS; ++k) {
       const u32 p = tid + k * RS_THREADS;
       const u64 kk = s_keys[p];
-      const u32 dst = s_gofs[(u32)(kk >> SHIFT) & 255u] + p;
+      const u32 dst = s_gofs[(u32)(kk >> SHIFT) & RS_DIGIT_MASK] + p;
       keys_out[dst] = kk;
       vals_out[dst] = s_vals[p];
     }
@@ -538,7 +550,7 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
       const u32 p = tid + k * RS_THREADS;
       if (p < valid) {
         const u64 kk = s_keys[p];
-        const u32 dst = s_gofs[(u32)(kk >> SHIFT) & 255u] + p;
+        const u32 dst = s_gofs[(u32)(kk >> SHIFT) & RS_DIGIT_MASK] + p;
         keys_out[dst] = kk;
         vals_out[dst] = s_vals[p];
       }
@@ -570,6 +582,24 @@ launch_onesweep_pass(const u64* kin, const u32* vin, u64* kout, u32* vout, u32 n
   kernel<<<tiles, RS_THREADS, RS_SMEM_BYTES, stream>>>(kin, vin, kout, vout, n, digit_base, status, ticket);
 }
 
+size_t
+sort_hist_words()
+{
+  return (size_t)RS_PASSES * RS_RADIX;
+}
+
+int
+sort_passes()
+{
+  return RS_PASSES;
+}
+
+int
+sort_input_buffer()
+{
+  return RS_PASSES & 1; // an odd number of ping-pongs ends in buffer 0 when it starts in buffer 1
+}
+
 void
 launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hist, u32* status, u32* ticket,
                   cudaStream_t stream)
@@ -577,16 +607,16 @@ launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hi
   if (n == 0)
     return;
   const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
-  digit_base_kernel<<<1, 256, 0, stream>>>(hist);
+  digit_base_kernel<<<1, RS_PASSES * 32, 0, stream>>>(hist);
   cudaMemsetAsync(ticket, 0, 8 * sizeof(u32), stream);
-  u64* kin = keys0;
-  u64* kout = keys1;
-  u32* vin = vals0;
-  u32* vout = vals1;
-  for (int pass = 0; pass < 8; ++pass) {
-    // two status arrays alternate so that the memset of pass p+1 is independent of pass p's kernel
+  const bool from1 = sort_input_buffer() == 1;
+  u64* kin = from1 ? keys1 : keys0;
+  u64* kout = from1 ? keys0 : keys1;
+  u32* vin = from1 ? vals1 : vals0;
+  u32* vout = from1 ? vals0 : vals1;
+  for (int pass = 0; pass < RS_PASSES; ++pass) {
     cudaMemsetAsync(status, 0, (size_t)tiles * RS_RADIX * sizeof(u32), stream);
-    const u32* base = hist + pass * 256;
+    const u32* base = hist + pass * RS_RADIX;
     u32* tk = ticket + pass;
     switch (pass) {
       case 0: launch_onesweep_pass<0>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
@@ -595,8 +625,12 @@ launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hi
       case 3: launch_onesweep_pass<3>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
       case 4: launch_onesweep_pass<4>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
       case 5: launch_onesweep_pass<5>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+#if RS_PASSES > 7
       case 6: launch_onesweep_pass<6>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
       default: launch_onesweep_pass<7>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+#else
+      default: launch_onesweep_pass<6>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+#endif
     }
     u64* tk2 = kin;
     kin = kout;

@@ -1118,20 +1118,30 @@ launch_select_argmin(const SwArgminArgs& a, u64* status, u32* ticket, cudaStream
 // spacing because its cells are 5 spacings wide), so the result is the lexicographically first
 // maximal independent set of the "closer than spacing" graph.
 //
-// Parallel formulation (exact): a point is REJECTED as soon as one earlier in-range point is
-// ACCEPTED, and ACCEPTED once every earlier in-range point is REJECTED.  Candidates are found
-// through Morton cells whose side is >= spacing: the list is sorted, so a cell is a contiguous run
-// and "earlier" = earlier in the own cell + every point of the neighbour cells with a smaller
-// Morton code.  Each undecided point scans its candidates in a fixed order with a persistent
-// cursor and stops at the first in-range candidate that is still undecided.  One cooperative
-// kernel iterates to the fix point with grid-wide barriers and a shrinking work list.
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
-
+// Parallel formulation (exact): only ACCEPTED points ever influence a decision, and a point can only
+// be influenced by points that precede it in Morton order.  The list is sorted, so a Morton cell whose
+// side is >= spacing is a contiguous run, every point within the spacing lies in the same or an
+// adjacent cell, and all points of an adjacent cell with a smaller Morton code precede all points of
+// this cell.  Cells are therefore processed as a wavefront in Morton order: a cell waits until its (at
+// most 26) earlier neighbour cells of the same node have published their accepted points, then walks
+// its own points in order, 32 (or 256) at a time: every point is first tested against the accepted
+// points known so far (neighbours + own), the survivors of a batch are resolved in order by one warp.
+// Cells are handed out through an atomic ticket in Morton order, so every cell a group waits for is
+// already owned by a resident group (the decoupled look-back argument): no deadlock, no grid barrier,
+// and every point is touched once.  The critical path is the longest chain of adjacent cells with
+// increasing Morton code inside one node (measured: ~4 000 cells for a 128 x 128 x 4 terrain slab).
+// md_wave_warp_kernel gives a cell to one warp (sparse levels: few points per cell, many cells),
+// md_wave_cta_kernel to a whole CTA (dense levels: thousands of points per cell on the critical path).
+//
+// (Round 1 used fix-point rounds over an "undecided" work list in a cooperative kernel: exact too, but
+// the blocked-on chains run through points that are about to be rejected -- 13 000 rounds for one
+// million terrain points, 1.2 s.)
 #define MD_UNDECIDED 0
 #define MD_ACCEPTED 1
 #define MD_REJECTED 2
 #define MD_NBR_SLOTS 27 /* slot 0 = count, then up to 26 earlier neighbour cells */
+#define MD_OWN_CAP 64   /* accepted points of one cell: pairwise >= spacing apart inside a cube of side < 2 spacings */
+#define MD_DESC_DONE (1ull << 63) /* cell descriptor: done | accepted count << 32 | offset into acc_xyz */
 
 static cudaError_t
 grow(SwGrowBuf& b, size_t bytes)
@@ -1152,8 +1162,8 @@ grow(SwGrowBuf& b, size_t bytes)
 void
 free_min_distance_scratch(SwMinDistScratch& sc)
 {
-  SwGrowBuf* all[] = { &sc.cell_start, &sc.cell_tile_rank0, &sc.cell_of, &sc.state, &sc.cur_off, &sc.cur_seg, &sc.lpos,
-                       &sc.wl0,        &sc.wl1,             &sc.hkeys,   &sc.hvals, &sc.nbr,     &sc.counters };
+  SwGrowBuf* all[] = { &sc.cell_start, &sc.cell_tile_rank0, &sc.state, &sc.lpos, &sc.desc,  &sc.acc_xyz,    &sc.hkeys,
+                       &sc.hvals,      &sc.nbr,             &sc.deps,  &sc.queue, &sc.cell_active, &sc.counters };
   for (SwGrowBuf* b : all) {
     if (b->p)
       cudaFree(b->p);
@@ -1162,52 +1172,39 @@ free_min_distance_scratch(SwMinDistScratch& sc)
   }
 }
 
-// per point: cell rank, activity (take-all nodes are never sampled), compact position copy
+// per point: activity (take-all nodes are never sampled), compact position copy; counts the active points
 __global__ void __launch_bounds__(SWP_THREADS)
-md_setup_kernel(SwMinDistArgs a, int cell_shift, const u32* __restrict__ cell_tile_rank0, u32* __restrict__ cell_of,
-                unsigned char* __restrict__ state, u32* __restrict__ cur_off, unsigned char* __restrict__ cur_seg,
-                double* __restrict__ lpos)
+md_setup_kernel(SwMinDistArgs a, unsigned char* __restrict__ state, double* __restrict__ lpos,
+                u32* __restrict__ n_active)
 {
   __shared__ u32 s_w[SWP_WARPS];
-  __shared__ u32 s_w2[SWP_WARPS];
   const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 tile = blockIdx.x;
   const u64 base = (u64)tile * SW_SWEEP_TILE;
   const u32 lt = lanemask_lt();
-  u32 nmask[SWP_ITEMS], cmask[SWP_ITEMS];
-  u32 wn = 0, wc = 0;
+  u32 nmask[SWP_ITEMS];
+  u32 wn = 0;
 #pragma unroll
   for (int j = 0; j < SWP_ITEMS; ++j) {
     const u64 i = base + item_pos(warp, lane, j);
-    bool nh = false, ch = false;
+    bool nh = false;
     if (i < a.count) {
       const u64 k = a.in_key[i] & SW_KEY_MASK;
-      if (i == 0) {
-        nh = ch = true;
-      } else {
-        const u64 pk = a.in_key[i - 1] & SW_KEY_MASK;
-        nh = (k >> a.node_shift) != (pk >> a.node_shift);
-        ch = (k >> cell_shift) != (pk >> cell_shift);
-      }
+      nh = (i == 0) || (k >> a.node_shift) != ((a.in_key[i - 1] & SW_KEY_MASK) >> a.node_shift);
     }
     nmask[j] = __ballot_sync(0xffffffffu, nh);
-    cmask[j] = __ballot_sync(0xffffffffu, ch);
     wn += __popc(nmask[j]);
-    wc += __popc(cmask[j]);
   }
-  u32 tn, tc;
+  u32 tn;
   const u32 nexcl = warp_totals_exclusive(wn, warp, lane, s_w, tn);
-  const u32 cexcl = warp_totals_exclusive(wc, warp, lane, s_w2, tc);
   u32 nrun = a.tile_rank0[tile] + nexcl;
-  u32 crun = cell_tile_rank0[tile] + cexcl;
+  u32 my_active = 0;
 #pragma unroll
   for (int j = 0; j < SWP_ITEMS; ++j) {
     const u64 i = base + item_pos(warp, lane, j);
     const u32 self = lt | (1u << lane);
     const u32 node_rank = nrun + __popc(nmask[j] & self) - 1;
-    const u32 cell_rank = crun + __popc(cmask[j] & self) - 1;
     nrun += __popc(nmask[j]);
-    crun += __popc(cmask[j]);
     if (i < a.count) {
       bool active = true;
       if (a.allow_take_all) {
@@ -1218,10 +1215,8 @@ md_setup_kernel(SwMinDistArgs a, int cell_shift, const u32* __restrict__ cell_ti
       // the node's range are analysed, every other point is rejected without touching the grid
       if (a.nth_point > 1 && ((u32)i - a.node_start[node_rank]) % a.nth_point != 0)
         active = false;
-      cell_of[i] = cell_rank;
       state[i] = active ? MD_UNDECIDED : MD_REJECTED;
-      cur_off[i] = 0;
-      cur_seg[i] = 0;
+      my_active += active ? 1u : 0u;
       if (lpos) {
         const u64 idx = a.in_idx[i];
         lpos[3 * i] = a.pos_sorted[3 * idx];
@@ -1230,6 +1225,11 @@ md_setup_kernel(SwMinDistArgs a, int cell_shift, const u32* __restrict__ cell_ti
       }
     }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    my_active += __shfl_xor_sync(0xffffffffu, my_active, o);
+  if (lane == 0 && my_active)
+    atomicAdd(n_active, my_active);
 }
 
 __device__ __forceinline__ u32
@@ -1241,14 +1241,22 @@ md_hash(u64 code, u32 mask)
   return (u32)code & mask;
 }
 
+// One thread per cell: is there anything to analyse in the cell (cells of take-all nodes are not), and
+// where is the cell in the hash table of occupied cells.
 __global__ void __launch_bounds__(256)
 md_hash_insert_kernel(const u64* __restrict__ in_key, const u32* __restrict__ cell_start, u32 n_cells, int cell_shift,
+                      const unsigned char* __restrict__ state, unsigned char* __restrict__ cell_active,
                       u64* __restrict__ hkeys, u32* __restrict__ hvals, u32 mask)
 {
   const u32 c = blockIdx.x * 256 + threadIdx.x;
   if (c >= n_cells)
     return;
-  const u64 code = (in_key[cell_start[c]] & SW_KEY_MASK) >> cell_shift;
+  const u32 b = cell_start[c], e = cell_start[c + 1];
+  bool active = false;
+  for (u32 i = b; i < e && !active; ++i) // analysed cells answer at their first point
+    active = state[i] == MD_UNDECIDED;
+  cell_active[c] = active ? 1 : 0;
+  const u64 code = (in_key[b] & SW_KEY_MASK) >> cell_shift;
   u32 slot = md_hash(code, mask);
   while (true) {
     const u64 prev = atomicCAS(&hkeys[slot], 0ull, code + 1);
@@ -1260,17 +1268,25 @@ md_hash_insert_kernel(const u64* __restrict__ in_key, const u32* __restrict__ ce
   }
 }
 
-// earlier neighbour cells (smaller Morton code, same node) of every cell
+// Neighbour cells of every analysed cell, same node only: the EARLIER ones (smaller Morton code: their
+// accepted points constrain this cell) and the LATER ones (they wait for this cell).  Cells without
+// analysed points never hold an accepted point and are left out on both sides.  A cell whose earlier
+// list is empty is ready at once and goes straight into the ready queue.
+// nbr row: [0] = earlier count | later count << 8, [1 ...] = earlier cells, then later cells.
+// counters: [0] pop ticket, [1] next free slot of acc_xyz, [2] error flag, [3] active points,
+//           [4] cell count (node_rle), [5] analysed cells, [6] push ticket
 __global__ void __launch_bounds__(256)
 md_neighbors_kernel(const u64* __restrict__ in_key, const u32* __restrict__ cell_start, u32 n_cells, int cell_shift,
-                    int cell_levels, int node_levels, const u64* __restrict__ hkeys, const u32* __restrict__ hvals,
-                    u32 mask, u32* __restrict__ nbr)
+                    int cell_levels, int node_levels, const unsigned char* __restrict__ cell_active,
+                    const u64* __restrict__ hkeys, const u32* __restrict__ hvals, u32 mask, u32* __restrict__ nbr,
+                    u32* __restrict__ deps, u32* __restrict__ queue, u32* __restrict__ counters)
 {
   const u32 c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= n_cells)
+  if (c >= n_cells || !cell_active[c])
     return;
   u32* out = nbr + (size_t)c * MD_NBR_SLOTS;
-  u32 cnt = 0;
+  u32 later[26];
+  u32 n_early = 0, n_late = 0;
   const int below = cell_levels - node_levels; // cell levels below the node
   if (below > 0) {
     const u64 code = (in_key[cell_start[c]] & SW_KEY_MASK) >> cell_shift;
@@ -1288,7 +1304,7 @@ md_neighbors_kernel(const u64* __restrict__ in_key, const u32* __restrict__ cell
           if (X < 0 || Y < 0 || Z < 0 || X >= side || Y >= side || Z >= side)
             continue;
           const u64 nc = expand_bits_by_3((u64)Z) | (expand_bits_by_3((u64)Y) << 1) | (expand_bits_by_3((u64)X) << 2);
-          if (nc >= code || (nc >> (3 * below)) != node_prefix)
+          if ((nc >> (3 * below)) != node_prefix)
             continue;
           u32 slot = md_hash(nc, mask);
           while (true) {
@@ -1296,127 +1312,361 @@ md_neighbors_kernel(const u64* __restrict__ in_key, const u32* __restrict__ cell
             if (k == 0ull)
               break;
             if (k == nc + 1) {
-              out[1 + cnt++] = hvals[slot];
+              const u32 other = hvals[slot];
+              if (cell_active[other]) {
+                if (nc < code)
+                  out[1 + n_early++] = other;
+                else
+                  later[n_late++] = other;
+              }
               break;
             }
             slot = (slot + 1) & mask;
           }
         }
   }
-  out[0] = cnt;
+  for (u32 k = 0; k < n_late; ++k)
+    out[1 + n_early + k] = later[k];
+  out[0] = n_early | (n_late << 8);
+  deps[c] = n_early;
+  atomicAdd(&counters[5], 1u);
+  if (n_early == 0)
+    queue[atomicAdd(&counters[6], 1u)] = c;
 }
 
-__device__ __forceinline__ unsigned char
-ld_state(const unsigned char* p)
+#define MD_QUEUE_EMPTY 0xffffffffu
+
+__device__ __forceinline__ u32
+ld_acquire_u32(const u32* p)
 {
-  return __ldcg(p); // L2: sees decisions made by other SMs during the same round
+  u32 v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
-// counters: [0] work-list length A, [1] work-list length B, [2] rounds
-__global__ void __launch_bounds__(256)
-md_rounds_kernel(u64 count, const double* __restrict__ P, const u32* __restrict__ cell_start,
-                 const u32* __restrict__ cell_of, const u32* __restrict__ nbr, unsigned char* state,
-                 u32* __restrict__ cur_off, unsigned char* __restrict__ cur_seg, u32* wl0, u32* wl1, u32* counters,
-                 double threshold)
+__device__ __forceinline__ void
+st_release_u32(u32* p, u32 v)
 {
-  cg::grid_group grid = cg::this_grid();
-  const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  const u64 nthreads = (u64)gridDim.x * blockDim.x;
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Takes the next ready cell.  Every analysed cell is pushed exactly once (when its last earlier neighbour
+// finishes, or by md_neighbors_kernel when it has none), so tickets below the analysed-cell count are
+// always served; whoever waits, waits on its own queue slot.  Returns MD_QUEUE_EMPTY when all cells are
+// handed out.  Called by one thread.
+__device__ __forceinline__ u32
+md_pop_cell(const u32* queue, u32* counters)
+{
+  const u32 t = atomicAdd(&counters[0], 1u);
+  if (t >= __ldcg(&counters[5]))
+    return MD_QUEUE_EMPTY;
+  u32 c;
+  while ((c = ld_acquire_u32(queue + t)) == MD_QUEUE_EMPTY)
+    __nanosleep(100);
+  return c;
+}
+
+// This cell is finished (its accepted points and descriptor are written and fenced): release the later
+// neighbours, queue those that have become ready.  Called by up to 26 threads, one per later neighbour.
+__device__ __forceinline__ void
+md_release_later(u32 cell, u32* deps, u32* queue, u32* counters)
+{
+  if (atomicSub(&deps[cell], 1u) == 1u) {
+    __threadfence(); // everything the other earlier neighbours published is visible before the push
+    st_release_u32(queue + atomicAdd(&counters[6], 1u), cell);
+  }
+}
+
+// squared distance exactly as Vector3::squaredDistanceTo (math/Vector3.h:55-62): x*x + y*y + z*z, no FMA
+__device__ __forceinline__ bool
+md_in_range(double px, double py, double pz, double qx, double qy, double qz, double threshold)
+{
+  const double dx = px - qx, dy = py - qy, dz = pz - qz;
+  return dx * dx + dy * dy + dz * dz < threshold;
+}
+
+// Tests one point against a list of accepted points; the warp leaves the loop as soon as none of its
+// lanes is a candidate any more (in a dense cell the first few accepted points reject almost everything).
+__device__ __forceinline__ bool
+md_filter(bool cand, double px, double py, double pz, const double* acc, u32 n, double threshold)
+{
+  for (u32 k = 0; k < n; ++k) {
+    if ((k & 3u) == 0 && !__any_sync(0xffffffffu, cand))
+      break;
+    if (cand && md_in_range(px, py, pz, acc[3 * k], acc[3 * k + 1], acc[3 * k + 2], threshold))
+      cand = false;
+  }
+  return cand;
+}
+
+// Resolves the surviving candidates of one warp-wide batch in lane (= point) order: the first candidate
+// is accepted, every later candidate within the spacing of it is dropped, and so on.  The accepted
+// positions are appended to `own` at [n_own ...); returns whether this lane's point was accepted.
+__device__ __forceinline__ bool
+md_resolve_warp(bool cand, double px, double py, double pz, double threshold, double* own, u32& n_own, u32* error_flag)
+{
   const u32 lane = threadIdx.x & 31;
-  u64 work = count; // round 0 visits every point
-  u32* wl_in = nullptr;
-  u32* wl_out = wl0;
-  u32 round = 0;
+  bool accepted = false;
+  u32 m = __ballot_sync(0xffffffffu, cand);
+  while (m) {
+    const int l = __ffs(m) - 1;
+    const double ax = __shfl_sync(0xffffffffu, px, l);
+    const double ay = __shfl_sync(0xffffffffu, py, l);
+    const double az = __shfl_sync(0xffffffffu, pz, l);
+    if ((int)lane == l) {
+      accepted = true;
+      cand = false;
+      if (n_own < MD_OWN_CAP) {
+        own[3 * n_own] = ax;
+        own[3 * n_own + 1] = ay;
+        own[3 * n_own + 2] = az;
+      } else {
+        atomicExch(error_flag, 1u); // cannot happen for cells of side < 2 spacings; reported, never silent
+      }
+    } else if (cand && md_in_range(px, py, pz, ax, ay, az, threshold)) {
+      cand = false;
+    }
+    if (n_own < MD_OWN_CAP)
+      ++n_own;
+    m = __ballot_sync(0xffffffffu, cand);
+  }
+  return accepted;
+}
+
+// counters: [0] cell ticket, [1] next free slot of acc_xyz, [2] error flag, [3] active points,
+//           [4] cell count (node_rle)
+#define MDW_WARP_NBR_CAP 96
+#define MDW_WARP_CAP (MD_OWN_CAP + MDW_WARP_NBR_CAP)
+
+// one warp per cell (sparse levels)
+__global__ void __launch_bounds__(256)
+md_wave_warp_kernel(const double* __restrict__ P, const u32* __restrict__ cell_start, const u32* __restrict__ nbr,
+                    unsigned char* __restrict__ state, u64* desc, double* acc_xyz, u32* deps, u32* queue,
+                    u32* counters, double threshold)
+{
+  __shared__ double s_acc[8][MDW_WARP_CAP * 3];
+  const u32 lane = threadIdx.x & 31;
+  double* own = s_acc[threadIdx.x >> 5];  // own accepted points first: they reject most of a dense cell
+  double* nacc = own + MD_OWN_CAP * 3;    // then the neighbours' accepted points
   while (true) {
-    u32* out_count = counters + (round & 1u);
-    // uniform trip count per warp so that the aggregated append below stays convergent
-    const u64 iters = (work + nthreads - 1) / nthreads;
-    for (u64 it = 0; it < iters; ++it) {
-      const u64 w = it * nthreads + tid;
-      bool still = false;
-      u32 i = 0;
-      if (w < work) {
-        i = wl_in ? wl_in[w] : (u32)w;
-        if (ld_state(state + i) == MD_UNDECIDED) {
-          const u32 c = cell_of[i];
-          const u32* nb = nbr + (size_t)c * MD_NBR_SLOTS;
-          const u32 nseg = 1 + nb[0];
-          u32 seg = cur_seg[i], off = cur_off[i];
-          const double px = P[3 * (u64)i], py = P[3 * (u64)i + 1], pz = P[3 * (u64)i + 2];
-          int decided = 0;
-          while (seg < nseg) {
-            u32 b, e;
-            if (seg == 0) {
-              b = cell_start[c];
-              e = i;
-            } else {
-              const u32 nc = nb[seg];
-              b = cell_start[nc];
-              e = cell_start[nc + 1];
-            }
-            u32 q = b + off;
-            bool blocked = false;
-            for (; q < e; ++q) {
-              const unsigned char s = ld_state(state + q);
-              if (s == MD_REJECTED)
-                continue;
-              const double dx = px - P[3 * (u64)q];
-              const double dy = py - P[3 * (u64)q + 1];
-              const double dz = pz - P[3 * (u64)q + 2];
-              const double d = dx * dx + dy * dy + dz * dz; // x*x + y*y + z*z, no FMA
-              if (d < threshold) {
-                if (s == MD_ACCEPTED)
-                  decided = MD_REJECTED;
-                else
-                  blocked = true;
-                break;
-              }
-            }
-            if (decided || blocked) {
-              off = q - b;
-              break;
-            }
-            ++seg;
-            off = 0;
-          }
-          if (decided) {
-            state[i] = MD_REJECTED;
-          } else if (seg >= nseg) {
-            state[i] = MD_ACCEPTED;
-          } else {
-            cur_seg[i] = (unsigned char)seg;
-            cur_off[i] = off;
-            still = true;
+    u32 c = 0;
+    if (lane == 0)
+      c = md_pop_cell(queue, counters);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c == MD_QUEUE_EMPTY)
+      break;
+    const u32 b = cell_start[c], e = cell_start[c + 1];
+    // every earlier neighbour is finished: fetch their accepted points (one lane per neighbour)
+    const u32* nb = nbr + (size_t)c * MD_NBR_SLOTS;
+    const u32 nn = nb[0] & 0xffu, n_late = nb[0] >> 8;
+    u64 d = 0;
+    if (lane < nn)
+      d = __ldcg(desc + nb[1 + lane]);
+    const u32 ncnt = (u32)(d >> 32) & 0xffu;
+    const u32 noff = (u32)d;
+    u32 incl = ncnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o)
+        incl += t;
+    }
+    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    const bool staged = total <= MDW_WARP_NBR_CAP;
+    if (staged) {
+      const u32 first = incl - ncnt;
+      for (u32 k = 0; k < ncnt; ++k) {
+        const double* src = acc_xyz + 3 * (size_t)(noff + k);
+        nacc[3 * (first + k)] = __ldcg(src);
+        nacc[3 * (first + k) + 1] = __ldcg(src + 1);
+        nacc[3 * (first + k) + 2] = __ldcg(src + 2);
+      }
+    }
+    __syncwarp();
+    u32 n_own = 0;
+    for (u32 base = b; base < e; base += 32) {
+      const u32 i = base + lane;
+      const bool valid = i < e && state[i] == MD_UNDECIDED;
+      double px = 0, py = 0, pz = 0;
+      if (valid) {
+        px = P[3 * (size_t)i];
+        py = P[3 * (size_t)i + 1];
+        pz = P[3 * (size_t)i + 2];
+      }
+      bool cand = md_filter(valid, px, py, pz, own, n_own, threshold);
+      if (staged) {
+        cand = md_filter(cand, px, py, pz, nacc, total, threshold);
+      } else { // more neighbour points than the staging area holds: stream them from L2
+        for (u32 j = 0; j < nn; ++j) {
+          const u32 o = __shfl_sync(0xffffffffu, noff, j), cn = __shfl_sync(0xffffffffu, ncnt, j);
+          for (u32 k = 0; k < cn; ++k) {
+            const double* src = acc_xyz + 3 * (size_t)(o + k);
+            if (cand && md_in_range(px, py, pz, __ldcg(src), __ldcg(src + 1), __ldcg(src + 2), threshold))
+              cand = false;
           }
         }
       }
-      // warp-aggregated append of the points that are still undecided
-      const u32 m = __ballot_sync(0xffffffffu, still);
-      if (m) {
-        u32 basep = 0;
-        if (lane == (u32)(__ffs(m) - 1))
-          basep = atomicAdd(out_count, __popc(m));
-        basep = __shfl_sync(0xffffffffu, basep, __ffs(m) - 1);
-        if (still)
-          wl_out[basep + __popc(m & lanemask_lt())] = i;
+      const bool accepted = md_resolve_warp(cand, px, py, pz, threshold, own, n_own, counters + 2);
+      __syncwarp();
+      if (valid)
+        state[i] = accepted ? MD_ACCEPTED : MD_REJECTED;
+    }
+    // publish the accepted points of this cell
+    u32 off = 0;
+    if (n_own) {
+      if (lane == 0)
+        off = atomicAdd(&counters[1], n_own);
+      off = __shfl_sync(0xffffffffu, off, 0);
+      for (u32 k = lane; k < n_own; k += 32) {
+        double* dst = acc_xyz + 3 * (size_t)(off + k);
+        __stcg(dst, own[3 * k]);
+        __stcg(dst + 1, own[3 * k + 1]);
+        __stcg(dst + 2, own[3 * k + 2]);
+      }
+      __threadfence();
+    }
+    if (lane == 0)
+      __stcg(desc + c, MD_DESC_DONE | ((u64)n_own << 32) | off);
+    __threadfence();
+    __syncwarp();
+    if (lane < n_late)
+      md_release_later(nb[1 + nn + lane], deps, queue, counters);
+  }
+}
+
+// one CTA of T threads per cell (dense levels: thousands of points per cell, every cell on a long chain)
+#define MDW_CTA_NBR_CAP (26 * MD_OWN_CAP)
+#define MDW_CTA_SMEM(T) ((MD_OWN_CAP + MDW_CTA_NBR_CAP) * 24 + (T) * 24 + (T) * 2 + (T))
+
+template<int T>
+__global__ void __launch_bounds__(T)
+md_wave_cta_kernel(const double* __restrict__ P, const u32* __restrict__ cell_start, const u32* __restrict__ nbr,
+                   unsigned char* __restrict__ state, u64* desc, double* acc_xyz, u32* deps, u32* queue,
+                   u32* counters, double threshold)
+{
+  constexpr int WARPS = T / 32;
+  extern __shared__ __align__(16) unsigned char md_smem[];
+  double* own = reinterpret_cast<double*>(md_smem);                        // MD_OWN_CAP x 3
+  double* nacc = own + MD_OWN_CAP * 3;                                     // MDW_CTA_NBR_CAP x 3
+  double* s_p = nacc + MDW_CTA_NBR_CAP * 3;                                // T x 3: the batch's positions
+  unsigned short* s_cand = reinterpret_cast<unsigned short*>(s_p + T * 3); // candidate threads, in order
+  unsigned char* s_flag = reinterpret_cast<unsigned char*>(s_cand + T);    // accepted flag per thread
+  __shared__ u32 s_c, s_total, s_ncand, s_nown, s_off;
+  __shared__ u32 s_noff[32], s_ncnt[32], s_nfirst[32], s_wcount[WARPS];
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  while (true) {
+    if (tid == 0)
+      s_c = md_pop_cell(queue, counters);
+    __syncthreads();
+    const u32 c = s_c;
+    if (c == MD_QUEUE_EMPTY)
+      break;
+    const u32 b = cell_start[c], e = cell_start[c + 1];
+    const u32* nb = nbr + (size_t)c * MD_NBR_SLOTS;
+    const u32 nn = nb[0] & 0xffu, n_late = nb[0] >> 8;
+    if (warp == 0) { // every earlier neighbour is finished: where are their accepted points
+      u64 d = 0;
+      if (lane < nn)
+        d = __ldcg(desc + nb[1 + lane]);
+      const u32 ncnt = (u32)(d >> 32) & 0xffu;
+      u32 incl = ncnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o)
+          incl += t;
+      }
+      s_noff[lane] = (u32)d;
+      s_ncnt[lane] = ncnt;
+      s_nfirst[lane] = incl - ncnt;
+      if (lane == 31)
+        s_total = incl;
+    }
+    __syncthreads();
+    const u32 n_nbr = s_total; // <= 26 * MD_OWN_CAP by construction
+    for (u32 j = warp; j < nn; j += WARPS) // one warp copies one neighbour's accepted points
+      for (u32 k = lane; k < s_ncnt[j]; k += 32) {
+        const double* src = acc_xyz + 3 * (size_t)(s_noff[j] + k);
+        double* dst = nacc + 3 * (s_nfirst[j] + k);
+        dst[0] = __ldcg(src);
+        dst[1] = __ldcg(src + 1);
+        dst[2] = __ldcg(src + 2);
+      }
+    if (tid == 0)
+      s_nown = 0;
+    __syncthreads();
+    for (u32 base = b; base < e; base += T) {
+      const u32 i = base + tid;
+      const bool valid = i < e && state[i] == MD_UNDECIDED;
+      double px = 0, py = 0, pz = 0;
+      if (valid) {
+        px = P[3 * (size_t)i];
+        py = P[3 * (size_t)i + 1];
+        pz = P[3 * (size_t)i + 2];
+      }
+      const u32 n_checked = s_nown;
+      bool cand = md_filter(valid, px, py, pz, own, n_checked, threshold);
+      cand = md_filter(cand, px, py, pz, nacc, n_nbr, threshold);
+      // ordered list of the surviving candidates
+      const u32 wm = __ballot_sync(0xffffffffu, cand);
+      if (lane == 0)
+        s_wcount[warp] = __popc(wm);
+      s_p[3 * tid] = px;
+      s_p[3 * tid + 1] = py;
+      s_p[3 * tid + 2] = pz;
+      s_flag[tid] = 0;
+      __syncthreads();
+      u32 wbase = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w)
+        wbase += (w < (int)warp) ? s_wcount[w] : 0u;
+      if (cand)
+        s_cand[wbase + __popc(wm & lanemask_lt())] = (unsigned short)tid;
+      if (tid == T - 1)
+        s_ncand = wbase + __popc(wm);
+      __syncthreads();
+      if (warp == 0) { // resolve in order, 32 candidates at a time
+        const u32 ncand = s_ncand;
+        u32 n_own = n_checked;
+        for (u32 chunk = 0; chunk < ncand; chunk += 32) {
+          const bool have = chunk + lane < ncand;
+          const u32 t = have ? s_cand[chunk + lane] : 0u;
+          const double qx = s_p[3 * t], qy = s_p[3 * t + 1], qz = s_p[3 * t + 2];
+          bool cc = have;
+          for (u32 k = n_checked; k < n_own; ++k) // accepted earlier in this batch
+            if (cc && md_in_range(qx, qy, qz, own[3 * k], own[3 * k + 1], own[3 * k + 2], threshold))
+              cc = false;
+          if (md_resolve_warp(cc, qx, qy, qz, threshold, own, n_own, counters + 2))
+            s_flag[t] = 1;
+          __syncwarp();
+        }
+        if (lane == 0)
+          s_nown = n_own;
+      }
+      __syncthreads();
+      if (valid)
+        state[i] = s_flag[tid] ? MD_ACCEPTED : MD_REJECTED;
+    }
+    const u32 n_own = s_nown;
+    if (n_own) {
+      if (tid == 0)
+        s_off = atomicAdd(&counters[1], n_own);
+      __syncthreads();
+      if (tid < n_own) {
+        double* dst = acc_xyz + 3 * (size_t)(s_off + tid);
+        __stcg(dst, own[3 * tid]);
+        __stcg(dst + 1, own[3 * tid + 1]);
+        __stcg(dst + 2, own[3 * tid + 2]);
+        __threadfence();
       }
     }
-    __threadfence();
-    grid.sync();
-    const u32 remaining = *((volatile u32*)out_count);
-    ++round;
-    if (remaining == 0)
-      break;
-    // next round reads what was just written; reset the other counter for the round after
-    work = remaining;
-    wl_in = wl_out;
-    wl_out = (wl_out == wl0) ? wl1 : wl0;
     if (tid == 0)
-      counters[round & 1u] = 0;
-    grid.sync();
+      __stcg(desc + c, MD_DESC_DONE | ((u64)n_own << 32) | (n_own ? s_off : 0u));
+    __threadfence();
+    __syncthreads();
+    if (tid < n_late)
+      md_release_later(nb[1 + nn + tid], deps, queue, counters);
   }
-  if (tid == 0)
-    counters[2] = round;
 }
 
 cudaError_t
@@ -1434,12 +1684,8 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
   } while (0)
   MD_TRY(grow(sc.cell_start, (n + 1) * 4));
   MD_TRY(grow(sc.cell_tile_rank0, tiles * 4));
-  MD_TRY(grow(sc.cell_of, n * 4));
   MD_TRY(grow(sc.state, n));
-  MD_TRY(grow(sc.cur_off, n * 4));
-  MD_TRY(grow(sc.cur_seg, n));
-  MD_TRY(grow(sc.wl0, n * 4));
-  MD_TRY(grow(sc.wl1, n * 4));
+  MD_TRY(grow(sc.acc_xyz, n * 24));
   MD_TRY(grow(sc.counters, 64));
   if (a.in_idx)
     MD_TRY(grow(sc.lpos, n * 24));
@@ -1454,13 +1700,18 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
   MD_TRY(cudaMemsetAsync(counters, 0, 64, stream));
   launch_node_rle(a.in_key, n, cell_shift, static_cast<u32*>(sc.cell_start.p), static_cast<u32*>(sc.cell_tile_rank0.p),
                   counters + 4, sc.status, sc.ticket, stream);
-  md_setup_kernel<<<(u32)tiles, SWP_THREADS, 0, stream>>>(
-    a, cell_shift, static_cast<const u32*>(sc.cell_tile_rank0.p), static_cast<u32*>(sc.cell_of.p),
-    static_cast<unsigned char*>(sc.state.p), static_cast<u32*>(sc.cur_off.p), static_cast<unsigned char*>(sc.cur_seg.p),
-    a.in_idx ? static_cast<double*>(sc.lpos.p) : nullptr);
-  MD_TRY(cudaMemcpyAsync(sc.h_pinned, counters + 4, 4, cudaMemcpyDeviceToHost, stream));
+  md_setup_kernel<<<(u32)tiles, SWP_THREADS, 0, stream>>>(a, static_cast<unsigned char*>(sc.state.p),
+                                                         a.in_idx ? static_cast<double*>(sc.lpos.p) : nullptr,
+                                                         counters + 3);
+  MD_TRY(cudaMemcpyAsync(sc.h_pinned, counters + 3, 8, cudaMemcpyDeviceToHost, stream));
   MD_TRY(cudaStreamSynchronize(stream));
-  const u32 n_cells = sc.h_pinned[0];
+  const u32 n_active = sc.h_pinned[0];
+  const u32 n_cells = sc.h_pinned[1];
+  *rounds = 0;
+  *launches = 2;
+  *bytes = n * (8 + 8 + 1 + (a.in_idx ? 52 : 0));
+  if (n_active == 0) // every node of the level is stored whole
+    return cudaGetLastError();
 
   u32 cap = 64;
   while (cap < 2 * n_cells)
@@ -1468,47 +1719,73 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
   MD_TRY(grow(sc.hkeys, (size_t)cap * 8));
   MD_TRY(grow(sc.hvals, (size_t)cap * 4));
   MD_TRY(grow(sc.nbr, (size_t)n_cells * MD_NBR_SLOTS * 4));
+  MD_TRY(grow(sc.desc, (size_t)n_cells * 8));
+  MD_TRY(grow(sc.deps, (size_t)n_cells * 4));
+  MD_TRY(grow(sc.queue, (size_t)n_cells * 4));
+  MD_TRY(grow(sc.cell_active, (size_t)n_cells));
   MD_TRY(cudaMemsetAsync(sc.hkeys.p, 0, (size_t)cap * 8, stream));
+  MD_TRY(cudaMemsetAsync(sc.queue.p, 0xff, (size_t)n_cells * 4, stream));
+  const double* P = a.in_idx ? static_cast<const double*>(sc.lpos.p) : a.pos_sorted;
+  const u32* cell_start = static_cast<const u32*>(sc.cell_start.p);
+  u32* nbr = static_cast<u32*>(sc.nbr.p);
+  unsigned char* state = static_cast<unsigned char*>(sc.state.p);
+  unsigned char* cell_active = static_cast<unsigned char*>(sc.cell_active.p);
+  u64* desc = static_cast<u64*>(sc.desc.p);
+  u32* deps = static_cast<u32*>(sc.deps.p);
+  u32* queue = static_cast<u32*>(sc.queue.p);
+  double* acc_xyz = static_cast<double*>(sc.acc_xyz.p);
   const u32 cgrid = (n_cells + 255) / 256;
-  md_hash_insert_kernel<<<cgrid, 256, 0, stream>>>(a.in_key, static_cast<const u32*>(sc.cell_start.p), n_cells,
-                                                   cell_shift, static_cast<u64*>(sc.hkeys.p),
-                                                   static_cast<u32*>(sc.hvals.p), cap - 1);
-  md_neighbors_kernel<<<cgrid, 256, 0, stream>>>(a.in_key, static_cast<const u32*>(sc.cell_start.p), n_cells, cell_shift,
-                                                 cell_levels, a.node_levels, static_cast<const u64*>(sc.hkeys.p),
-                                                 static_cast<const u32*>(sc.hvals.p), cap - 1,
-                                                 static_cast<u32*>(sc.nbr.p));
+  md_hash_insert_kernel<<<cgrid, 256, 0, stream>>>(a.in_key, cell_start, n_cells, cell_shift, state, cell_active,
+                                                   static_cast<u64*>(sc.hkeys.p), static_cast<u32*>(sc.hvals.p),
+                                                   cap - 1);
+  md_neighbors_kernel<<<cgrid, 256, 0, stream>>>(a.in_key, cell_start, n_cells, cell_shift, cell_levels, a.node_levels,
+                                                 cell_active, static_cast<const u64*>(sc.hkeys.p),
+                                                 static_cast<const u32*>(sc.hvals.p), cap - 1, nbr, deps, queue,
+                                                 counters);
 
-  // persistent cooperative kernel: as many CTAs as are co-resident
-  static int coop_blocks = 0;
-  if (!coop_blocks) {
+  // persistent dataflow kernel: every resident group pops ready cells until all analysed cells are done
+  static int warp_blocks = 0, cta256_blocks = 0, cta1024_blocks = 0;
+  if (!warp_blocks) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, md_rounds_kernel, 256, 0);
-    coop_blocks = sms * (per_sm > 0 ? per_sm : 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, md_wave_warp_kernel, 256, 0);
+    warp_blocks = sms * (per_sm > 0 ? per_sm : 1);
+    cudaFuncSetAttribute(md_wave_cta_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDW_CTA_SMEM(256));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, md_wave_cta_kernel<256>, 256, MDW_CTA_SMEM(256));
+    cta256_blocks = sms * (per_sm > 0 ? per_sm : 1);
+    cudaFuncSetAttribute(md_wave_cta_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDW_CTA_SMEM(1024));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, md_wave_cta_kernel<1024>, 1024, MDW_CTA_SMEM(1024));
+    cta1024_blocks = sms * (per_sm > 0 ? per_sm : 1);
   }
-  u64 count = n;
-  const double* P = a.in_idx ? static_cast<const double*>(sc.lpos.p) : a.pos_sorted;
-  const u32* cell_start = static_cast<const u32*>(sc.cell_start.p);
-  const u32* cell_of = static_cast<const u32*>(sc.cell_of.p);
-  const u32* nbr = static_cast<const u32*>(sc.nbr.p);
-  unsigned char* state = static_cast<unsigned char*>(sc.state.p);
-  u32* cur_off = static_cast<u32*>(sc.cur_off.p);
-  unsigned char* cur_seg = static_cast<unsigned char*>(sc.cur_seg.p);
-  u32* wl0 = static_cast<u32*>(sc.wl0.p);
-  u32* wl1 = static_cast<u32*>(sc.wl1.p);
-  double thr = a.threshold;
-  void* args[] = { &count, &P, &cell_start, &cell_of, &nbr, &state, &cur_off, &cur_seg, &wl0, &wl1, &counters, &thr };
-  u64 want_blocks = (n + 255) / 256;
-  int blocks = (int)(want_blocks < (u64)coop_blocks ? want_blocks : (u64)coop_blocks);
-  if (blocks < 1)
-    blocks = 1;
-  MD_TRY(cudaLaunchCooperativeKernel((void*)md_rounds_kernel, dim3(blocks), dim3(256), args, 0, stream));
+  // group size by the average number of analysed points per cell: the time of one cell is on the
+  // critical path of the dependency graph, so dense levels get a whole CTA per cell
+  int mode = 0;
+  if (const char* env = getenv("SWGPU_MD_GROUP")) // tuning experiments: 32, 256 or 1024
+    mode = atoi(env);
+  if (mode != 32 && mode != 256 && mode != 1024)
+    mode = (u64)n_active >= 384ull * n_cells ? 1024 : ((u64)n_active >= 48ull * n_cells ? 256 : 32);
+  if (mode == 1024) {
+    const u32 blocks = n_cells < (u32)cta1024_blocks ? n_cells : (u32)cta1024_blocks;
+    md_wave_cta_kernel<1024><<<blocks, 1024, MDW_CTA_SMEM(1024), stream>>>(P, cell_start, nbr, state, desc, acc_xyz,
+                                                                          deps, queue, counters, a.threshold);
+  } else if (mode == 256) {
+    const u32 blocks = n_cells < (u32)cta256_blocks ? n_cells : (u32)cta256_blocks;
+    md_wave_cta_kernel<256><<<blocks, 256, MDW_CTA_SMEM(256), stream>>>(P, cell_start, nbr, state, desc, acc_xyz, deps,
+                                                                        queue, counters, a.threshold);
+  } else {
+    const u32 want = (n_cells + 7) / 8;
+    const u32 blocks = want < (u32)warp_blocks ? want : (u32)warp_blocks;
+    md_wave_warp_kernel<<<blocks, 256, 0, stream>>>(P, cell_start, nbr, state, desc, acc_xyz, deps, queue, counters,
+                                                    a.threshold);
+  }
   MD_TRY(cudaMemcpyAsync(sc.h_pinned, counters + 2, 4, cudaMemcpyDeviceToHost, stream));
   MD_TRY(cudaStreamSynchronize(stream));
-  *rounds = sc.h_pinned[0];
+  if (sc.h_pinned[0]) // a cell produced more accepted points than MD_OWN_CAP: reported, never silent
+    return cudaErrorAssert;
+  *rounds = 1; // swgpu_stats.min_distance_rounds now counts wavefront launches (one per sampled level)
   *launches = 5;
-  *bytes = n * (8 + 8 + 8 + (a.in_idx ? 52 : 0) + 24 + 10);
+  *bytes = n * (8 + 8 + 1 + (a.in_idx ? 52 : 0) + 24 + 2) + (u64)n_cells * (MD_NBR_SLOTS * 4 + 8 + 28);
   return cudaGetLastError();
 #undef MD_TRY
 }

@@ -11,7 +11,7 @@
 // K1: index_point<21> (clamp + Morton encode) fused with the 8 digit histograms of the sort.
 //   xyz        AoS n x 3 doubles (clamped in place when a point lies outside the bounds)
 //   keys       n x u64
-//   hist       8 x 256 u32, zeroed by the caller
+//   hist       sort_hist_words() u32 (one row of digit counts per radix pass), zeroed by the caller
 //   n_clamped  device counter of points that were clamped (zeroed by the caller)
 void launch_morton_encode(double* xyz, u64 n, const SwBounds& b, u64* keys, u32* hist, u32* n_clamped,
                           cudaStream_t stream);
@@ -19,11 +19,15 @@ void launch_morton_encode(double* xyz, u64 n, const SwBounds& b, u64* keys, u32*
 // histogram only (keys already exist: tests, multi-GPU path after the shuffle)
 void launch_key_histogram(const u64* keys, u64 n, u32* hist, cudaStream_t stream);
 
-// Stable LSD radix sort of (key, id) pairs, 8 passes of 8 bits (onesweep: one read + one write per
-// pass, decoupled look-back between tiles).  `hist` are the 8 x 256 digit counts of the keys.
-// Sorted result ends in keys[0] / vals[0] (8 passes = even number of ping-pongs).  vals[0] need
-// not be initialised: the first pass generates ids 0..n-1 on the fly.
+// Stable LSD radix sort of (key, id) pairs over the 63 bits of a MortonIndex64 (bit 63 must be clear):
+// 7 passes of 9 bits (onesweep: one read + one write per pass, decoupled look-back between tiles).
+// `hist` are the digit counts of the keys (sort_hist_words() u32, filled by K1 / launch_key_histogram).
+// The unsorted keys must be in keys<sort_input_buffer()>; the sorted result ends in keys0 / vals0.  The
+// vals buffers need not be initialised: the first pass generates ids 0..n-1 on the fly.
 // `status` must hold sort_status_words(n) u32; `ticket` 8 u32.
+size_t sort_hist_words();
+int sort_input_buffer();
+int sort_passes();
 size_t sort_status_words(u64 n);
 void launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hist, u32* status, u32* ticket,
                        cudaStream_t stream);
@@ -157,8 +161,7 @@ struct SwMinDistArgs
 
 struct SwMinDistScratch
 {
-  SwGrowBuf cell_start, cell_tile_rank0, cell_of, state, cur_off, cur_seg, lpos, wl0, wl1, hkeys, hvals, nbr,
-    counters;
+  SwGrowBuf cell_start, cell_tile_rank0, state, lpos, desc, acc_xyz, hkeys, hvals, nbr, deps, queue, cell_active, counters;
   u64* status; // look-back descriptors (>= sweep_tiles u64)
   u32* ticket;
   u32* h_pinned; // pinned host scratch, >= 8 u32

@@ -273,7 +273,7 @@ ensure_batch_buffers(swgpu_tiler* h, u64 n)
   }
   CK(h->wkey2.ensure(nn * 8));
   CK(h->widx2.ensure(nn * 4));
-  CK(h->hist.ensure(8 * 256 * 4));
+  CK(h->hist.ensure(sort_hist_words() * 4));
   CK(h->sort_status.ensure(sort_status_words(n) * 4));
   CK(h->node_start.ensure((nn + 1) * 4));
   CK(h->node_start_next.ensure((nn + 1) * 4));
@@ -614,14 +614,15 @@ run_batch(swgpu_tiler* h)
 
   record(h, 0);
   // K1 (every launcher is a no-op for an empty shard)
-  CK(cudaMemsetAsync(h->hist.p, 0, 8 * 256 * 4, s));
+  CK(cudaMemsetAsync(h->hist.p, 0, sort_hist_words() * 4, s));
   CK(cudaMemsetAsync(h->scalars.p, 0, 128, s));
+  u64* unsorted_keys = h->keys[sort_input_buffer()].as<u64>(); // the sort's last pass lands in keys[0]
   if (h->d_las) { // K1-LAS: 12 B record in, 24 B position + 8 B key out
-    launch_las_encode(h->d_las, n, h->las_t, h->bounds, h->d_xyz, h->keys[0].as<u64>(), h->hist.as<u32>(),
+    launch_las_encode(h->d_las, n, h->las_t, h->bounds, h->d_xyz, unsorted_keys, h->hist.as<u32>(),
                       h->d_n_clamped(), s);
     h->stats.bytes_index = 44 * n;
   } else {
-    launch_morton_encode(h->d_xyz, n, h->bounds, h->keys[0].as<u64>(), h->hist.as<u32>(), h->d_n_clamped(), s);
+    launch_morton_encode(h->d_xyz, n, h->bounds, unsorted_keys, h->hist.as<u32>(), h->d_n_clamped(), s);
     h->stats.bytes_index = 32 * n;
   }
   h->stats.kernel_launches += 1;
@@ -629,8 +630,8 @@ run_batch(swgpu_tiler* h)
   // K2
   launch_radix_sort(h->keys[0].as<u64>(), h->keys[1].as<u64>(), h->vals[0].as<u32>(), h->vals[1].as<u32>(), n,
                     h->hist.as<u32>(), h->sort_status.as<u32>(), h->d_tickets() + 8, s);
-  h->stats.kernel_launches += 9;
-  h->stats.bytes_sort = (8 * 24 - 4) * n;
+  h->stats.kernel_launches += 1 + sort_passes();
+  h->stats.bytes_sort = ((u64)sort_passes() * 24 - 4) * n;
   record(h, 2);
   // K4
   if (needs_positions(h->prm.sampling)) {
@@ -1233,8 +1234,8 @@ swgpu_morton_encode_device(swgpu_handle h, double* xyz_device, uint64_t n, uint6
   if (!h || (n && (!xyz_device || !keys_device)))
     return SW_ERR_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
-  CK(h->hist.ensure(8 * 256 * 4));
-  CK(cudaMemsetAsync(h->hist.p, 0, 8 * 256 * 4, h->stream));
+  CK(h->hist.ensure(sort_hist_words() * 4));
+  CK(cudaMemsetAsync(h->hist.p, 0, sort_hist_words() * 4, h->stream));
   CK(cudaMemsetAsync(h->scalars.p, 0, 128, h->stream));
   launch_morton_encode(xyz_device, n, h->bounds, reinterpret_cast<u64*>(keys_device), h->hist.as<u32>(), h->d_n_clamped(), h->stream);
   CK(cudaGetLastError());
@@ -1257,10 +1258,12 @@ swgpu_sort_keys_device(swgpu_handle h, uint64_t* keys_device, uint64_t n, uint32
   cudaSetDevice(h->device);
   CK(h->keys[1].ensure(n * 8));
   CK(h->vals[1].ensure(n * 4));
-  CK(h->hist.ensure(8 * 256 * 4));
+  CK(h->hist.ensure(sort_hist_words() * 4));
   CK(h->sort_status.ensure(sort_status_words(n) * 4));
-  CK(cudaMemsetAsync(h->hist.p, 0, 8 * 256 * 4, h->stream));
+  CK(cudaMemsetAsync(h->hist.p, 0, sort_hist_words() * 4, h->stream));
   launch_key_histogram(reinterpret_cast<const u64*>(keys_device), n, h->hist.as<u32>(), h->stream);
+  if (sort_input_buffer() == 1) // odd number of passes: start in the scratch buffer, finish in the caller's
+    CK(cudaMemcpyAsync(h->keys[1].p, keys_device, n * 8, cudaMemcpyDeviceToDevice, h->stream));
   launch_radix_sort(reinterpret_cast<u64*>(keys_device), h->keys[1].as<u64>(), order_device, h->vals[1].as<u32>(), n, h->hist.as<u32>(),
                     h->sort_status.as<u32>(), h->d_tickets() + 8, h->stream);
   CK(cudaGetLastError());
