@@ -38,11 +38,13 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace swo {
@@ -109,10 +111,65 @@ struct Orchestrator
   int32_t start_level = -1; /* FAST: level_of_start_nodes */
   std::map<std::pair<uint32_t, uint64_t>, size_t> node_lookup;
 
-  Orchestrator(Prims& p, const sw_params& prm)
+  /* The reference runs the per-node work as taskflow tasks on its worker threads (one task per start node
+   * in FAST, TilingAlgorithms.cpp:1314-1351; one subflow task per child node in ACCURATE, :499-561) and
+   * indexes in parallel chunks (parallel::transform, :588-598); its sort is a single std::sort.  With
+   * threads > 1 the same units of work run on std::threads here: every task writes into its own Collector,
+   * collectors are merged in task order, so the result does not depend on the thread count. */
+  unsigned threads = 1;
+
+  struct Collector
+  {
+    std::vector<sw_node> nodes;
+    std::vector<uint32_t> ids;
+  };
+
+  Orchestrator(Prims& p, const sw_params& prm, unsigned n_threads = 1)
     : prims(p)
     , params(prm)
+    , threads(n_threads ? n_threads : 1)
   {}
+
+  template<class Fn>
+  void parallel_for(size_t n_tasks, Fn fn)
+  {
+    if (threads <= 1 || n_tasks <= 1) {
+      for (size_t t = 0; t < n_tasks; ++t)
+        fn(t);
+      return;
+    }
+    std::atomic<size_t> next{ 0 };
+    std::vector<std::exception_ptr> errors(threads);
+    std::vector<std::thread> pool;
+    const unsigned n_workers = static_cast<unsigned>(std::min<size_t>(threads, n_tasks));
+    for (unsigned w = 0; w < n_workers; ++w)
+      pool.emplace_back([&, w]() {
+        try {
+          for (size_t t = next.fetch_add(1); t < n_tasks; t = next.fetch_add(1))
+            fn(t);
+        } catch (...) {
+          errors[w] = std::current_exception();
+          next.store(n_tasks);
+        }
+      });
+    for (auto& th : pool)
+      th.join();
+    for (auto& e : errors)
+      if (e)
+        std::rethrow_exception(e);
+  }
+
+  void merge(Collector& c)
+  {
+    const uint64_t base = ids.size();
+    ids.insert(ids.end(), c.ids.begin(), c.ids.end());
+    for (sw_node n : c.nodes) {
+      n.first += base;
+      node_lookup[{ n.levels, n.index }] = nodes.size();
+      nodes.push_back(n);
+    }
+    c = Collector{};
+  }
 
   Box root_bounds() const
   {
@@ -138,22 +195,30 @@ struct Orchestrator
     return r;
   }
 
-  void persist(const Item* begin, const Item* end, const NodeStructure& node, uint32_t flags)
+  void persist(const Item* begin, const Item* end, const NodeStructure& node, uint32_t flags, Collector& out)
   {
     sw_node n{};
     n.index = node.path_index;
     n.levels = node.path_levels;
     n.flags = flags;
-    n.first = ids.size();
+    n.first = out.ids.size();
     n.count = static_cast<uint64_t>(end - begin);
     for (const Item* it = begin; it != end; ++it)
-      ids.push_back(prims.id(*it));
-    node_lookup[{ n.levels, n.index }] = nodes.size();
-    nodes.push_back(n);
+      out.ids.push_back(prims.id(*it));
+    out.nodes.push_back(n);
   }
 
+  /* a subtree whose tiling was deferred to the worker threads (ACCURATE) */
+  struct Deferred
+  {
+    Item* begin;
+    Item* end;
+    NodeStructure node;
+  };
+
   /* tile_node + tile_internal_node + tile_terminal_node + recursion of do_tiling_for_node */
-  void do_tiling_for_node(Item* begin, Item* end, const NodeStructure& node, const NodeStructure& root)
+  void do_tiling_for_node(Item* begin, Item* end, const NodeStructure& node, const NodeStructure& root, Collector& out,
+                          std::vector<Deferred>* defer = nullptr, int defer_below_level = 0)
   {
     const int32_t sample_level = prims.required_depth(node.level, root);
     const bool requires_deeper = sample_level > node.level;
@@ -172,7 +237,7 @@ struct Orchestrator
     }
 
     if (terminal) {
-      persist(begin, end, node, SW_NODE_TERMINAL);
+      persist(begin, end, node, SW_NODE_TERMINAL, out);
       return;
     }
 
@@ -190,7 +255,7 @@ struct Orchestrator
                                       TakeAllWhenCountBelowMaxPoints);
     const bool took_all = (begin + taken == end);
     const bool by_count = static_cast<uint64_t>(end - begin) <= params.max_points_per_node;
-    persist(begin, begin + taken, node, (took_all && by_count) ? SW_NODE_TAKE_ALL : 0u);
+    persist(begin, begin + taken, node, (took_all && by_count) ? SW_NODE_TAKE_ALL : 0u, out);
 
     /* split_range_into_child_nodes, :116-162 */
     Item* rest = begin + taken;
@@ -211,7 +276,10 @@ struct Orchestrator
       child.max_spacing /= 2;
       child.path_index = (node.path_index << 3) | octant;
       child.path_levels = node.path_levels + 1;
-      do_tiling_for_node(rest + cuts[octant], rest + cuts[octant + 1], child, root);
+      if (defer && child.level >= defer_below_level)
+        defer->push_back({ rest + cuts[octant], rest + cuts[octant + 1], child });
+      else
+        do_tiling_for_node(rest + cuts[octant], rest + cuts[octant + 1], child, root, out, defer, defer_below_level);
     }
   }
 
@@ -260,21 +328,57 @@ struct Orchestrator
     return MAX_LEVEL;
   }
 
+  /* parallel::transform over chunks of the batch (TilingAlgorithms.cpp:588-598, :1262-1285) */
+  void index_items(std::vector<Item>& items)
+  {
+    if (threads <= 1) {
+      prims.index_all(items, root_bounds());
+      return;
+    }
+    const size_t n = prims.point_count();
+    const size_t n_chunks = std::min<size_t>(threads, std::max<size_t>(1, n / 65536));
+    std::vector<std::vector<Item>> parts(n_chunks);
+    const Box rb = root_bounds();
+    parallel_for(n_chunks, [&](size_t c) {
+      prims.index_range(n * c / n_chunks, n * (c + 1) / n_chunks, parts[c], rb);
+    });
+    items.clear();
+    items.reserve(n);
+    for (auto& part : parts)
+      items.insert(items.end(), part.begin(), part.end());
+  }
+
   void run_accurate()
   {
     std::vector<Item> items;
-    prims.index_all(items, root_bounds());
+    index_items(items);
     sort_items(items);
     if (items.empty()) /* the reference would throw in tile_internal_node */
       throw OracleError(SW_ERR_EMPTY_NODE, "tile_internal_node: Got zero points to tile");
     const NodeStructure root = make_root();
-    do_tiling_for_node(items.data(), items.data() + items.size(), root, root);
+    Collector top;
+    if (threads <= 1) {
+      do_tiling_for_node(items.data(), items.data() + items.size(), root, root, top);
+      merge(top);
+      return;
+    }
+    /* the root and its children are single tasks in the reference as well; their subtrees (nodes of
+     * level >= 1) become independent tasks */
+    std::vector<Deferred> tasks;
+    do_tiling_for_node(items.data(), items.data() + items.size(), root, root, top, &tasks, 1);
+    merge(top);
+    std::vector<Collector> outs(tasks.size());
+    parallel_for(tasks.size(), [&](size_t t) {
+      do_tiling_for_node(tasks[t].begin, tasks[t].end, tasks[t].node, root, outs[t]);
+    });
+    for (auto& c : outs)
+      merge(c);
   }
 
   void run_fast()
   {
     std::vector<Item> items;
-    prims.index_all(items, root_bounds());
+    index_items(items);
     /* parallel::scatter throws when there are fewer points than tasks (threading/Parallel.h:181-186) */
     if (items.size() < params.concurrency)
       throw OracleError(SW_ERR_TOO_FEW_POINTS, "fewer points than indexing threads");
@@ -287,6 +391,7 @@ struct Orchestrator
     const uint32_t shift = (MAX_OCTREE_LEVELS - S) * 3;
     size_t b = 0;
     std::vector<uint64_t> start_nodes;
+    std::vector<Deferred> tasks;
     while (b < items.size()) {
       const uint64_t prefix = prims.key(items[b]) >> shift;
       size_t e = b + 1;
@@ -303,9 +408,15 @@ struct Orchestrator
       n.path_index = prefix;
       n.path_levels = S;
       start_nodes.push_back(prefix);
-      do_tiling_for_node(items.data() + b, items.data() + e, n, root);
+      tasks.push_back({ items.data() + b, items.data() + e, n });
       b = e;
     }
+    std::vector<Collector> outs(tasks.size());
+    parallel_for(tasks.size(), [&](size_t t) {
+      do_tiling_for_node(tasks[t].begin, tasks[t].end, tasks[t].node, root, outs[t]);
+    });
+    for (auto& c : outs)
+      merge(c);
     reconstruct(S, start_nodes);
   }
 
@@ -322,7 +433,9 @@ struct Orchestrator
         parents.push_back(p >> (3 * (S - lv)));
       std::sort(parents.begin(), parents.end());
       parents.erase(std::unique(parents.begin(), parents.end()), parents.end());
-      for (uint64_t parent : parents) {
+      std::vector<Collector> outs(parents.size());
+      parallel_for(parents.size(), [&](size_t pi) {
+        const uint64_t parent = parents[pi];
         std::vector<uint32_t> child_ids;
         for (uint8_t octant = 0; octant < 8; ++octant) {
           auto it = node_lookup.find({ static_cast<uint32_t>(lv + 1), (parent << 3) | octant });
@@ -346,8 +459,10 @@ struct Orchestrator
         NodeStructure n{};
         n.path_index = parent;
         n.path_levels = static_cast<uint32_t>(lv);
-        persist(items.data(), items.data() + taken, n, SW_NODE_RECONSTRUCTED);
-      }
+        persist(items.data(), items.data() + taken, n, SW_NODE_RECONSTRUCTED, outs[pi]);
+      });
+      for (auto& c : outs)
+        merge(c);
     }
   }
 

@@ -129,6 +129,17 @@ struct RefPrims
       out.push_back(index_point<21>(r, b, OutlierPointsBehaviour::ClampToBounds));
   }
 
+  uint64_t point_count() const { return refs.size(); }
+
+  void index_range(uint64_t b, uint64_t e, std::vector<Item>& out, const swo::Box& bounds)
+  {
+    const AABB bb = to_aabb(bounds);
+    out.clear();
+    out.reserve(e - b);
+    for (uint64_t i = b; i < e; ++i)
+      out.push_back(index_point<21>(refs[i], bb, OutlierPointsBehaviour::ClampToBounds));
+  }
+
   void index_ids(const std::vector<uint32_t>& ids, std::vector<Item>& out, const swo::Box& bounds)
   {
     const AABB b = to_aabb(bounds);
@@ -337,6 +348,16 @@ swr_sample_points(int32_t sampling,
   }
 }
 
+/* worker threads of the following swr_tile calls: the reference's taskflow workers (one task per start
+ * node / child subtree) become std::threads over the same units of work, see orchestrator.h */
+static unsigned g_threads = 1;
+
+void
+swr_set_threads(uint32_t n)
+{
+  g_threads = n ? n : 1;
+}
+
 int
 swr_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
 {
@@ -344,7 +365,7 @@ swr_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
   *out_handle = h;
   try {
     RefPrims prims(xyz, n, params->sampling, params->max_points_per_node);
-    swo::Orchestrator<RefPrims> o(prims, *params);
+    swo::Orchestrator<RefPrims> o(prims, *params, g_threads);
     o.run();
     h->nodes = std::move(o.nodes);
     h->ids = std::move(o.ids);

@@ -161,6 +161,7 @@ class Oracle:
           [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32,
            C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p])
         f("tile", C.c_int, [C.POINTER(SwParams), C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)])
+        f("set_threads", None, [C.c_uint32])
         f("node_count", C.c_uint64, [C.c_void_p])
         f("point_id_count", C.c_uint64, [C.c_void_p])
         f("start_level", C.c_int32, [C.c_void_p])
@@ -269,6 +270,11 @@ class Oracle:
         self._payload_las(xyz.ctypes.data, ids.ctypes.data, nodes.ctypes.data, len(nodes), bmin.ctypes.data,
                           bmax.ctypes.data, out.ctypes.data, headers.ctypes.data)
         return out, headers
+
+    def set_threads(self, n):
+        """Worker threads for tile(): the reference's taskflow tasks (per start node / child subtree, chunked
+        indexing) on std::threads; the sort stays one std::sort as in the reference.  Default 1."""
+        self._set_threads(int(n))
 
     # --- whole batch --------------------------------------------------------------------------
     def tile(self, params: SwParams, xyz, return_clamped=False):

@@ -246,6 +246,17 @@ struct RestatedPrims
     }
   }
 
+  uint64_t point_count() const { return n; }
+
+  void index_range(uint64_t b, uint64_t e, std::vector<IP>& out, const Box& bounds)
+  {
+    out.resize(e - b);
+    for (uint64_t i = b; i < e; ++i) {
+      out[i - b].key = index_point(xyz + 3 * i, bounds);
+      out[i - b].id = static_cast<uint32_t>(i);
+    }
+  }
+
   void index_ids(const std::vector<uint32_t>& ids, std::vector<IP>& out, const Box& bounds)
   {
     out.resize(ids.size());
@@ -657,6 +668,15 @@ swo_sample_points(int32_t sampling,
 }
 
 /* whole-batch tiling: ACCURATE (V1) or FAST (V3 first iteration + finalize) */
+/* worker threads of the following swo_tile calls (1 = the plain sequential restatement) */
+static unsigned g_threads = 1;
+
+void
+swo_set_threads(uint32_t n)
+{
+  g_threads = n ? n : 1;
+}
+
 int
 swo_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
 {
@@ -665,7 +685,7 @@ swo_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
   *out_handle = h;
   try {
     RestatedPrims prims{ xyz, n, params->sampling, params->max_points_per_node };
-    Orchestrator<RestatedPrims> o(prims, *params);
+    Orchestrator<RestatedPrims> o(prims, *params, g_threads);
     o.run();
     h->nodes = std::move(o.nodes);
     h->ids = std::move(o.ids);

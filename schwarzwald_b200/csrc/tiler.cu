@@ -1073,6 +1073,21 @@ las_scale_from_bounds(const double mn[3], const double mx[3])
   return 0.0001;
 }
 
+// The output holds sorted positions.  Strategies that read positions have them gathered into Morton
+// order already (K4): node contents are then nearly sequential in that copy.  RANDOM_GRID never gathers, so
+// its payload goes through the sort permutation into the caller's array.
+static void
+payload_source(const swgpu_tiler* h, const double** xyz, const u32** perm)
+{
+  if (needs_positions(h->prm.sampling) && h->pos_sorted.p) {
+    *xyz = h->pos_sorted.as<double>();
+    *perm = nullptr;
+  } else {
+    *xyz = h->d_xyz;
+    *perm = h->vals[0].as<u32>();
+  }
+}
+
 static int
 payload_checks(swgpu_tiler* h)
 {
@@ -1092,7 +1107,10 @@ swgpu_get_payload_pnts_device(swgpu_handle h, float* xyz_f32_device)
   if (rc)
     return rc;
   cudaSetDevice(h->device);
-  launch_payload_pnts(h->d_xyz, h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, xyz_f32_device, h->stream);
+  const double* src = nullptr;
+  const u32* perm = nullptr;
+  payload_source(h, &src, &perm);
+  launch_payload_pnts(src, perm, h->out_idx.as<u32>(), h->out_count, xyz_f32_device, h->stream);
   CK(cudaGetLastError());
   return SW_OK;
 }
@@ -1151,7 +1169,10 @@ swgpu_get_payload_las_device(swgpu_handle h, int32_t* xyz_i32_device, sw_las_nod
   }
   CK(h->node_hdr.ensure(h->node_count * 32));
   CK(cudaMemcpyAsync(h->node_hdr.p, hdr.data(), h->node_count * 32, cudaMemcpyHostToDevice, h->stream));
-  launch_payload_las(h->d_xyz, h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, h->node_first.as<u64>(),
+  const double* src = nullptr;
+  const u32* perm = nullptr;
+  payload_source(h, &src, &perm);
+  launch_payload_las(src, perm, h->out_idx.as<u32>(), h->out_count, h->node_first.as<u64>(),
                      (u32)h->node_count, h->node_hdr.as<double>(), xyz_i32_device, h->stream);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream)); // hdr is a stack-owned staging vector

@@ -265,6 +265,18 @@ class GpuTiler:
                                                     C.c_void_p(headers.ctypes.data)))
         return out[:ni], headers
 
+    def payload_pnts_device(self, out_device_ptr):
+        """payload_pnts() into a caller-owned device buffer of n_point_ids x 3 float32."""
+        self._check(self._lib.swgpu_get_payload_pnts_device(self._h, C.c_void_p(int(out_device_ptr))))
+
+    def payload_las_device(self, out_device_ptr):
+        """payload_las() into a caller-owned device buffer of n_point_ids x 3 int32; returns the node headers."""
+        nn, _ = self.result_size()
+        headers = np.zeros(nn, LAS_HEADER_DTYPE)
+        self._check(self._lib.swgpu_get_payload_las_device(self._h, C.c_void_p(int(out_device_ptr)),
+                                                           C.c_void_p(headers.ctypes.data)))
+        return headers
+
     def result_device_ids(self, ids_device_ptr):
         nn, _ = self.result_size()
         nodes = np.empty(nn, NODE_DTYPE)
