@@ -307,6 +307,7 @@ def main():
         step()
         phase_ms = {k: round(v, 3) for k, v in tiler.last["phase_ms"].items()}
         phase_ms["bytes_sent_off_gpu"] = tiler.last["bytes_sent_off_gpu"]
+        phase_ms["exchange"] = tiler.last.get("exchange")
         tiler.profile = False
     if world > 1:
         t = torch.tensor([ms], device=dev)

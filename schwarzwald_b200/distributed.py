@@ -61,6 +61,18 @@ class TorchDistComm:
         self._dist.all_gather_into_tensor(out, t, group=self.group)
         return out
 
+    def peer_buffers(self, n_bytes, device):
+        """Symmetric receive buffer of n_bytes on every rank, mapped into every process of the group
+        (torch symmetric memory: CUDA VMM allocations exchanged once, peer access over NVLink).  Returns
+        (own tensor of uint8, [device pointer of rank r's buffer as seen from THIS process]).  Collective."""
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty((int(n_bytes),), dtype=torch.uint8, device=device)
+        hdl = symm_mem.rendezvous(t, self.group if self.group is not None else self._dist.group.WORLD)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        assert len(ptrs) == self.world and ptrs[self.rank] == t.data_ptr()
+        return t, ptrs, hdl
+
     def all_to_all_rows(self, send, send_counts, recv_counts=None):
         """send: tensor whose rows are ordered by destination; returns (recv, recv_counts).
         recv_counts, when the caller already knows them, saves the count exchange and its sync."""
@@ -204,7 +216,7 @@ class ShardedTiler:
     of the per-rank point counts)."""
 
     def __init__(self, sampling, tiling, bounds_min, bounds_max, spacing_at_root, max_points_per_node=20000,
-                 max_depth=100, concurrency=8, device=0, comm=None, shard_levels=None):
+                 max_depth=100, concurrency=8, device=0, comm=None, shard_levels=None, exchange="auto"):
         import torch
         self._torch = torch
         self.comm = comm if comm is not None else TorchDistComm()
@@ -227,6 +239,14 @@ class ShardedTiler:
         self._views = {}
         self.last = {}
         self.profile = False  # True: per-phase CUDA-event times in self.last["phase_ms"] (adds a sync)
+        # The exchange step.  "peer": ONE kernel partitions the local points and writes them straight into the
+        # destinations' receive buffers over NVLink (swgpu_partition_to_peers_device on symmetric memory);
+        # "nccl": partition into a send buffer, then all_to_all_single.  "auto" = peer where the communicator
+        # can map peer memory (a real multi-process NCCL group), else nccl.
+        self.exchange = exchange
+        self._peer = None  # dict(cap, xyz, ids, xyz_ptrs, ids_ptrs, handles)
+        self._peer_failed = None
+        self._tiny = None
 
     # -- plumbing -----------------------------------------------------------------------------------
     def set_stream(self, cuda_stream_handle):
@@ -258,6 +278,31 @@ class ShardedTiler:
             import traceback
             traceback.print_exc()
             return 1
+
+    def _peer_wanted(self):
+        if self.exchange == "nccl" or self.comm.world < 2 or not hasattr(self.comm, "peer_buffers"):
+            return False
+        return self._peer_failed is None
+
+    def _ensure_peer_buffers(self, need_points):
+        """(Re)allocates the symmetric receive buffers for at least need_points points per rank.  Every rank
+        calls this with the same value (it comes from the all-gathered count matrix)."""
+        if self._peer is not None and self._peer["cap"] >= need_points:
+            return True
+        try:
+            cap = int(need_points * 1.1) + (1 << 16)
+            self._peer = None  # release the old mapping first
+            xyz, xyz_ptrs, hx = self.comm.peer_buffers(cap * 24, self.device)
+            ids, ids_ptrs, hi = self.comm.peer_buffers(cap * 4, self.device)
+            self._peer = {"cap": cap, "xyz": xyz, "ids": ids, "xyz_ptrs": xyz_ptrs, "ids_ptrs": ids_ptrs,
+                          "handles": (hx, hi)}
+            return True
+        except Exception as e:  # no peer mapping on this system: the NCCL exchange does the same job
+            if self.exchange == "peer":
+                raise
+            self._peer_failed = repr(e)
+            self._peer = None
+            return False
 
     # -- the two calls of TilingAlgorithmBase --------------------------------------------------------
     def build_execution_graph(self, xyz, id_base=None):
@@ -307,6 +352,44 @@ class ShardedTiler:
         assert int(counts[comm.rank]) == n
         if id_base is None:
             id_base = int(counts[:comm.rank].sum())
+        sc = [int(x) for x in count_matrix[comm.rank]]
+        rc = [int(x) for x in count_matrix[:, comm.rank]]
+        recv_totals = count_matrix.sum(axis=0)
+        if self._peer_wanted() and self._ensure_peer_buffers(int(recv_totals.max())):
+            # 4+5 in ONE kernel: stable partition written straight into the destinations' receive buffers
+            # (peer memory over NVLink).  The all-gather above ordered this step after every rank's previous
+            # use of its receive buffer; the tiny all-reduce below orders every rank's tiling after all writes.
+            world = comm.world
+            pk = self._peer
+            dst_offsets = np.array([int(count_matrix[:comm.rank, r].sum()) for r in range(world)], np.uint64)
+            px = (C.c_void_p * world)(*pk["xyz_ptrs"])
+            pi = (C.c_void_p * world)(*pk["ids_ptrs"])
+            t._check(lib.swgpu_partition_to_peers_device(
+                t._h, C.c_void_p(keys.data_ptr()), C.c_void_p(xyz.data_ptr()), n, C.c_void_p(first_prefix.ctypes.data),
+                world, int(id_base), px, pi, C.c_void_p(dst_offsets.ctypes.data), None))
+            del keys
+            mark("partition+exchange (peer kernel)")
+            if self._tiny is None:
+                self._tiny = torch.zeros(1, dtype=torch.int32, device=self.device)
+            comm.all_reduce_sum(self._tiny)
+            m = int(recv_totals[comm.rank])
+            mark("barrier")
+            t._check(lib.swgpu_set_shard(t._h, self.shard_levels, int(start_level), self._hook, None,
+                                         C.c_void_p(pk["ids_ptrs"][comm.rank] if m else 0)))
+            self._keep = {"xyz": pk["xyz"][:m * 24].view(torch.float64).view(m, 3),
+                          "ids": pk["ids"][:m * 4].view(torch.int32)}
+            t._check(lib.swgpu_index_batch_device(t._h, C.c_void_p(pk["xyz_ptrs"][comm.rank] if m else 0), m))
+            mark("tile")
+            phases = {}
+            if self.profile:
+                torch.cuda.synchronize(self.device)
+                for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+                    phases[name] = e0.elapsed_time(e1)
+            self.last = {"phase_ms": phases, "n_local": n, "n_shard": m, "n_global": n_global,
+                         "start_level": start_level, "first_prefix": first_prefix, "send_counts": sc, "recv_counts": rc,
+                         "exchange": "peer kernel (swgpu_partition_to_peers_device over symmetric memory)",
+                         "bytes_sent_off_gpu": int(sum(c for r, c in enumerate(sc) if r != comm.rank)) * 28}
+            return n
         # 4. stable partition into the send buffer
         send_xyz = torch.empty((max(n, 1), 3), dtype=torch.float64, device=self.device)
         send_ids = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
@@ -318,9 +401,7 @@ class ShardedTiler:
         del keys
         mark("partition")
         # 5. the exchange: every GPU receives whole subtrees, sources in rank order
-        sc = [int(x) for x in count_matrix[comm.rank]]
         assert sc == [int(x) for x in send_counts], "partition and histogram disagree"
-        rc = [int(x) for x in count_matrix[:, comm.rank]]
         recv_xyz, recv_counts = comm.all_to_all_rows(send_xyz[:n], sc, rc)
         recv_ids, _ = comm.all_to_all_rows(send_ids[:n], sc, rc)
         del send_xyz, send_ids
@@ -339,6 +420,8 @@ class ShardedTiler:
                 phases[name] = e0.elapsed_time(e1)
         self.last = {"phase_ms": phases, "n_local": n, "n_shard": m, "n_global": n_global, "start_level": start_level,
                      "first_prefix": first_prefix, "send_counts": sc, "recv_counts": recv_counts,
+                     "exchange": "nccl all_to_all" + (" (peer mapping unavailable: %s)" % self._peer_failed
+                                                      if self._peer_failed else ""),
                      "bytes_sent_off_gpu": int(sum(c for r, c in enumerate(sc) if r != comm.rank)) * 28}
         return n
 
