@@ -118,6 +118,15 @@ public:
   // build_execution_graph for one batch: xyz = PointBuffer::positions() (AoS doubles); outliers are
   // clamped in place exactly as index_point does (OctreeAlgorithms.h:156-170)
   void index_batch(double* xyz_host, uint64_t n) { check(swgpu_index_batch(_handle, xyz_host, n)); }
+  // The same batch while it is still in LAS record form (laszip_point::X/Y/Z): the device computes what
+  // position_from_las_point (core/io/LASFile.cpp:79-94) and the tiler's shift-to-centre transformation
+  // (core/process/TilerProcess.cpp:552-559) compute on the host, fused with the indexing kernel.
+  void index_batch_las(const int32_t* las_xyz_host, uint64_t n, const sw_las_transform& transform)
+  {
+    check(swgpu_index_batch_las(_handle, las_xyz_host, n, &transform));
+  }
+  // PointBuffer positions of the last batch (n x 3 doubles, original order, after index_point's clamping)
+  void positions(double* xyz_host) { check(swgpu_get_positions(_handle, xyz_host)); }
   void finalize() { check(swgpu_finalize(_handle)); }
 
   struct Result
@@ -135,6 +144,35 @@ public:
     r.point_ids.resize(n_ids);
     check(swgpu_get_nodes(_handle, r.nodes.data(), r.point_ids.data()));
     return r;
+  }
+
+  // Position payloads of ALL nodes in the node-major order of result(): what PNTSWriter's PositionAttribute
+  // (core/io/PNTSWriter.cpp:326-342) and LASPersistence::persist_points (core/io/LASPersistence.h:119-131,
+  // 160-163) store.  Row i of the node table owns records [first, first + count).
+  std::vector<float> payload_pnts()
+  {
+    uint64_t n_nodes = 0, n_ids = 0;
+    check(swgpu_result_size(_handle, &n_nodes, &n_ids));
+    std::vector<float> out(3 * n_ids);
+    if (n_ids)
+      check(swgpu_get_payload_pnts(_handle, out.data()));
+    return out;
+  }
+  struct LasPayload
+  {
+    std::vector<int32_t> records;            // n_point_ids x 3
+    std::vector<sw_las_node_header> headers; // one per node table row
+  };
+  LasPayload payload_las()
+  {
+    uint64_t n_nodes = 0, n_ids = 0;
+    check(swgpu_result_size(_handle, &n_nodes, &n_ids));
+    LasPayload p;
+    p.records.resize(3 * n_ids);
+    p.headers.resize(n_nodes);
+    if (n_ids)
+      check(swgpu_get_payload_las(_handle, p.records.data(), p.headers.data()));
+    return p;
   }
 
   int32_t start_level()
