@@ -136,6 +136,19 @@ class ThreadComm:
         sh.barrier.wait()
         return out
 
+    def peer_buffers(self, n_bytes, device):
+        """Virtual ranks share one device: every rank's receive buffer is an ordinary tensor whose pointer is
+        valid for all of them, which drives swgpu_partition_to_peers_device exactly as real peer mappings do."""
+        import torch
+        sh = self.shared
+        t = torch.empty(int(n_bytes), dtype=torch.uint8, device=device)
+        sh.barrier.wait()  # the previous round of slot users is done
+        sh.slots[self.rank] = t
+        sh.barrier.wait()
+        ptrs = [int(sh.slots[r].data_ptr()) for r in range(self.world)]
+        sh.barrier.wait()
+        return t, ptrs, None
+
     def all_to_all_rows(self, send, send_counts, recv_counts=None):
         import torch
         sh = self.shared

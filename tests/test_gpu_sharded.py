@@ -97,3 +97,20 @@ def test_sharded_min_distance_invariants():
             s = np.float32(spacing) / np.float32(2.0 ** int(node["levels"]))
             pairs = cKDTree(xyz[ids]).query_pairs(float(s) * (1 - 1e-6))
             assert not pairs, "min spacing violated inside a shard part"
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_exchange_paths_agree(port_oracle, exchange, world):
+    """The exchange step both ways: ONE kernel that partitions straight into the destinations' receive buffers
+    (swgpu_partition_to_peers_device; the virtual ranks' buffers live on the same device, real ranks map them
+    over NVLink) and partition + all-to-all.  Both must reproduce the oracle bit for bit."""
+    from oracle import sworacle
+    xyz, bmin, bmax, spacing = _setup("urban", 500_000, 3, side_m=800.0)
+    params = sworacle.make_params("GRID_CENTER", "FAST", spacing, bmin, bmax, max_points_per_node=2500, concurrency=4)
+    want = port_oracle.tile(params, xyz)
+    got, parts, infos = _run_sharded(xyz, world, "GRID_CENTER", "FAST", bmin, bmax, spacing, max_points_per_node=2500,
+                                     concurrency=4, exchange=exchange)
+    assert all(i["exchange"].startswith("peer kernel" if exchange == "peer" else "nccl") for i in infos)
+    assert sum(i["n_shard"] for i in infos) == len(xyz)
+    _assert_equal(want, got)
