@@ -754,6 +754,27 @@ bounds_from_key(u64 key, int depth, const SwBounds& b, double mn[3], double mx[3
   }
 }
 
+// the same recurrence continued from bounds that already hold `from_depth` levels
+__device__ __forceinline__ void
+bounds_continue(u64 key, int from_depth, int depth, double mn[3], double mx[3])
+{
+  for (int level = from_depth; level < depth; ++level) {
+    const u32 oct = (u32)(key >> (3 * (20 - level))) & 7u;
+    const double hx = (mx[0] - mn[0]) * 0.5;
+    const double hy = (mx[1] - mn[1]) * 0.5;
+    const double hz = (mx[2] - mn[2]) * 0.5;
+    if (oct & 4u)
+      mn[0] = mn[0] + hx;
+    if (oct & 2u)
+      mn[1] = mn[1] + hy;
+    if (oct & 1u)
+      mn[2] = mn[2] + hz;
+    mx[0] = mn[0] + hx;
+    mx[1] = mn[1] + hy;
+    mx[2] = mn[2] + hz;
+  }
+}
+
 __device__ __forceinline__ double
 squared_distance(const double p[3], const double t[3])
 {
@@ -775,12 +796,10 @@ struct JitterNode
   double permutation_cell_size;
 };
 
-// per-node quantities of JitteredSampling::sample_points, Sampling.h:621-660
+// per-node quantities of JitteredSampling::sample_points, Sampling.h:621-660, from the node's bounds
 __device__ __forceinline__ u32
-jitter_node_setup(u64 key, const SwArgminArgs& a, JitterNode& jn)
+jitter_node_setup(const double mn[3], const double mx[3], const SwArgminArgs& a, JitterNode& jn)
 {
-  double mn[3], mx[3];
-  bounds_from_key(key, a.node_level + 1, a.bounds, mn, mx);
   const double ext_x = mx[0] - mn[0];
   const double perfect = ext_x / a.spacing_at_node;
   u32 x = __double2uint_rz(perfect);
@@ -845,6 +864,42 @@ jitter_target(u64 key, const SwArgminArgs& a, const JitterNode& jn, double t[3])
   t[2] = jn.node_min[2] + ((double)gz * jn.grid_cell_size + (double)pz * jn.permutation_cell_size);
 }
 
+// Everything select_argmin_kernel needs per NODE, computed once per node instead of once per point: the
+// node's bounds (the halving recurrence down to the node) and, for JITTERED, the grid quantities of
+// Sampling.h:621-660 including the two exceptions it can throw (only for nodes that are really sampled).
+__global__ void __launch_bounds__(256)
+argmin_nodes_kernel(SwArgminArgs a)
+{
+  const u32 r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= a.n_nodes)
+    return;
+  const u64 key = a.in_key[a.node_start[r]] & SW_KEY_MASK;
+  SwArgminNode nd;
+  bounds_from_key(key, a.node_level + 1, a.bounds, nd.mn, nd.mx);
+  nd.shift = a.cell_shift;
+  nd.levels = 0;
+  nd.cells = 1;
+  nd.grid_cell_size = 0.0;
+  nd.permutation_cell_size = 0.0;
+  if (a.sampling == SW_JITTERED) {
+    JitterNode jn;
+    const u32 e = jitter_node_setup(nd.mn, nd.mx, a, jn);
+    nd.shift = jn.shift;
+    nd.levels = jn.levels;
+    nd.cells = jn.cells;
+    nd.grid_cell_size = jn.grid_cell_size;
+    nd.permutation_cell_size = jn.permutation_cell_size;
+    if (e) {
+      bool active = true;
+      if (a.allow_take_all)
+        active = (u64)node_point_count(a.node_start, a.node_gcount, r) > a.max_points_per_node;
+      if (active)
+        atomicMax(a.error_flag, e);
+    }
+  }
+  a.nodes[r] = nd;
+}
+
 // tile descriptors of the segmented scan: flag word + two 16-byte payload slots per tile
 struct ArgminDesc
 {
@@ -853,7 +908,7 @@ struct ArgminDesc
   u32 has_head;
 };
 
-__global__ void __launch_bounds__(SWP_THREADS)
+__global__ void __launch_bounds__(SWP_THREADS, 4)
 select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__ ticket)
 {
   __shared__ u32 s_slot;
@@ -891,7 +946,6 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
   // ---- phase 2: per point head / tail flags and distance ------------------------------------------
   ArgminVal val[SWP_ITEMS];
   u32 hbits = 0, tbits = 0; // per item: this lane's element is a segment head / tail
-  u32 local_err = 0;
   {
     u32 run = a.tile_rank0[tile] + hexcl;
 #pragma unroll
@@ -915,17 +969,33 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
                                 a.pos_sorted[3 * (u64)idx + 2] };
           double t[3];
           int cshift;
+          const SwArgminNode* nd = a.nodes + node_rank;
           if (a.sampling == SW_JITTERED) {
             JitterNode jn;
-            const u32 e = jitter_node_setup(k, a, jn);
-            if (e)
-              local_err = local_err ? local_err : e;
+            jn.shift = nd->shift;
+            jn.levels = nd->levels;
+            jn.cells = nd->cells;
+            jn.node_min[0] = nd->mn[0];
+            jn.node_min[1] = nd->mn[1];
+            jn.node_min[2] = nd->mn[2];
+            jn.grid_cell_size = nd->grid_cell_size;
+            jn.permutation_cell_size = nd->permutation_cell_size;
             cshift = jn.shift;
             jitter_target(k, a, jn, t);
           } else {
             cshift = a.cell_shift;
             double mn[3], mx[3];
-            bounds_from_key(k, a.cand_level + 1, a.bounds, mn, mx);
+            if (a.cand_level >= a.node_level) { // the usual case: continue from the node's bounds
+              mn[0] = nd->mn[0];
+              mn[1] = nd->mn[1];
+              mn[2] = nd->mn[2];
+              mx[0] = nd->mx[0];
+              mx[1] = nd->mx[1];
+              mx[2] = nd->mx[2];
+              bounds_continue(k, a.node_level + 1, a.cand_level + 1, mn, mx);
+            } else { // spacing coarser than the node: the candidate cell is an ancestor of the node
+              bounds_from_key(k, a.cand_level + 1, a.bounds, mn, mx);
+            }
             // AABB::getCenter = min + extent()/2 (math/AABB.h:70)
             t[0] = mn[0] + (mx[0] - mn[0]) * 0.5;
             t[1] = mn[1] + (mx[1] - mn[1]) * 0.5;
@@ -947,9 +1017,6 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
       tbits |= (tail ? 1u : 0u) << j;
     }
   }
-  if (local_err)
-    atomicMax(a.error_flag, local_err);
-
   // ---- phase 3: segmented inclusive min-scan inside the warp (items in order, lanes in order) -----
   // seen[j]: a head exists between the start of the warp's range and this element (inclusive)
   u32 seen_bits = 0;
@@ -1104,6 +1171,7 @@ launch_select_argmin(const SwArgminArgs& a, u64* status, u32* ticket, cudaStream
   const size_t tiles = sweep_tiles(a.count);
   cudaMemsetAsync(status, 0, tiles * sizeof(u64), stream); // flag words
   cudaMemsetAsync(ticket, 0, sizeof(u32), stream);
+  argmin_nodes_kernel<<<(a.n_nodes + 255) / 256, 256, 0, stream>>>(a);
   select_argmin_kernel<<<(u32)tiles, SWP_THREADS, 0, stream>>>(a, status, ticket);
 }
 

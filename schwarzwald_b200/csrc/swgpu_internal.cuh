@@ -109,6 +109,17 @@ void launch_tile_rank0(const u32* node_start, u32 n_nodes, u64 count, u32* tile_
 void launch_level_compact(const SwLevelArgs& a, u64* n_selected, u32 n_child_slots, u32* next_node_start,
                           u32* n_nodes_next, cudaStream_t stream);
 
+// per-node quantities of the GRID_CENTER / JITTERED selection (argmin_nodes_kernel)
+struct SwArgminNode
+{
+  double mn[3], mx[3]; // node bounds by the get_octant_bounds recurrence
+  double grid_cell_size, permutation_cell_size; // JITTERED, Sampling.h:655-660
+  int shift;  // key shift of the selection cells
+  int levels; // JITTERED: log2(cells per axis)
+  u32 cells;
+  u32 pad;
+};
+
 struct SwArgminArgs
 {
   const u64* in_key;
@@ -130,6 +141,8 @@ struct SwArgminArgs
   const u32* node_gcount; // see SwLevelArgs
   int allow_take_all;
   u64 max_points_per_node;
+  u32 n_nodes;
+  SwArgminNode* nodes; // n_nodes entries, filled by launch_select_argmin
 };
 // status >= 5 * sweep_tiles(count) u64
 void launch_select_argmin(const SwArgminArgs& a, u64* status, u32* ticket, cudaStream_t stream);

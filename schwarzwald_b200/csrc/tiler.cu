@@ -115,7 +115,7 @@ struct swgpu_tiler
   DevBuf xyz_own;
   const int* d_las = nullptr; // current batch arrives as LAS record coordinates (swgpu_index_batch_las*)
   SwLasTransform las_t{};
-  DevBuf las_own, payload_tmp, node_hdr;
+  DevBuf las_own, payload_tmp, node_hdr, argmin_nodes;
   DevBuf keys[2], vals[2];
   DevBuf wkey2, widx2;
   DevBuf hist, sort_status, scalars;
@@ -431,8 +431,11 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
         g.node_gcount = node_gcount;
         g.allow_take_all = allow_take_all ? 1 : 0;
         g.max_points_per_node = h->prm.max_points_per_node;
+        CK(h->argmin_nodes.ensure(std::max<size_t>(n_nodes, 1) * sizeof(SwArgminNode)));
+        g.n_nodes = n_nodes;
+        g.nodes = h->argmin_nodes.as<SwArgminNode>();
         launch_select_argmin(g, h->scan_status.as<u64>(), h->d_tickets(), s);
-        h->stats.kernel_launches += 1;
+        h->stats.kernel_launches += 2;
         h->stats.bytes_sample += (8 + 4 + 24 + 1 + 1) * count;
         a.sel = h->sel.as<unsigned char>();
         break;
@@ -818,7 +821,7 @@ swgpu_destroy(swgpu_handle h)
     return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  DevBuf* bufs[] = { &h->las_own, &h->payload_tmp, &h->node_hdr, &h->xyz_own,    &h->keys[0],   &h->keys[1],       &h->vals[0],     &h->vals[1],  &h->wkey2,
+  DevBuf* bufs[] = { &h->las_own, &h->payload_tmp, &h->node_hdr, &h->argmin_nodes, &h->xyz_own,    &h->keys[0],   &h->keys[1],       &h->vals[0],     &h->vals[1],  &h->wkey2,
                      &h->widx2,      &h->hist,      &h->sort_status,   &h->scalars,     &h->pos_sorted, &h->out_key,
                      &h->out_idx,    &h->node_start, &h->node_start_next, &h->selbits, &h->tile_sel, &h->child_count, &h->tile_rank0,   &h->sel,         &h->scan_status, &h->node_index,
                      &h->node_first, &h->bins,      &h->ids_tmp,     &h->dense_counts, &h->node_gcount,
