@@ -143,6 +143,12 @@ int swgpu_sort_keys_device(swgpu_handle h, uint64_t* keys_device, uint64_t n, ui
 typedef int (*swgpu_allreduce_u32_fn)(void* ctx, uint32_t* device_counters, uint64_t count, void* cuda_stream);
 
 int swgpu_prefix_histogram_device(swgpu_handle h, const uint64_t* keys_device, uint64_t n, uint32_t* bins_device);
+/* The same for the leading `levels` (1..4) octree levels: 8^levels bins, accumulated in shared memory (one read
+ * of the keys, no L2 atomic per key).  Enough for balanced splitters; with start_level = -1 in swgpu_set_shard
+ * the exact level-5 counts FAST's start level needs are taken from the sorted keys after the exchange and
+ * summed through the all-reduce hook. */
+int swgpu_prefix_histogram_coarse_device(swgpu_handle h, const uint64_t* keys_device, uint64_t n, uint32_t levels,
+                                         uint32_t* bins_device);
 /* estimate_start_node_level_in_octree (TilingAlgorithms.cpp:1473-1535) on GLOBAL level-5 prefix
  * counts (host array of SWGPU_PREFIX_BINS).  Pure host function. */
 int swgpu_estimate_start_level(const uint32_t* bins_host, uint32_t concurrency, int32_t* level);
@@ -169,8 +175,9 @@ int swgpu_partition_to_peers_device(swgpu_handle h, const uint64_t* keys_device,
                                     const uint32_t* first_prefix, uint32_t n_ranks, uint32_t id_base,
                                     void* const* peer_xyz_device, void* const* peer_ids_device,
                                     const uint64_t* dst_offsets, uint64_t* send_counts_host);
-/* Marks the handle as tiling one shard.  start_level: FAST's global start level (-1 = estimate from
- * the local points); global_ids_device: id of every received point (returned by swgpu_get_nodes
+/* Marks the handle as tiling one shard.  start_level: FAST's global start level; -1 = the library estimates
+ * it itself: on the GLOBAL level-5 counts (one 1 MB all-reduce through the hook, collective over all ranks)
+ * when a hook is given, on the local points otherwise; global_ids_device: id of every received point (returned by swgpu_get_nodes
  * instead of local indices; may be NULL).  shard_levels = 0 switches sharding off. */
 int swgpu_set_shard(swgpu_handle h, uint32_t shard_levels, int32_t start_level, swgpu_allreduce_u32_fn allreduce,
                     void* allreduce_ctx, const uint32_t* global_ids_device);

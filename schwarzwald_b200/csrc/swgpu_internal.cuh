@@ -192,6 +192,10 @@ void free_min_distance_scratch(SwMinDistScratch& sc);
 
 // bins[key >> 45] += 1 for unsorted keys (bins are accumulated, not zeroed)
 void launch_prefix_histogram(const u64* keys, u64 n, u32* bins, cudaStream_t stream);
+// the same for the leading `levels` <= 4 octree levels (8^levels bins), privatised in shared memory
+void launch_prefix_histogram_coarse(const u64* keys, u64 n, int levels, u32* bins, cudaStream_t stream);
+// counts[b] = bin_start[b + 1] - bin_start[b]
+void launch_bin_counts(const u32* bin_start, u32 n_bins, u32* counts, cudaStream_t stream);
 // Stable multi-way partition of (xyz, id_base + i) by destination rank; rank r owns the level-5
 // prefixes [first_prefix[r], first_prefix[r+1]).  tile_counts: partition_tiles(n) * SW_MAX_RANKS
 // u32 scratch; send_counts: SW_MAX_RANKS u64 (device).

@@ -590,6 +590,30 @@ estimate_start_level(swgpu_tiler* h, int* S_out)
   return SW_OK;
 }
 
+// one shard of a multi-GPU run: the same estimate on GLOBAL counts.  Every rank takes its level-5 bin
+// counts from its sorted keys, the caller's all-reduce hook sums them (1 MB), every rank evaluates the
+// same rule on the same numbers.  Collective: called by every rank, empty shards included.
+int
+estimate_start_level_global(swgpu_tiler* h, int* S_out)
+{
+  launch_level5_bins(h->keys[0].as<u64>(), h->n, h->bins.as<u32>(), h->stream);
+  CK(h->dense_counts.ensure(262144 * 4));
+  launch_bin_counts(h->bins.as<u32>(), 262144u, h->dense_counts.as<u32>(), h->stream);
+  h->stats.kernel_launches += 2;
+  CK(cudaGetLastError());
+  if (h->allreduce(h->allreduce_ctx, h->dense_counts.as<u32>(), 262144u, h->stream) != 0)
+    return fail(h, SW_ERR_COLLECTIVE, "the all-reduce hook failed (start level)");
+  std::vector<u32> counts(262144);
+  CK(cudaMemcpyAsync(counts.data(), h->dense_counts.p, 262144 * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<u64> prefix(262145, 0);
+  for (u32 b = 0; b < 262144u; ++b)
+    prefix[b + 1] = prefix[b] + counts[b];
+  *S_out = start_level_from_prefix_counts([&](u32 b, u32 group) -> u64 { return prefix[b + group] - prefix[b]; },
+                                          h->prm.concurrency);
+  return SW_OK;
+}
+
 int
 run_batch(swgpu_tiler* h)
 {
@@ -653,7 +677,7 @@ run_batch(swgpu_tiler* h)
       launch_level5_bins(h->keys[0].as<u64>(), h->n, h->bins.as<u32>(), h->stream); // start nodes below
       h->stats.kernel_launches += 1;
     } else {
-      rc = estimate_start_level(h, &S);
+      rc = (sharded && h->allreduce) ? estimate_start_level_global(h, &S) : estimate_start_level(h, &S);
       if (rc)
         return rc;
     }
@@ -1302,6 +1326,18 @@ swgpu_prefix_histogram_device(swgpu_handle h, const uint64_t* keys_device, uint6
     return SW_ERR_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
   launch_prefix_histogram(reinterpret_cast<const u64*>(keys_device), n, bins_device, h->stream);
+  CK(cudaGetLastError());
+  return SW_OK;
+}
+
+int
+swgpu_prefix_histogram_coarse_device(swgpu_handle h, const uint64_t* keys_device, uint64_t n, uint32_t levels,
+                                     uint32_t* bins_device)
+{
+  if (!h || !bins_device || (n && !keys_device) || levels < 1 || levels > 4)
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  launch_prefix_histogram_coarse(reinterpret_cast<const u64*>(keys_device), n, (int)levels, bins_device, h->stream);
   CK(cudaGetLastError());
   return SW_OK;
 }

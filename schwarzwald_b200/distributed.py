@@ -6,12 +6,14 @@ task per start node (tiling/TilingAlgorithms.cpp:1314-1351) and per >= 100 000-p
 intact, so every GPU runs the unchanged single-GPU pipeline on its subtrees:
 
   1. local Morton keys                         swgpu_morton_encode_device  (index_point, clamps in place)
-  2. level-5 prefix histogram, summed          swgpu_prefix_histogram_device + all-reduce (1 MiB)
-  3. global FAST start level + splitters       swgpu_estimate_start_level / swgpu_choose_splitters
-  4. stable partition by destination           swgpu_partition_device
-  5. all-to-all of (xyz 24 B, id 4 B)          NCCL over NVLink (torch.distributed.all_to_all_single)
-  6. single-GPU pipeline on the received points; nodes above the shard depth get their take-all
-     decision from all-reduced counts (the hook passed to swgpu_set_shard)
+  2. coarse (4-level) prefix histogram         swgpu_prefix_histogram_coarse_device + ONE all-gather (16 KB/rank)
+  3. splitters + send/recv count matrix        swgpu_choose_splitters on the summed histogram (host)
+  4+5. partition AND exchange in one kernel    swgpu_partition_to_peers_device: every point is written straight
+       into its destination's receive buffer (peer memory over NVLink, torch symmetric memory); communicators
+       without peer mapping: swgpu_partition_device + all_to_all_single (28 B per point)
+  6. single-GPU pipeline on the received points; FAST's start level from the global level-5 counts of the
+     sorted keys and the take-all decision of nodes above the shard depth both go through the all-reduce
+     hook passed to swgpu_set_shard
 
 Results: every rank reports its nodes with GLOBAL point ids.  Nodes with fewer than `shard_levels`
 levels span ranks; their parts concatenated in rank order (= Morton order) are the node
@@ -35,6 +37,7 @@ import numpy as np
 from . import native
 from .tiler import GpuTiler, TileResult, NODE_DTYPE, SwgpuError
 
+COARSE_LEVELS = 4  # octree levels of the pre-exchange histogram (splitters, count matrix)
 PREFIX_BINS = native.PREFIX_BINS
 
 
@@ -246,7 +249,7 @@ class ShardedTiler:
         if self.shard_levels < 1:
             raise ValueError("spacing too coarse to shard: a sampling cell would span GPUs")
         # device scratch owned here (torch tensors): histogram, node-count exchange buffer
-        self._bins = torch.zeros(PREFIX_BINS, dtype=torch.int32, device=self.device)
+        self._bins = torch.zeros(8 ** COARSE_LEVELS, dtype=torch.int32, device=self.device)
         self._hook = native.ALLREDUCE_FN(self._allreduce_hook)  # keep the callback object alive
         self._keep = {}
         self._views = {}
@@ -336,17 +339,20 @@ class ShardedTiler:
         keys = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
         t.morton_encode_device(xyz.data_ptr(), n, keys.data_ptr())
         mark("encode")
-        # 2. level-5 prefix histogram of the local slice; ONE all-gather gives every rank all
-        #    histograms: their sum is the global histogram (start level, splitters) and, cut at the
-        #    splitters, the complete send/recv count matrix — no further count exchange or sync
+        # 2. coarse (4-level, 4096-bin) prefix histogram of the local slice, accumulated in shared memory; ONE
+        #    all-gather of 16 KB per rank gives every rank all histograms: their sum yields the splitters and,
+        #    cut at the splitters, the complete send/recv count matrix — no further count exchange.  (The exact
+        #    8^6-bin histogram costs one L2 atomic per key, 1.8 ms per 100 M keys; FAST's start level, which
+        #    needs those exact counts, is taken from the sorted keys after the exchange instead, step 6.)
+        cl = COARSE_LEVELS
         self._bins.zero_()
-        t._check(lib.swgpu_prefix_histogram_device(t._h, C.c_void_p(keys.data_ptr()), n,
-                                                   C.c_void_p(self._bins.data_ptr())))
-        all_bins = comm.all_gather(self._bins)  # (world, 8^6) int32, stays on the device
-        bins = all_bins.sum(dim=0, dtype=torch.int32).cpu().numpy().view(np.uint32)  # global histogram
+        t._check(lib.swgpu_prefix_histogram_coarse_device(t._h, C.c_void_p(keys.data_ptr()), n, cl,
+                                                          C.c_void_p(self._bins.data_ptr())))
+        all_bins = comm.all_gather(self._bins).cpu().numpy().view(np.uint32).astype(np.int64)  # (world, 8^cl)
         mark("histogram+allgather")
-        # 3. start level (FAST) and splitters from the global histogram (host, ~0.3 ms)
-        n_global = int(bins.sum(dtype=np.int64))
+        # 3. splitters from the global histogram (host)
+        coarse = all_bins.sum(axis=0)
+        n_global = int(coarse.sum())
         if n_global >= 2 ** 32:
             raise ValueError("global point ids are 32 bit: at most 2^32 - 1 points per batch")
         # reference behaviour on degenerate batches (TilingAlgorithms.cpp:253-259, Parallel.h:181-186)
@@ -354,13 +360,17 @@ class ShardedTiler:
             raise SwgpuError(7, "tile_internal_node: Got zero points to tile @ node r")
         if self.tiling == "FAST" and n_global < self.concurrency:
             raise SwgpuError(9, "Can't scatter a range that has less than 'scatter_factor' elements!")
-        start_level = estimate_start_level(bins, self.concurrency) if self.tiling == "FAST" else -1
-        first_prefix = choose_splitters(bins, comm.world, self.shard_levels)
+        start_level = -1  # FAST: estimated by the library on the global level-5 counts (all-reduce hook)
+        unit = 8 ** (6 - cl)  # level-5 prefixes per coarse bin
+        fine = np.zeros(PREFIX_BINS, np.uint32)
+        fine[::unit] = coarse.astype(np.uint32) if n_global < 2 ** 32 else 0
+        shard_levels = min(self.shard_levels, cl)
+        first_prefix = choose_splitters(fine, comm.world, shard_levels)
         # send/recv count matrix [source, destination]: per-rank histograms cut at the splitters
-        cum = torch.zeros((comm.world, PREFIX_BINS + 1), dtype=torch.int64, device=all_bins.device)
-        torch.cumsum(all_bins, dim=1, dtype=torch.int64, out=cum[:, 1:])
-        cuts = torch.from_numpy(first_prefix.astype(np.int64)).to(all_bins.device)
-        count_matrix = torch.diff(cum[:, cuts], dim=1).cpu().numpy()
+        cum = np.zeros((comm.world, 8 ** cl + 1), np.int64)
+        np.cumsum(all_bins, axis=1, out=cum[:, 1:])
+        cuts = (first_prefix.astype(np.int64) // unit)
+        count_matrix = np.diff(cum[:, cuts], axis=1)
         counts = count_matrix.sum(axis=1)
         assert int(counts[comm.rank]) == n
         if id_base is None:
@@ -387,7 +397,7 @@ class ShardedTiler:
             comm.all_reduce_sum(self._tiny)
             m = int(recv_totals[comm.rank])
             mark("barrier")
-            t._check(lib.swgpu_set_shard(t._h, self.shard_levels, int(start_level), self._hook, None,
+            t._check(lib.swgpu_set_shard(t._h, shard_levels, int(start_level), self._hook, None,
                                          C.c_void_p(pk["ids_ptrs"][comm.rank] if m else 0)))
             self._keep = {"xyz": pk["xyz"][:m * 24].view(torch.float64).view(m, 3),
                           "ids": pk["ids"][:m * 4].view(torch.int32)}
@@ -399,7 +409,7 @@ class ShardedTiler:
                 for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
                     phases[name] = e0.elapsed_time(e1)
             self.last = {"phase_ms": phases, "n_local": n, "n_shard": m, "n_global": n_global,
-                         "start_level": start_level, "first_prefix": first_prefix, "send_counts": sc, "recv_counts": rc,
+                         "start_level": t.start_level(), "first_prefix": first_prefix, "send_counts": sc, "recv_counts": rc,
                          "exchange": "peer kernel (swgpu_partition_to_peers_device over symmetric memory)",
                          "bytes_sent_off_gpu": int(sum(c for r, c in enumerate(sc) if r != comm.rank)) * 28}
             return n
@@ -421,7 +431,7 @@ class ShardedTiler:
         m = int(recv_xyz.shape[0])
         mark("all_to_all")
         # 6. the single-GPU pipeline on the shard
-        t._check(lib.swgpu_set_shard(t._h, self.shard_levels, int(start_level), self._hook, None,
+        t._check(lib.swgpu_set_shard(t._h, shard_levels, int(start_level), self._hook, None,
                                      C.c_void_p(recv_ids.data_ptr() if m else 0)))
         self._keep = {"xyz": recv_xyz, "ids": recv_ids}
         t._check(lib.swgpu_index_batch_device(t._h, C.c_void_p(recv_xyz.data_ptr() if m else 0), m))
@@ -431,7 +441,7 @@ class ShardedTiler:
             torch.cuda.synchronize(self.device)
             for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
                 phases[name] = e0.elapsed_time(e1)
-        self.last = {"phase_ms": phases, "n_local": n, "n_shard": m, "n_global": n_global, "start_level": start_level,
+        self.last = {"phase_ms": phases, "n_local": n, "n_shard": m, "n_global": n_global, "start_level": t.start_level(),
                      "first_prefix": first_prefix, "send_counts": sc, "recv_counts": recv_counts,
                      "exchange": "nccl all_to_all" + (" (peer mapping unavailable: %s)" % self._peer_failed
                                                       if self._peer_failed else ""),

@@ -92,6 +92,7 @@ SYMBOLS = [
     ("swgpu_morton_encode_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     ("swgpu_sort_keys_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     ("swgpu_prefix_histogram_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    ("swgpu_prefix_histogram_coarse_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     ("swgpu_estimate_start_level", C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]),
     ("swgpu_choose_splitters", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     ("swgpu_max_shard_levels", C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
