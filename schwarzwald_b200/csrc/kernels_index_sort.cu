@@ -285,9 +285,22 @@ launch_las_encode(const int* las, u64 n, const SwLasTransform& t, const SwBounds
 #ifndef RS_MATCH_MODE
 #define RS_MATCH_MODE 2 /* 0 = __match_any_sync, 1 = eight ballots, 2 = shared-memory atomicOr */
 #endif
-#define RS_LOOK 8 /* look-back descriptors fetched per round trip */
+#ifndef RS_LOOK
+#define RS_LOOK 4 /* look-back descriptors fetched per round trip (measured: 1: 6.21, 2: 5.87, 4: 5.79, 8: 5.87, 16: 6.12 ms per sort) */
+#endif
 #ifndef RS_MIN_CTAS
 #define RS_MIN_CTAS (1024 / RS_THREADS) /* CTAs per SM the register allocation is capped for: 32 warps per SM */
+#endif
+
+// RS_EXPERIMENT: bit mask of measurement-only switches that remove one phase of the pass to see what it
+// costs (tools/bench_sort.py; the output is NOT sorted when any bit is set, never set in the product build):
+//   1 = no look-back (global offsets = digit base only)   2 = no ranking (trivial ranks)
+//   4 = no scatter (coalesced tile-order stores)           8 = no early-count atomics
+#ifndef RS_EXPERIMENT
+#define RS_EXPERIMENT 0
+#endif
+#ifndef RS_SPLIT_TABLE
+#define RS_SPLIT_TABLE 1 /* 0 = {mask, count} entries of 8 bytes, 1 = separate arrays (5 % faster: 32 banks instead of 16 bank pairs), 2 = + alternating mask arrays (no further gain) */
 #endif
 
 #define RS_FLAG_AGG (1u << 30)
@@ -349,6 +362,12 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
   // per (warp, digit) table entry: .x = lanes currently holding the digit (RS_MATCH_MODE 2),
   // .y = count, later the next free tile-local rank.  Aliases s_keys.
   uint2* s_tab = reinterpret_cast<uint2*>(smem);             // RS_WARPS * 256 * 8 B
+#if RS_SPLIT_TABLE
+  // the same table as two u32 arrays: an 8-byte entry spans two banks, so 256 entries only spread over 16
+  // bank pairs; separate mask / count arrays spread the warp's 32 accesses over all 32 banks
+  u32* s_cnt = reinterpret_cast<u32*>(smem);                 // RS_WARPS * RS_RADIX
+  u32* s_msk = s_cnt + RS_WARPS * RS_RADIX;                  // RS_WARPS * RS_RADIX (x 2 when RS_SPLIT_TABLE == 2)
+#endif
   u32* s_gofs = reinterpret_cast<u32*>(smem + RS_TILE * 12); // 256: global base - tile-local offset
   u32* s_wsum = s_gofs + RS_RADIX;                           // RS_WARPS
   __shared__ u32 s_tile;
@@ -362,6 +381,11 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
 #pragma unroll
   for (int i = 0; i < RS_WARPS; ++i)
     s_tab[i * RS_RADIX + tid] = make_uint2(0u, 0u);
+#if RS_SPLIT_TABLE == 2
+#pragma unroll
+  for (int i = 0; i < RS_WARPS; ++i)
+    s_msk[(RS_WARPS + i) * RS_RADIX + tid] = 0u; // the second mask array
+#endif
   __syncthreads();
   const u32 tile = s_tile;
   const u32 tile_base = tile * RS_TILE;
@@ -385,9 +409,20 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
 
   // ---- 1. early counts --------------------------------------------------------------------------
   uint2* my_tab = s_tab + warp * RS_RADIX;
+  (void)my_tab;
+#if RS_SPLIT_TABLE
+  u32* my_cnt = s_cnt + warp * RS_RADIX;
+  u32* my_msk = s_msk + warp * RS_RADIX;
+#endif
+#if !(RS_EXPERIMENT & 8)
 #pragma unroll
   for (int j = 0; j < RS_ITEMS; ++j)
+#if RS_SPLIT_TABLE
+    atomicAdd(&my_cnt[(u32)(key[j] >> SHIFT) & RS_DIGIT_MASK], 1u);
+#else
     atomicAdd(&my_tab[(u32)(key[j] >> SHIFT) & RS_DIGIT_MASK].y, 1u);
+#endif
+#endif
   __syncthreads();
 
   u32 my_excl;  // tile-local exclusive offset of digit `tid`
@@ -398,7 +433,11 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
     u32 run = 0;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
+#if RS_SPLIT_TABLE
+      c[w] = s_cnt[w * RS_RADIX + d];
+#else
       c[w] = s_tab[w * RS_RADIX + d].y;
+#endif
       run += c[w];
     }
     my_count = run;
@@ -424,7 +463,11 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
     u32 acc = my_excl;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
+#if RS_SPLIT_TABLE
+      s_cnt[w * RS_RADIX + d] = acc;
+#else
       s_tab[w * RS_RADIX + d].y = acc;
+#endif
       acc += c[w];
     }
   }
@@ -438,10 +481,40 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
   unsigned short rank[RS_ITEMS];
   {
     const u32 lt = lanemask_lt();
-#if RS_MATCH_MODE == 2
+#if RS_EXPERIMENT & 2
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j)
+      rank[j] = (unsigned short)(warp_base - lane + j * 32 + lane);
+    (void)lt;
+#elif RS_MATCH_MODE == 2
     const u32 lane_bit = 1u << lane;
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
+#if RS_SPLIT_TABLE
+      const u32 dg = (u32)(key[j] >> SHIFT) & RS_DIGIT_MASK;
+#if RS_SPLIT_TABLE == 2
+      // rows alternate between two mask arrays: the leader's clear of row j cannot race with the ORs of
+      // row j + 1, which saves the third warp barrier of every row
+      u32* msk = my_msk + (j & 1) * (RS_WARPS * RS_RADIX);
+#else
+      u32* msk = my_msk;
+#endif
+      atomicOr(&msk[dg], lane_bit);
+      __syncwarp();
+      uint2 v;
+      v.x = msk[dg];    // group
+      v.y = my_cnt[dg]; // first free rank
+      __syncwarp();
+      const u32 lower = __popc(v.x & lt);
+      if ((v.x >> lane) <= 1u) { // highest lane of the group: reserve the ranks, clear the group
+        msk[dg] = 0u;
+        my_cnt[dg] = v.y + lower + 1u;
+      }
+#if RS_SPLIT_TABLE != 2
+      __syncwarp();
+#endif
+      rank[j] = (unsigned short)(v.y + lower);
+#else
       uint2* e = &my_tab[(u32)(key[j] >> SHIFT) & RS_DIGIT_MASK];
       atomicOr(&e->x, lane_bit);
       __syncwarp();
@@ -452,6 +525,7 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
         *e = make_uint2(0u, v.y + lower + 1u);
       __syncwarp();
       rank[j] = (unsigned short)(v.y + lower);
+#endif
     }
 #else
 #pragma unroll
@@ -500,7 +574,7 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
   {
     const u32 d = tid;
     u32 prev = 0;
-    if (tile != 0) {
+    if (tile != 0 && !(RS_EXPERIMENT & 1)) {
       u32* my_status = status + (size_t)tile * RS_RADIX + d;
       // RS_LOOK predecessors are fetched per round trip (their descriptors were published before
       // their ranking started, so they are almost always present): ~9 dependent L2 latencies
@@ -526,6 +600,9 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
       }
       st_relaxed_u32(my_status, RS_FLAG_PFX | ((prev + my_count) & RS_VAL_MASK));
     }
+#if RS_EXPERIMENT & 1
+    prev = tile * my_count; // keeps the write pattern spread out (roughly where the real offsets are)
+#endif
     s_gofs[d] = digit_base[d] + prev - my_excl;
   }
 
@@ -540,7 +617,14 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
     for (int k = 0; k < RS_ITEMS; ++k) {
       const u32 p = tid + k * RS_THREADS;
       const u64 kk = s_keys[p];
+#if RS_EXPERIMENT & 4
+      const u32 dst = tile_base + p;
+#elif RS_EXPERIMENT & 1
+      u32 dst = s_gofs[(u32)(kk >> SHIFT) & RS_DIGIT_MASK] + p;
+      dst = dst < n ? dst : dst % n;
+#else
       const u32 dst = s_gofs[(u32)(kk >> SHIFT) & RS_DIGIT_MASK] + p;
+#endif
       keys_out[dst] = kk;
       vals_out[dst] = s_vals[p];
     }
@@ -550,7 +634,10 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
       const u32 p = tid + k * RS_THREADS;
       if (p < valid) {
         const u64 kk = s_keys[p];
-        const u32 dst = s_gofs[(u32)(kk >> SHIFT) & RS_DIGIT_MASK] + p;
+        u32 dst = s_gofs[(u32)(kk >> SHIFT) & RS_DIGIT_MASK] + p;
+#if RS_EXPERIMENT
+        dst = (RS_EXPERIMENT & 4) ? tile_base + p : (dst < n ? dst : dst % n);
+#endif
         keys_out[dst] = kk;
         vals_out[dst] = s_vals[p];
       }
