@@ -300,7 +300,7 @@ launch_las_encode(const int* las, u64 n, const SwLasTransform& t, const SwBounds
 #define RS_EXPERIMENT 0
 #endif
 #ifndef RS_SPLIT_TABLE
-#define RS_SPLIT_TABLE 1 /* 0 = {mask, count} entries of 8 bytes, 1 = separate arrays (5 % faster: 32 banks instead of 16 bank pairs), 2 = + alternating mask arrays (no further gain) */
+#define RS_SPLIT_TABLE 1 /* 0 = {mask, count} entries of 8 bytes, 1 = separate arrays (5 % faster: 32 banks instead of 16 bank pairs), 2 = + alternating mask arrays (no further gain), 3 = two rows per round (slower: more table reads) */
 #endif
 
 #define RS_FLAG_AGG (1u << 30)
@@ -381,7 +381,7 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
 #pragma unroll
   for (int i = 0; i < RS_WARPS; ++i)
     s_tab[i * RS_RADIX + tid] = make_uint2(0u, 0u);
-#if RS_SPLIT_TABLE == 2
+#if RS_SPLIT_TABLE >= 2
 #pragma unroll
   for (int i = 0; i < RS_WARPS; ++i)
     s_msk[(RS_WARPS + i) * RS_RADIX + tid] = 0u; // the second mask array
@@ -486,6 +486,37 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
     for (int j = 0; j < RS_ITEMS; ++j)
       rank[j] = (unsigned short)(warp_base - lane + j * 32 + lane);
     (void)lt;
+#elif RS_MATCH_MODE == 2 && RS_SPLIT_TABLE == 3
+    // two rows per round: row j marks its lanes in mask array A, row j + 1 in mask array B; one set of
+    // warp barriers serves both rows.  A digit's running count is advanced once per round by exactly one
+    // lane: the leader of its row-(j+1) group if there is one, else the leader of its row-j group.
+    const u32 lane_bit = 1u << lane;
+    u32* mskA = my_msk;
+    u32* mskB = my_msk + RS_WARPS * RS_RADIX;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j += 2) {
+      const u32 d0 = (u32)(key[j] >> SHIFT) & RS_DIGIT_MASK;
+      const u32 d1 = (u32)(key[j + 1] >> SHIFT) & RS_DIGIT_MASK;
+      atomicOr(&mskA[d0], lane_bit);
+      atomicOr(&mskB[d1], lane_bit);
+      __syncwarp();
+      const u32 a0 = mskA[d0], b0 = mskB[d0], c0 = my_cnt[d0];
+      const u32 a1 = mskA[d1], b1 = mskB[d1], c1 = my_cnt[d1];
+      __syncwarp();
+      rank[j] = (unsigned short)(c0 + __popc(a0 & lt));
+      rank[j + 1] = (unsigned short)(c1 + __popc(a1) + __popc(b1 & lt));
+      if ((a0 >> lane) <= 1u && b0 == 0u) { // leader of a row-j group whose digit does not occur in row j + 1
+        my_cnt[d0] = c0 + __popc(a0);
+        mskA[d0] = 0u;
+      }
+      if ((b1 >> lane) <= 1u) { // leader of a row-(j+1) group: accounts for the row-j group of the digit too
+        my_cnt[d1] = c1 + __popc(a1) + __popc(b1);
+        mskB[d1] = 0u;
+        if (a1)
+          mskA[d1] = 0u;
+      }
+      __syncwarp();
+    }
 #elif RS_MATCH_MODE == 2
     const u32 lane_bit = 1u << lane;
 #pragma unroll

@@ -114,3 +114,27 @@ def test_sharded_exchange_paths_agree(port_oracle, exchange, world):
     assert all(i["exchange"].startswith("peer kernel" if exchange == "peer" else "nccl") for i in infos)
     assert sum(i["n_shard"] for i in infos) == len(xyz)
     _assert_equal(want, got)
+
+
+@pytest.mark.parametrize("levels", [1, 3, 4])
+def test_coarse_prefix_histogram_matches_numpy(levels):
+    """swgpu_prefix_histogram_coarse_device: counts of the leading `levels` octree levels of unsorted keys."""
+    import ctypes as C
+    import torch
+    import schwarzwald_b200 as sw
+    xyz, bmin, bmax, spacing = _setup("urban", 300_001, 4, side_m=500.0)
+    dev = torch.from_numpy(xyz).cuda()
+    n = len(xyz)
+    keys = torch.empty(n, dtype=torch.int64, device="cuda")
+    bins = torch.zeros(8 ** levels, dtype=torch.int32, device="cuda")
+    with sw.GpuTiler("RANDOM_GRID", "ACCURATE", bmin, bmax, spacing) as t:
+        t.morton_encode_device(dev.data_ptr(), n, keys.data_ptr())
+        for _ in range(2):  # bins are accumulated, not zeroed
+            t._check(t._lib.swgpu_prefix_histogram_coarse_device(t._h, C.c_void_p(keys.data_ptr()), n, levels,
+                                                                 C.c_void_p(bins.data_ptr())))
+        torch.cuda.synchronize()
+        assert t._lib.swgpu_prefix_histogram_coarse_device(t._h, C.c_void_p(keys.data_ptr()), n, 5,
+                                                           C.c_void_p(bins.data_ptr())) != 0  # levels > 4 refused
+    k = keys.cpu().numpy().view(np.uint64)
+    want = np.bincount((k >> np.uint64(63 - 3 * levels)).astype(np.int64), minlength=8 ** levels)
+    assert np.array_equal(bins.cpu().numpy().astype(np.int64), 2 * want)

@@ -190,3 +190,27 @@ def test_gpu_payloads_after_double_input(port_oracle):
     w_las, w_headers = port_oracle.payload_las(clamped, got.ids, got.nodes, (bmin, bmax))
     assert np.array_equal(pnts.view(np.uint32), w_pnts.view(np.uint32))
     assert np.array_equal(las, w_las) and headers.tobytes() == w_headers.tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sampling", ["RANDOM_GRID", "GRID_CENTER"])
+def test_gpu_payload_device_variants_equal_host_variants(sampling):
+    """swgpu_get_payload_*_device write the same records into caller-owned device buffers.  RANDOM_GRID reads the
+    positions through the sort permutation, the other strategies from the Morton-ordered copy."""
+    import torch
+    import schwarzwald_b200 as sw
+    rng = np.random.default_rng(17)
+    xyz = np.round(rng.random((90_000, 3)) * [120.0, 90.0, 30.0] + [10.0, 20.0, 5.0], 3)
+    bmin, bmax = sw.cubic_bounds(xyz.min(0), xyz.max(0))
+    spacing = sw.spacing_from_diagonal_fraction(bmin, bmax)
+    with sw.GpuTiler(sampling, "FAST", bmin, bmax, spacing, max_points_per_node=600, concurrency=2) as g:
+        g.tile(xyz.copy())
+        _, ni = g.result_size()
+        pnts, (las, headers) = g.payload_pnts(), g.payload_las()
+        d_pnts = torch.empty((ni, 3), dtype=torch.float32, device="cuda")
+        d_las = torch.empty((ni, 3), dtype=torch.int32, device="cuda")
+        g.payload_pnts_device(d_pnts.data_ptr())
+        d_headers = g.payload_las_device(d_las.data_ptr())
+        torch.cuda.synchronize()
+    assert np.array_equal(d_pnts.cpu().numpy().view(np.uint32), pnts.view(np.uint32))
+    assert np.array_equal(d_las.cpu().numpy(), las) and d_headers.tobytes() == headers.tobytes()
