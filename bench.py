@@ -7,7 +7,8 @@ A "step" is one pass of the hot path over one synthetic batch: Morton indexing, 
 the per-level sampling sweep and (FAST) the reconstruct of the skipped upper levels.  At N = 1 the
 workload is BASELINE.json configs[1]: 100 M-point terrain-like cloud, RANDOM_GRID, FAST.  At N > 1
 (torchrun, one rank per GPU) every rank generates 100 M points of an N x 100 M cloud, the points are
-shuffled so that every GPU owns whole Morton-prefix subtrees (NCCL all-to-all over NVLink), and each
+shuffled so that every GPU owns whole Morton-prefix subtrees (one kernel partitions the local points straight
+into the peers' receive buffers over NVLink; NCCL carries the 16 KB histograms and the barriers), and each
 GPU tiles its subtrees; `value` is all points / max-over-ranks device time ("weak" scaling).
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU code path

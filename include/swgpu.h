@@ -120,14 +120,18 @@ int swgpu_sort_keys_device(swgpu_handle h, uint64_t* keys_device, uint64_t n, ui
  * task per start node, tiling/TilingAlgorithms.cpp:1314-1351, :499-561).  These entry points let a
  * host driver (schwarzwald_b200/distributed.py over torch.distributed/NCCL, or a C++ driver over
  * ncclSend/ncclRecv) shard the points by the leading octree levels of their Morton key:
- *   1. swgpu_morton_encode_device       local keys (index_point, clamps in place)
- *   2. swgpu_prefix_histogram_device    local counts of the 8^6 level-5 prefixes; the caller SUMS
- *                                       them over the ranks (all-reduce)
- *   3. swgpu_estimate_start_level       FAST: global start level from the summed histogram
- *      swgpu_choose_splitters           contiguous prefix ranges of (nearly) equal point count
- *   4. swgpu_partition_device           stable send buffer (positions + global ids) per destination
- *   5. [caller: all-to-all over NVLink]
- *   6. swgpu_set_shard + swgpu_index_batch_device on the received points, swgpu_finalize
+ *   1. swgpu_morton_encode_device            local keys (index_point, clamps in place)
+ *   2. swgpu_prefix_histogram_coarse_device  local counts of the leading 4 octree levels; the caller all-gathers
+ *                                            them (16 KB per rank): sum = global histogram, cut at the splitters =
+ *                                            the complete send/receive count matrix
+ *      (or swgpu_prefix_histogram_device     the exact 8^6-bin variant, one L2 atomic per key)
+ *   3. swgpu_choose_splitters                contiguous prefix ranges of (nearly) equal point count
+ *   4. swgpu_partition_to_peers_device       stable partition written straight into the destinations' receive
+ *                                            buffers (peer memory over NVLink): partition AND exchange in one kernel
+ *      (or swgpu_partition_device + the caller's all-to-all, where peer memory cannot be mapped)
+ *   5. swgpu_set_shard + swgpu_index_batch_device on the received points, swgpu_finalize; FAST's start level
+ *      comes from the global level-5 counts of the sorted keys through the all-reduce hook (start_level = -1)
+ *      or from swgpu_estimate_start_level on an exact global histogram
  * Nodes with fewer than `shard_levels` levels span GPUs: every GPU reports its part of such a node
  * (same index/levels, ids in Morton order); the parts concatenated in rank order are the node.
  * Their take-all decision (Sampling.h:201-208) uses the global point count, summed through the
