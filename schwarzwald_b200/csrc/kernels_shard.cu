@@ -99,7 +99,9 @@ launch_bin_counts(const u32* bin_start, u32 n_bins, u32* counts, cudaStream_t st
 // ---------------------------------------------------------------------------------------------
 #define PT_THREADS 256
 #define PT_WARPS 8
+#ifndef PT_ITEMS
 #define PT_ITEMS 4
+#endif
 #define PT_TILE (PT_THREADS * PT_ITEMS)
 
 struct SwSplitters
@@ -215,17 +217,20 @@ partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict_
 {
   __shared__ double s_x[3 * PT_TILE];
   __shared__ u32 s_id[PT_TILE];
-  __shared__ unsigned char s_d[PT_TILE];
   __shared__ u32 s_wcnt[PT_WARPS][SW_MAX_RANKS];
+  __shared__ u32 s_wbase[PT_WARPS][SW_MAX_RANKS]; // first staged position of (warp, destination)
+  __shared__ u32 s_tot[SW_MAX_RANKS];
   __shared__ u32 s_seg[SW_MAX_RANKS + 1]; // first staged position of every destination's segment
-  __shared__ double* s_gx[SW_MAX_RANKS];
+  __shared__ double* s_gx[SW_MAX_RANKS];  // destination pointers, biased by the segment start
   __shared__ u32* s_gi[SW_MAX_RANKS];
-  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const u64 base = (u64)blockIdx.x * PT_TILE;
-  const u32 tile_valid = (n - base) < PT_TILE ? (u32)(n - base) : PT_TILE;
   const u32 lt = lanemask_lt();
-  // warp-striped: item j of a warp covers 32 consecutive points; a warp owns PT_ITEMS * 32 of them
+  // warp-striped: item j of a warp covers 32 consecutive points; a warp owns PT_ITEMS * 32 of them.
+  // One ballot per (item, destination) yields both the warp's counts and the point's rank inside its
+  // (warp, destination) group: items in order, lanes in order = index order, so the partition is stable.
   u32 dest[PT_ITEMS];
+  u32 low[PT_ITEMS];
   u32 cnt[SW_MAX_RANKS];
 #pragma unroll
   for (u32 r = 0; r < SW_MAX_RANKS; ++r)
@@ -234,10 +239,15 @@ partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict_
   for (int j = 0; j < PT_ITEMS; ++j) {
     const u64 i = base + warp * (32 * PT_ITEMS) + j * 32 + lane;
     dest[j] = (i < n) ? dest_of(keys[i], sp) : 0xFFu;
+    low[j] = 0;
 #pragma unroll
     for (u32 r = 0; r < SW_MAX_RANKS; ++r)
-      if (r < sp.n_ranks) // warp-uniform: a ballot costs ~2.6 SM-cycles, skip the unused ranks
-        cnt[r] += __popc(__ballot_sync(0xffffffffu, dest[j] == r));
+      if (r < sp.n_ranks) { // warp-uniform: a ballot costs ~2.6 SM-cycles, skip the unused ranks
+        const u32 m = __ballot_sync(0xffffffffu, dest[j] == r);
+        if (dest[j] == r)
+          low[j] = cnt[r] + __popc(m & lt);
+        cnt[r] += __popc(m);
+      }
   }
   if (lane < SW_MAX_RANKS) {
     u32 mine = 0;
@@ -247,65 +257,64 @@ partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict_
     s_wcnt[warp][lane] = mine;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    u32 run = 0;
-    u64 sent_before = 0; // local send buffer: destinations are laid out one after the other
-    for (u32 r = 0; r < SW_MAX_RANKS; ++r) {
-      s_seg[r] = run;
-      u32 tot = 0;
-      for (u32 w = 0; w < PT_WARPS; ++w)
-        tot += s_wcnt[w][r];
-      run += tot;
-      if (r < sp.n_ranks) {
-        const u64 off = sent_before + tile_offsets[(u64)blockIdx.x * SW_MAX_RANKS + r];
-        s_gx[r] = dst.xyz[r] + 3 * off;
-        s_gi[r] = dst.ids[r] + off;
-        if (send_counts)
-          sent_before += send_counts[r];
-      }
-    }
-    s_seg[SW_MAX_RANKS] = run;
+  if (tid < SW_MAX_RANKS) {
+    u32 tot = 0;
+#pragma unroll
+    for (u32 w = 0; w < PT_WARPS; ++w)
+      tot += s_wcnt[w][tid];
+    s_tot[tid] = tot;
   }
   __syncthreads();
-  u32 run[SW_MAX_RANKS]; // staged position of the next point of this warp per destination
-#pragma unroll
-  for (u32 r = 0; r < SW_MAX_RANKS; ++r) {
-    u32 o = s_seg[r];
-    for (u32 w = 0; w < warp; ++w)
-      o += s_wcnt[w][r];
-    run[r] = o;
+  if (tid < SW_MAX_RANKS) {
+    const u32 r = tid;
+    u32 seg = 0;
+    u64 sent_before = 0; // local send buffer: destinations are laid out one after the other
+    for (u32 q = 0; q < r; ++q) {
+      seg += s_tot[q];
+      if (send_counts && q < sp.n_ranks)
+        sent_before += send_counts[q];
+    }
+    s_seg[r] = seg;
+    if (r == SW_MAX_RANKS - 1)
+      s_seg[SW_MAX_RANKS] = seg + s_tot[r];
+    if (r < sp.n_ranks) {
+      const u64 off = sent_before + tile_offsets[(u64)blockIdx.x * SW_MAX_RANKS + r];
+      // staged element e of this destination's segment goes to pointer[e]: bias by the segment start
+      s_gx[r] = dst.xyz[r] + 3 * off - 3 * (u64)seg;
+      s_gi[r] = dst.ids[r] + off - seg;
+    }
   }
+  __syncthreads();
+  if (tid < PT_WARPS * SW_MAX_RANKS) {
+    const u32 w = tid / SW_MAX_RANKS, r = tid % SW_MAX_RANKS;
+    u32 o = s_seg[r];
+    for (u32 q = 0; q < w; ++q)
+      o += s_wcnt[q][r];
+    s_wbase[w][r] = o;
+  }
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < PT_ITEMS; ++j) {
     const u64 i = base + warp * (32 * PT_ITEMS) + j * 32 + lane;
-    u32 pos = 0;
-#pragma unroll
-    for (u32 r = 0; r < SW_MAX_RANKS; ++r) {
-      if (r < sp.n_ranks) {
-        const u32 m = __ballot_sync(0xffffffffu, dest[j] == r);
-        if (dest[j] == r)
-          pos = run[r] + __popc(m & lt);
-        run[r] += __popc(m);
-      }
-    }
     if (i < n) {
+      const u32 pos = s_wbase[warp][dest[j]] + low[j];
       s_x[3 * pos] = xyz[3 * i];
       s_x[3 * pos + 1] = xyz[3 * i + 1];
       s_x[3 * pos + 2] = xyz[3 * i + 2];
       s_id[pos] = id_base + (u32)i;
-      s_d[pos] = (unsigned char)dest[j];
     }
   }
   __syncthreads();
-  // copy-out: consecutive threads write consecutive doubles of a destination's segment
-  for (u32 e = threadIdx.x; e < 3 * tile_valid; e += PT_THREADS) {
-    const u32 q = e / 3, c = e - 3 * q;
-    const u32 d = s_d[q];
-    s_gx[d][3 * (q - s_seg[d]) + c] = s_x[e];
-  }
-  for (u32 q = threadIdx.x; q < tile_valid; q += PT_THREADS) {
-    const u32 d = s_d[q];
-    s_gi[d][q - s_seg[d]] = s_id[q];
+  // copy-out, one destination after the other: a segment leaves as one contiguous run of coalesced stores
+  // (no per-element destination lookup, no division)
+  for (u32 r = 0; r < sp.n_ranks; ++r) {
+    const u32 b = s_seg[r], e = s_seg[r + 1];
+    double* gx = s_gx[r];
+    u32* gi = s_gi[r];
+    for (u32 k = 3 * b + tid; k < 3 * e; k += PT_THREADS)
+      gx[k] = s_x[k];
+    for (u32 k = b + tid; k < e; k += PT_THREADS)
+      gi[k] = s_id[k];
   }
 }
 
