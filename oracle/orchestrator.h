@@ -283,11 +283,18 @@ struct Orchestrator
     }
   }
 
+  /* The reference calls std::sort (TilingAlgorithms.cpp:600-604, 1289-1292), whose order of equal keys is
+   * unspecified; parity runs pin it to "stable by original index"  with std::stable_sort.
+   * Timing runs of the reference arm use std::sort itself. */
+  bool reference_sort = false;
+
   void sort_items(std::vector<Item>& items)
   {
-    std::stable_sort(items.begin(), items.end(), [this](const Item& l, const Item& r) {
-      return prims.key(l) < prims.key(r);
-    });
+    auto by_key = [this](const Item& l, const Item& r) { return prims.key(l) < prims.key(r); };
+    if (reference_sort)
+      std::sort(items.begin(), items.end(), by_key);
+    else
+      std::stable_sort(items.begin(), items.end(), by_key);
     sorted_keys.resize(items.size());
     sorted_ids.resize(items.size());
     duplicate_keys = 0;

@@ -36,6 +36,7 @@
 #include "io/LASPersistence.h"
 #include "io/PNTSWriter.h"
 
+#include <chrono>
 #include <cstring>
 #include <memory>
 
@@ -215,6 +216,7 @@ struct Handle
   std::vector<uint32_t> order;
   uint64_t duplicate_keys = 0;
   int32_t start_level = -1;
+  double seconds = 0.0; /* index + sort + tiling only (o.run()), without building or copying buffers */
   std::string error;
 };
 
@@ -358,6 +360,15 @@ swr_set_threads(uint32_t n)
   g_threads = n ? n : 1;
 }
 
+/* 1 = sort with std::sort as the reference does (timing runs), 0 = std::stable_sort (parity runs, default) */
+static int g_reference_sort = 0;
+
+void
+swr_set_reference_sort(int32_t on)
+{
+  g_reference_sort = on;
+}
+
 int
 swr_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
 {
@@ -366,7 +377,10 @@ swr_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
   try {
     RefPrims prims(xyz, n, params->sampling, params->max_points_per_node);
     swo::Orchestrator<RefPrims> o(prims, *params, g_threads);
+    o.reference_sort = g_reference_sort != 0;
+    const auto t0 = std::chrono::steady_clock::now();
     o.run();
+    h->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     h->nodes = std::move(o.nodes);
     h->ids = std::move(o.ids);
     h->keys = std::move(o.sorted_keys);
@@ -388,6 +402,12 @@ swr_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
     h->error = e.what();
     return SW_ERR_STATE;
   }
+}
+
+double
+swr_tile_seconds(void* handle)
+{
+  return static_cast<Handle*>(handle)->seconds;
 }
 
 uint64_t

@@ -162,6 +162,8 @@ class Oracle:
            C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p])
         f("tile", C.c_int, [C.POINTER(SwParams), C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)])
         f("set_threads", None, [C.c_uint32])
+        f("set_reference_sort", None, [C.c_int32])
+        f("tile_seconds", C.c_double, [C.c_void_p])
         f("node_count", C.c_uint64, [C.c_void_p])
         f("point_id_count", C.c_uint64, [C.c_void_p])
         f("start_level", C.c_int32, [C.c_void_p])
@@ -276,6 +278,11 @@ class Oracle:
         indexing) on std::threads; the sort stays one std::sort as in the reference.  Default 1."""
         self._set_threads(int(n))
 
+    def set_reference_sort(self, on=True):
+        """Timing runs: sort with std::sort exactly as the reference does (tie order unspecified) instead of the
+        std::stable_sort that pins the tie order for the parity runs."""
+        self._set_reference_sort(1 if on else 0)
+
     # --- whole batch --------------------------------------------------------------------------
     def tile(self, params: SwParams, xyz, return_clamped=False):
         xyz = np.array(xyz, dtype=np.float64, order="C", copy=True).reshape(-1, 3)
@@ -295,6 +302,7 @@ class Oracle:
             self._get_keys(h, keys.ctypes.data, order.ctypes.data)
             res = TileResult(nodes, ids, keys, order, int(self._start_level(h)),
                              int(self._duplicate_keys(h)))
+            res.seconds = float(self._tile_seconds(h))  # index + sort + tiling inside the library
         finally:
             self._destroy(h)
         if return_clamped:

@@ -17,6 +17,7 @@
  */
 #include "orchestrator.h"
 
+#include <chrono>
 #include <cstring>
 #include <unordered_map>
 
@@ -539,6 +540,7 @@ struct Handle
   std::vector<uint32_t> order;
   uint64_t duplicate_keys = 0;
   int32_t start_level = -1;
+  double seconds = 0.0; /* index + sort + tiling only (o.run()), without building or copying buffers */
   std::string error;
 };
 
@@ -677,6 +679,15 @@ swo_set_threads(uint32_t n)
   g_threads = n ? n : 1;
 }
 
+/* 1 = sort with std::sort as the reference does (timing runs), 0 = std::stable_sort (parity runs, default) */
+static int g_reference_sort = 0;
+
+void
+swo_set_reference_sort(int32_t on)
+{
+  g_reference_sort = on;
+}
+
 int
 swo_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
 {
@@ -686,7 +697,10 @@ swo_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
   try {
     RestatedPrims prims{ xyz, n, params->sampling, params->max_points_per_node };
     Orchestrator<RestatedPrims> o(prims, *params, g_threads);
+    o.reference_sort = g_reference_sort != 0;
+    const auto t0 = std::chrono::steady_clock::now();
     o.run();
+    h->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     h->nodes = std::move(o.nodes);
     h->ids = std::move(o.ids);
     h->keys = std::move(o.sorted_keys);
@@ -701,6 +715,12 @@ swo_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
     h->error = e.what();
     return SW_ERR_STATE;
   }
+}
+
+double
+swo_tile_seconds(void* handle)
+{
+  return static_cast<Handle*>(handle)->seconds;
 }
 
 uint64_t
