@@ -41,6 +41,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <iterator>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -470,6 +471,145 @@ struct Orchestrator
       });
       for (auto& c : outs)
         merge(c);
+    }
+  }
+
+  /* ---- several batches through TilingAlgorithmV1 (ACCURATE) ---------------------------
+   * The reference keeps what every node stores in its persistence and, when a later batch reaches the node
+   * again, reads those points back, merges them with the incoming ones and samples the union
+   * (tile_node, TilingAlgorithms.cpp:351-492).  Restated here with a lossless in-memory store (MemoryPersistence:
+   * is_lossless() == true, so read_pnts_from_disk does not re-sort, :104-106).
+   * Extra Prims requirements:
+   *   uint64_t morton_in_bounds(uint32_t id, const Box& bounds);   // calculate_morton_index<21>, no clamping
+   *   Item make_item(uint32_t id, uint64_t key);
+   */
+  std::map<std::pair<uint32_t, uint64_t>, std::vector<uint32_t>> store; /* node -> stored ids, stored order */
+  std::map<std::pair<uint32_t, uint64_t>, uint32_t> store_flags;
+
+  void store_node(const Item* begin, const Item* end, const NodeStructure& node, uint32_t flags)
+  {
+    std::vector<uint32_t>& v = store[{ node.path_levels, node.path_index }];
+    v.clear();
+    for (const Item* it = begin; it != end; ++it)
+      v.push_back(prims.id(*it));
+    store_flags[{ node.path_levels, node.path_index }] = flags;
+  }
+
+  void tile_node_cached(std::vector<Item>& node_data, const NodeStructure& node, const NodeStructure& root)
+  {
+    /* read_pnts_from_disk, :50-109: the node's key is the baseline, only the levels below the node are
+     * recomputed, relative to the NODE's bounds */
+    std::vector<Item> cached;
+    const auto found = store.find({ node.path_levels, node.path_index });
+    if (found != store.end()) {
+      const uint32_t start_level = static_cast<uint32_t>(node.level + 1);
+      cached.reserve(found->second.size());
+      for (uint32_t id : found->second) {
+        const uint64_t below = prims.morton_in_bounds(id, node.bounds);
+        /* set_octant_at_level(level, below.get_octant_at_level(level - start_level)) for level >= start_level:
+         * the top (21 - start_level) levels of `below` move down behind the node's own levels */
+        const uint64_t key = node.morton_index | (start_level < MAX_OCTREE_LEVELS ? (below >> (3 * start_level)) : 0);
+        cached.push_back(prims.make_item(id, key));
+      }
+    }
+    const size_t cached_count = cached.size();
+
+    const int32_t sample_level = prims.required_depth(node.level, root);
+    const bool requires_deeper = sample_level > node.level;
+    const int32_t max_level = static_cast<int32_t>(std::min<uint32_t>(MAX_OCTREE_LEVELS - 1, node.max_depth));
+    bool terminal = false;
+    if (!requires_deeper) {
+      terminal = sample_level >= max_level; /* :420-427 */
+    } else {
+      if (node.level >= max_level) /* :436-442 */
+        terminal = true;
+      else if (sample_level >= static_cast<int32_t>(MAX_OCTREE_LEVELS)) /* :444-483 */
+        throw OracleError(SW_ERR_DEEP_REROOT, "deep re-root path is not supported");
+    }
+
+    std::vector<Item> all;
+    if (terminal) { /* merge_node_data_unsorted, Node.cpp:22-34 */
+      if (node_data.empty())
+        all = std::move(cached);
+      else {
+        all = std::move(node_data);
+        all.insert(all.end(), cached.begin(), cached.end());
+      }
+      store_node(all.data(), all.data() + all.size(), node, SW_NODE_TERMINAL);
+      return;
+    }
+    /* merge_node_data_sorted, Node.cpp:3-20: incoming points first on equal keys */
+    if (node_data.empty())
+      all = std::move(cached);
+    else if (cached.empty())
+      all = std::move(node_data);
+    else {
+      all.reserve(node_data.size() + cached.size());
+      std::merge(node_data.begin(), node_data.end(), cached.begin(), cached.end(), std::back_inserter(all),
+                 [this](const Item& l, const Item& r) { return prims.key(l) < prims.key(r); });
+    }
+    if (all.empty()) /* :253-259 */
+      throw OracleError(SW_ERR_EMPTY_NODE, "tile_internal_node: Got zero points to tile");
+
+    /* once a node has been sampled it is always sampled again (:272-275) */
+    const Behaviour behaviour = cached_count > 0 ? AlwaysAdhereToMinSpacing : TakeAllWhenCountBelowMaxPoints;
+    const int32_t rel_level = node.level - (root.level + 1);
+    const size_t taken = prims.sample(all.data(), all.data() + all.size(), node.morton_index, rel_level, root.bounds,
+                                      root.max_spacing, behaviour);
+    const bool took_all = taken == all.size();
+    const bool by_count = behaviour == TakeAllWhenCountBelowMaxPoints && all.size() <= params.max_points_per_node;
+    store_node(all.data(), all.data() + taken, node, (took_all && by_count) ? SW_NODE_TAKE_ALL : 0u);
+
+    /* split_range_into_child_nodes, :116-162: everything that was not selected moves down, points this node
+     * stored in an earlier batch included */
+    Item* rest = all.data() + taken;
+    Item* end = all.data() + all.size();
+    if (rest == end)
+      return;
+    const int32_t child_level = node.level + 1;
+    if (child_level >= static_cast<int32_t>(MAX_OCTREE_LEVELS))
+      throw OracleError(SW_ERR_DEEP_REROOT, "child level exceeds MortonIndex64 capacity");
+    const auto cuts = prims.partition(rest, end, static_cast<uint32_t>(child_level));
+    for (uint8_t octant = 0; octant < 8; ++octant) {
+      if (cuts[octant] == cuts[octant + 1])
+        continue;
+      NodeStructure child = node;
+      const uint32_t shift = (MAX_OCTREE_LEVELS - child_level - 1) * 3;
+      child.morton_index |= (static_cast<uint64_t>(octant & 7) << shift);
+      child.bounds = prims.octant_bounds(octant, node.bounds);
+      child.level = child_level;
+      child.max_spacing /= 2;
+      child.path_index = (node.path_index << 3) | octant;
+      child.path_levels = node.path_levels + 1;
+      std::vector<Item> child_data(rest + cuts[octant], rest + cuts[octant + 1]);
+      tile_node_cached(child_data, child, root);
+    }
+  }
+
+  /* batch b = points [offsets[b], offsets[b + 1]) of the prims' point array; one build_execution_graph per batch
+   * (TilingAlgorithms.cpp:577-626) */
+  void run_accurate_batches(const uint64_t* offsets, uint32_t n_batches)
+  {
+    const NodeStructure root = make_root();
+    const Box rb = root_bounds();
+    for (uint32_t b = 0; b < n_batches; ++b) {
+      std::vector<Item> items;
+      prims.index_range(offsets[b], offsets[b + 1], items, rb);
+      sort_items(items);
+      if (items.empty())
+        throw OracleError(SW_ERR_EMPTY_NODE, "tile_internal_node: Got zero points to tile");
+      tile_node_cached(items, root, root);
+    }
+    for (const auto& kv : store) { /* the final content of the persistence, (levels, index) order */
+      sw_node n{};
+      n.levels = kv.first.first;
+      n.index = kv.first.second;
+      n.flags = store_flags[kv.first];
+      n.first = ids.size();
+      n.count = kv.second.size();
+      ids.insert(ids.end(), kv.second.begin(), kv.second.end());
+      node_lookup[kv.first] = nodes.size();
+      nodes.push_back(n);
     }
   }
 

@@ -132,6 +132,14 @@ struct RefPrims
 
   uint64_t point_count() const { return refs.size(); }
 
+  /* the reference's own calculate_morton_index<21> (tiling/OctreeAlgorithms.h:64-87) relative to arbitrary
+   * bounds, as read_pnts_from_disk calls it (tiling/TilingAlgorithms.cpp:88-90) */
+  uint64_t morton_in_bounds(uint32_t id, const swo::Box& bounds)
+  {
+    return calculate_morton_index<21>(refs[id].position(), to_aabb(bounds)).get();
+  }
+  Item make_item(uint32_t id, uint64_t key) { return Item{ refs[id], MortonIndex64{ key } }; }
+
   void index_range(uint64_t b, uint64_t e, std::vector<Item>& out, const swo::Box& bounds)
   {
     const AABB bb = to_aabb(bounds);
@@ -408,6 +416,38 @@ double
 swr_tile_seconds(void* handle)
 {
   return static_cast<Handle*>(handle)->seconds;
+}
+
+int
+swr_tile_batches(const sw_params* params, double* xyz, uint64_t n, const uint64_t* offsets, uint32_t n_batches,
+                 void** out_handle)
+{
+  auto* h = new Handle();
+  *out_handle = h;
+  try {
+    if (params->tiling != SW_ACCURATE || n_batches == 0 || offsets[n_batches] != n)
+      throw swo::OracleError(SW_ERR_INVALID_ARGUMENT, "tile_batches: ACCURATE only, offsets must end at n");
+    RefPrims prims(xyz, n, params->sampling, params->max_points_per_node);
+    swo::Orchestrator<RefPrims> o(prims, *params, 1);
+    o.run_accurate_batches(offsets, n_batches);
+    h->nodes = std::move(o.nodes);
+    h->ids = std::move(o.ids);
+    h->keys = std::move(o.sorted_keys);
+    h->order = std::move(o.sorted_ids);
+    for (uint64_t i = 0; i < n; ++i) { /* index_point clamps in place inside the PointBuffer */
+      const auto& pos = prims.buffer.positions()[i];
+      xyz[3 * i] = pos.x;
+      xyz[3 * i + 1] = pos.y;
+      xyz[3 * i + 2] = pos.z;
+    }
+    return SW_OK;
+  } catch (const swo::OracleError& e) {
+    h->error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    h->error = e.what();
+    return SW_ERR_STATE;
+  }
 }
 
 uint64_t

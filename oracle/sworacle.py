@@ -161,6 +161,8 @@ class Oracle:
           [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32,
            C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p])
         f("tile", C.c_int, [C.POINTER(SwParams), C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)])
+        f("tile_batches", C.c_int, [C.POINTER(SwParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
+                                    C.POINTER(C.c_void_p)])
         f("set_threads", None, [C.c_uint32])
         f("set_reference_sort", None, [C.c_int32])
         f("tile_seconds", C.c_double, [C.c_void_p])
@@ -308,6 +310,30 @@ class Oracle:
         if return_clamped:
             return res, xyz
         return res
+
+
+def _tile_batches(self, params, xyz, batch_sizes, return_clamped=False):
+    """ACCURATE tiling of several batches (TilingAlgorithmV1 with cached points and a
+    lossless in-memory persistence).  `batch_sizes` splits xyz into consecutive batches; point ids are global."""
+    xyz = np.array(xyz, dtype=np.float64, order="C", copy=True).reshape(-1, 3)
+    offsets = np.concatenate([[0], np.cumsum(np.asarray(batch_sizes, np.int64))]).astype(np.uint64)
+    assert int(offsets[-1]) == len(xyz)
+    h = C.c_void_p()
+    rc = self._tile_batches(C.byref(params), xyz.ctypes.data, len(xyz), offsets.ctypes.data, len(offsets) - 1,
+                            C.byref(h))
+    try:
+        if rc != 0:
+            raise OracleFailure(rc, self._last_error(h).decode())
+        nodes = np.empty(self._node_count(h), NODE_DTYPE)
+        ids = np.empty(self._point_id_count(h), np.uint32)
+        self._get_nodes(h, nodes.ctypes.data, ids.ctypes.data)
+        res = TileResult(nodes, ids)
+    finally:
+        self._destroy(h)
+    return (res, xyz) if return_clamped else res
+
+
+Oracle.tile_batches = _tile_batches
 
 
 class OracleFailure(RuntimeError):

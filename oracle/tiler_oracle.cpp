@@ -249,6 +249,13 @@ struct RestatedPrims
 
   uint64_t point_count() const { return n; }
 
+  /* calculate_morton_index<21> relative to arbitrary bounds, no clamping (read_pnts_from_disk) */
+  uint64_t morton_in_bounds(uint32_t id, const Box& bounds) const
+  {
+    return calculate_morton_index(xyz + 3 * static_cast<uint64_t>(id), bounds);
+  }
+  static IP make_item(uint32_t id, uint64_t key) { return IP{ key, id }; }
+
   void index_range(uint64_t b, uint64_t e, std::vector<IP>& out, const Box& bounds)
   {
     out.resize(e - b);
@@ -721,6 +728,34 @@ double
 swo_tile_seconds(void* handle)
 {
   return static_cast<Handle*>(handle)->seconds;
+}
+
+/* ACCURATE tiling of several batches, batch b = points [offsets[b], offsets[b + 1]) */
+int
+swo_tile_batches(const sw_params* params, double* xyz, uint64_t n, const uint64_t* offsets, uint32_t n_batches,
+                 void** out_handle)
+{
+  auto* h = new Handle();
+  h->params = *params;
+  *out_handle = h;
+  try {
+    if (params->tiling != SW_ACCURATE || n_batches == 0 || offsets[n_batches] != n)
+      throw OracleError(SW_ERR_INVALID_ARGUMENT, "tile_batches: ACCURATE only, offsets must end at n");
+    RestatedPrims prims{ xyz, n, params->sampling, params->max_points_per_node };
+    Orchestrator<RestatedPrims> o(prims, *params, 1);
+    o.run_accurate_batches(offsets, n_batches);
+    h->nodes = std::move(o.nodes);
+    h->ids = std::move(o.ids);
+    h->keys = std::move(o.sorted_keys);
+    h->order = std::move(o.sorted_ids);
+    return SW_OK;
+  } catch (const OracleError& e) {
+    h->error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    h->error = e.what();
+    return SW_ERR_STATE;
+  }
 }
 
 uint64_t

@@ -124,3 +124,59 @@ def test_port_equals_committed_reference_golden(port_oracle, case):
     res = port_oracle.tile(p, xyz)
     digest = make_golden.digest(res)
     assert digest == g["digest"], (g["sampling"], g["tiling"], g["cloud"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# SURVEY section 8 f1 (groundwork): several batches through TilingAlgorithmV1 with cached points
+# ---------------------------------------------------------------------------------------------------
+def _batch_cloud():
+    import schwarzwald_b200 as sw
+    xyz = cloud(33, 90_000, [400.0, 300.0, 60.0], [1000.0, -20.0, 5.0])
+    xyz[:5] -= 700.0  # outliers of the first batch get clamped
+    bmin, bmax = sw.cubic_bounds(xyz[5:].min(0), xyz[5:].max(0))
+    return xyz, bmin, bmax, sw.spacing_from_diagonal_fraction(bmin, bmax)
+
+
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+def test_multi_batch_port_equals_reference(port_oracle, ref_oracle, sampling):
+    """read_pnts_from_disk re-keying (the reference's own calculate_morton_index relative to the node bounds in
+    the ref build), merge with the incoming points, AlwaysAdhereToMinSpacing on revisits."""
+    from oracle import sworacle
+    xyz, bmin, bmax, spacing = _batch_cloud()
+    p = sworacle.make_params(sampling, "ACCURATE", spacing, bmin, bmax, max_points_per_node=800, concurrency=2)
+    sizes = [20_000, 45_000, 25_000]
+    a, ca = port_oracle.tile_batches(p, xyz, sizes, return_clamped=True)
+    b, cb = ref_oracle.tile_batches(p, xyz, sizes, return_clamped=True)
+    assert np.array_equal(ca, cb)
+    ta, ia = a.canonical()
+    tb, ib = b.canonical()
+    assert np.array_equal(ta, tb) and np.array_equal(ia, ib)
+    seen = np.bincount(a.ids, minlength=len(xyz))
+    assert (seen == 1).all(), "every point is stored in exactly one node"
+
+
+@pytest.mark.parametrize("sampling", ["RANDOM_GRID", "JITTERED", "MIN_DISTANCE"])
+def test_one_batch_through_the_batch_path_equals_single_batch(port_oracle, sampling):
+    from oracle import sworacle
+    xyz, bmin, bmax, spacing = _batch_cloud()
+    p = sworacle.make_params(sampling, "ACCURATE", spacing, bmin, bmax, max_points_per_node=800, concurrency=2)
+    one = port_oracle.tile(p, xyz)
+    same = port_oracle.tile_batches(p, xyz, [len(xyz)])
+    t1, i1 = one.canonical()
+    t2, i2 = same.canonical()
+    assert np.array_equal(t1[:, :3], t2[:, :3]) and np.array_equal(i1, i2)
+
+
+def test_multi_batch_revisited_nodes_are_resampled(port_oracle):
+    """A node that already holds points is sampled with AlwaysAdhereToMinSpacing on the next visit: the union of
+    two small batches that would each be stored whole (count <= max_points_per_node) is thinned out."""
+    from oracle import sworacle
+    xyz, bmin, bmax, spacing = _batch_cloud()
+    xyz = xyz[5:6005]
+    p = sworacle.make_params("GRID_CENTER", "ACCURATE", spacing, bmin, bmax, max_points_per_node=4000, concurrency=2)
+    first = port_oracle.tile_batches(p, xyz[:3000], [3000])
+    assert len(first.nodes) == 1 and int(first.nodes["count"][0]) == 3000  # taken whole
+    both = port_oracle.tile_batches(p, xyz, [3000, 3000])
+    root = both.nodes[(both.nodes["levels"] == 0)]
+    assert len(root) == 1 and int(root["count"][0]) < 6000 and len(both.nodes) > 1
+    assert (np.bincount(both.ids, minlength=len(xyz)) == 1).all()
