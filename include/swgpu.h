@@ -47,7 +47,9 @@ int swgpu_reserve(swgpu_handle h, uint64_t n);
  *        (tiling/OctreeAlgorithms.h:156-170).
  * swgpu_index_batch takes a HOST buffer (copied to the device, clamped values copied back);
  * swgpu_index_batch_device takes a DEVICE pointer that stays owned by the caller and must stay
- * valid until the results have been fetched.
+ * valid until the results have been fetched.  Device pointers handed to the indexing entry points
+ * (positions, LAS records, keys) must be 16-byte aligned (any cudaMalloc / whole-tensor pointer is);
+ * others are refused with SW_ERR_INVALID_ARGUMENT.
  */
 int swgpu_index_batch(swgpu_handle h, double* xyz_host, uint64_t n);
 int swgpu_index_batch_device(swgpu_handle h, double* xyz_device, uint64_t n);

@@ -600,6 +600,11 @@ struct Orchestrator
         throw OracleError(SW_ERR_EMPTY_NODE, "tile_internal_node: Got zero points to tile");
       tile_node_cached(items, root, root);
     }
+    emit_store();
+  }
+
+  void emit_store()
+  {
     for (const auto& kv : store) { /* the final content of the persistence, (levels, index) order */
       sw_node n{};
       n.levels = kv.first.first;
@@ -611,6 +616,80 @@ struct Orchestrator
       node_lookup[kv.first] = nodes.size();
       nodes.push_back(n);
     }
+  }
+
+  /* TilingAlgorithmV3 over several batches: the first batch fixes the start level
+   * (build_execution_graph_for_first_iteration, :1250-1360); later batches are indexed and sorted in
+   * num_indexing_threads chunks, split at that level and k-way merged per start node
+   * (build_execution_graph_for_later_iterations, :1362-1453; merge_ranges, Algorithm.h:111-150, keeps the
+   * earlier chunk on equal keys) -- with the tie rule "stable by original index" that is the stable sort of the
+   * whole batch cut at the start nodes.  Every start node goes through tile_node with its cached points;
+   * finalize reconstructs the ancestors of every start node the persistence holds (:1717-1784). */
+  void run_fast_batches(const uint64_t* offsets, uint32_t n_batches)
+  {
+    const NodeStructure root = make_root();
+    const Box rb = root_bounds();
+    uint32_t S = 0;
+    for (uint32_t b = 0; b < n_batches; ++b) {
+      std::vector<Item> items;
+      prims.index_range(offsets[b], offsets[b + 1], items, rb);
+      if (items.size() < params.concurrency) /* parallel::scatter, threading/Parallel.h:181-186 */
+        throw OracleError(SW_ERR_TOO_FEW_POINTS, "fewer points than indexing threads");
+      sort_items(items);
+      if (b == 0) {
+        S = estimate_start_level(items, params.concurrency);
+        start_level = static_cast<int32_t>(S);
+      }
+      const uint32_t shift = (MAX_OCTREE_LEVELS - S) * 3;
+      size_t lo = 0;
+      while (lo < items.size()) {
+        const uint64_t prefix = prims.key(items[lo]) >> shift;
+        size_t hi = lo + 1;
+        while (hi < items.size() && (prims.key(items[hi]) >> shift) == prefix)
+          ++hi;
+        NodeStructure n{}; /* prepare_range_for_tiling, :1622-1660 */
+        n.bounds = root.bounds;
+        for (uint32_t l = 0; l < S; ++l)
+          n.bounds = prims.octant_bounds(static_cast<uint8_t>((prefix >> (3 * (S - 1 - l))) & 7), n.bounds);
+        n.level = static_cast<int32_t>(S) - 1;
+        n.max_depth = root.max_depth;
+        n.max_spacing = static_cast<float>(root.max_spacing / std::pow(2, S));
+        n.morton_index = prefix << shift;
+        n.path_index = prefix;
+        n.path_levels = S;
+        std::vector<Item> node_items(items.begin() + lo, items.begin() + hi);
+        tile_node_cached(node_items, n, root);
+        lo = hi;
+      }
+    }
+    /* finalize: reconstruct_left_out_nodes over every start node that exists */
+    for (int32_t lv = static_cast<int32_t>(S) - 1; lv >= 0; --lv) {
+      std::vector<uint64_t> parents;
+      for (const auto& kv : store)
+        if (kv.first.first == S)
+          parents.push_back(kv.first.second >> (3 * (S - lv)));
+      std::sort(parents.begin(), parents.end());
+      parents.erase(std::unique(parents.begin(), parents.end()), parents.end());
+      for (uint64_t parent : parents) {
+        std::vector<uint32_t> child_ids;
+        for (uint8_t octant = 0; octant < 8; ++octant) {
+          const auto it = store.find({ static_cast<uint32_t>(lv + 1), (parent << 3) | octant });
+          if (it != store.end())
+            child_ids.insert(child_ids.end(), it->second.begin(), it->second.end());
+        }
+        std::vector<Item> items;
+        prims.index_ids(child_ids, items, rb);
+        const uint32_t shift = (MAX_OCTREE_LEVELS - lv) * 3;
+        const uint64_t node_key = (lv == 0) ? 0 : (parent << shift);
+        const size_t taken = prims.sample(items.data(), items.data() + items.size(), node_key, lv - 1, rb,
+                                          params.spacing_at_root, AlwaysAdhereToMinSpacing);
+        NodeStructure n{};
+        n.path_index = parent;
+        n.path_levels = static_cast<uint32_t>(lv);
+        store_node(items.data(), items.data() + taken, n, SW_NODE_RECONSTRUCTED);
+      }
+    }
+    emit_store();
   }
 
   void run()

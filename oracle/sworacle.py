@@ -313,8 +313,8 @@ class Oracle:
 
 
 def _tile_batches(self, params, xyz, batch_sizes, return_clamped=False):
-    """ACCURATE tiling of several batches (TilingAlgorithmV1 with cached points and a
-    lossless in-memory persistence).  `batch_sizes` splits xyz into consecutive batches; point ids are global."""
+    """tiling of several batches (TilingAlgorithmV1 / V3 with cached points and a lossless
+    in-memory persistence; FAST fixes its start level on the first batch and reconstructs at the end).  `batch_sizes` splits xyz into consecutive batches; point ids are global."""
     xyz = np.array(xyz, dtype=np.float64, order="C", copy=True).reshape(-1, 3)
     offsets = np.concatenate([[0], np.cumsum(np.asarray(batch_sizes, np.int64))]).astype(np.uint64)
     assert int(offsets[-1]) == len(xyz)
@@ -327,7 +327,7 @@ def _tile_batches(self, params, xyz, batch_sizes, return_clamped=False):
         nodes = np.empty(self._node_count(h), NODE_DTYPE)
         ids = np.empty(self._point_id_count(h), np.uint32)
         self._get_nodes(h, nodes.ctypes.data, ids.ctypes.data)
-        res = TileResult(nodes, ids)
+        res = TileResult(nodes, ids, start_level=int(self._start_level(h)))
     finally:
         self._destroy(h)
     return (res, xyz) if return_clamped else res

@@ -739,11 +739,15 @@ swo_tile_batches(const sw_params* params, double* xyz, uint64_t n, const uint64_
   h->params = *params;
   *out_handle = h;
   try {
-    if (params->tiling != SW_ACCURATE || n_batches == 0 || offsets[n_batches] != n)
-      throw OracleError(SW_ERR_INVALID_ARGUMENT, "tile_batches: ACCURATE only, offsets must end at n");
+    if (n_batches == 0 || offsets[n_batches] != n)
+      throw OracleError(SW_ERR_INVALID_ARGUMENT, "tile_batches: offsets must end at n");
     RestatedPrims prims{ xyz, n, params->sampling, params->max_points_per_node };
     Orchestrator<RestatedPrims> o(prims, *params, 1);
-    o.run_accurate_batches(offsets, n_batches);
+    if (params->tiling == SW_FAST)
+      o.run_fast_batches(offsets, n_batches);
+    else
+      o.run_accurate_batches(offsets, n_batches);
+    h->start_level = o.start_level;
     h->nodes = std::move(o.nodes);
     h->ids = std::move(o.ids);
     h->keys = std::move(o.sorted_keys);

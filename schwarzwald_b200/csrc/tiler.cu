@@ -885,11 +885,20 @@ swgpu_reserve(swgpu_handle h, uint64_t n)
   return ensure_batch_buffers(h, n);
 }
 
+// the indexing kernels move 16-byte vectors (two points = three double2, four LAS records = three int4)
+static bool
+aligned16(const void* p)
+{
+  return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
 int
 swgpu_index_batch_device(swgpu_handle h, double* xyz_device, uint64_t n)
 {
   if (!h || (!xyz_device && n))
     return SW_ERR_INVALID_ARGUMENT;
+  if (!aligned16(xyz_device))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "device positions must be 16-byte aligned");
   cudaSetDevice(h->device);
   h->d_las = nullptr;
   h->d_xyz = xyz_device;
@@ -946,6 +955,8 @@ swgpu_index_batch_las_device(swgpu_handle h, const int32_t* las_xyz_device, uint
 {
   if (!h || !t || (!las_xyz_device && n))
     return SW_ERR_INVALID_ARGUMENT;
+  if (!aligned16(las_xyz_device))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "device LAS records must be 16-byte aligned");
   cudaSetDevice(h->device);
   set_las_transform(h, t);
   CK(h->xyz_own.ensure(std::max<size_t>(n, 1) * 24));
@@ -1281,6 +1292,8 @@ swgpu_morton_encode_device(swgpu_handle h, double* xyz_device, uint64_t n, uint6
 {
   if (!h || (n && (!xyz_device || !keys_device)))
     return SW_ERR_INVALID_ARGUMENT;
+  if (!aligned16(xyz_device) || !aligned16(keys_device))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "device positions and keys must be 16-byte aligned");
   cudaSetDevice(h->device);
   CK(h->hist.ensure(sort_hist_words() * 4));
   CK(cudaMemsetAsync(h->hist.p, 0, sort_hist_words() * 4, h->stream));

@@ -180,3 +180,27 @@ def test_multi_batch_revisited_nodes_are_resampled(port_oracle):
     root = both.nodes[(both.nodes["levels"] == 0)]
     assert len(root) == 1 and int(root["count"][0]) < 6000 and len(both.nodes) > 1
     assert (np.bincount(both.ids, minlength=len(xyz)) == 1).all()
+
+
+@pytest.mark.parametrize("sampling", SAMPLINGS)
+def test_multi_batch_fast_port_equals_reference(port_oracle, ref_oracle, sampling):
+    """TilingAlgorithmV3 over several batches: start level from the first batch, later batches cut at it and
+    merged with the stored start nodes, reconstruction over every start node at the end."""
+    from oracle import sworacle
+    xyz, bmin, bmax, spacing = _batch_cloud()
+    p = sworacle.make_params(sampling, "FAST", spacing, bmin, bmax, max_points_per_node=800, concurrency=2)
+    sizes = [40_000, 30_000, 20_000]
+    a = port_oracle.tile_batches(p, xyz, sizes)
+    b = ref_oracle.tile_batches(p, xyz, sizes)
+    assert a.start_level == b.start_level >= 3
+    ta, ia = a.canonical()
+    tb, ib = b.canonical()
+    assert np.array_equal(ta, tb) and np.array_equal(ia, ib)
+    below = a.nodes["levels"] >= a.start_level  # reconstructed upper levels hold copies
+    ids = np.concatenate([a.ids[int(n["first"]): int(n["first"]) + int(n["count"])] for n in a.nodes[below]])
+    assert (np.bincount(ids, minlength=len(xyz)) == 1).all()
+    one = port_oracle.tile(p, xyz)
+    same = port_oracle.tile_batches(p, xyz, [len(xyz)])
+    t1, i1 = one.canonical()
+    t2, i2 = same.canonical()
+    assert np.array_equal(t1[:, :3], t2[:, :3]) and np.array_equal(i1, i2)
