@@ -204,3 +204,20 @@ def test_multi_batch_fast_port_equals_reference(port_oracle, ref_oracle, samplin
     t1, i1 = one.canonical()
     t2, i2 = same.canonical()
     assert np.array_equal(t1[:, :3], t2[:, :3]) and np.array_equal(i1, i2)
+
+
+def _batches_golden():
+    return json.load(open(os.path.join(HERE, "golden", "batches_golden.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", range(10))
+def test_multi_batch_port_equals_committed_reference_golden(port_oracle, case):
+    """Fixtures generated from oracle/_ref by tests/golden/make_golden_batches.py (available without the
+    reference tree)."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden_batches as mgb
+    g = _batches_golden()[case]
+    res = mgb.run(port_oracle, g["sampling"], g["tiling"])
+    assert (len(res.nodes), len(res.ids), res.start_level) == (g["nodes"], g["ids"], g["start_level"])
+    assert mgb.digest(res) == g["digest"], (g["sampling"], g["tiling"])
