@@ -79,3 +79,38 @@ def test_synthetic_generators_are_deterministic_and_chunk_invariant():
     x = synth.generate("skewed", 200_000, 5, side_m=100.0)
     inside = ((x[:, 0] >= 31.0) & (x[:, 0] < 31.0 + 21.54)).float().mean().item()
     assert inside > 0.94
+
+
+def test_header_is_plain_c_and_struct_sizes_match_the_bindings(tmp_path):
+    """include/swgpu.h must be consumable from C (the boundary is a C ABI) and the ctypes / numpy mirrors must
+    have the sizes the C compiler gives the structs."""
+    import subprocess
+    from oracle import sworacle
+    from schwarzwald_b200 import native, tiler
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "swgpu.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(sw_params), sizeof(sw_node), sizeof(sw_las_transform),\n'
+        '                        sizeof(sw_las_node_header), sizeof(swgpu_stats)); return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(native.SwParams), tiler.NODE_DTYPE.itemsize, ctypes.sizeof(native.SwLasTransform),
+                     tiler.LAS_HEADER_DTYPE.itemsize, ctypes.sizeof(native.SwgpuStats)]
+    assert ctypes.sizeof(sworacle.SwLasTransform) == sizes[2] and sworacle.LAS_HEADER_DTYPE.itemsize == sizes[3]
+
+
+def test_cpp_host_layer_compiles_against_the_header(tmp_path):
+    """schwarzwald_b200/host/swgpu_tiler.hpp (the RAII layer the reference-side adapter builds on) instantiated
+    with every method, syntax and types only."""
+    import subprocess
+    src = tmp_path / "host.cpp"
+    src.write_text(
+        '#include "swgpu_tiler.hpp"\n'
+        'void use(swgpu::Tiler& t, double* xyz, const int32_t* las, const sw_las_transform& tr) {\n'
+        '  t.index_batch(xyz, 3); t.index_batch_las(las, 3, tr); t.positions(xyz); t.finalize();\n'
+        '  auto r = t.result(); auto p = t.payload_pnts(); auto l = t.payload_las(); (void)t.start_level();\n'
+        '  (void)r; (void)p; (void)l; (void)swgpu::node_name(5, 1); (void)swgpu::sampling_from_name("JITTERED"); }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
+                    "-I", os.path.join(ROOT, "schwarzwald_b200", "host"), str(src)], check=True)
