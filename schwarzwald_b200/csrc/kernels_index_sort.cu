@@ -691,11 +691,15 @@ launch_onesweep_pass(const u64* kin, const u32* vin, u64* kout, u32* vout, u32 n
                      u32* ticket, u32 tiles, cudaStream_t stream)
 {
   auto kernel = onesweep_pass_kernel<PASS, PASS == 0>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: one flag per device ordinal (a process may drive several GPUs)
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES);
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_set = true;
+    if (dev >= 0 && dev < 64)
+      attr_set[dev] = true;
   }
   kernel<<<tiles, RS_THREADS, RS_SMEM_BYTES, stream>>>(kin, vin, kout, vout, n, digit_base, status, ticket);
 }

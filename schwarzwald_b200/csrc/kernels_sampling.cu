@@ -1812,7 +1812,14 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
                                                  counters);
 
   // persistent dataflow kernel: every resident group pops ready cells until all analysed cells are done
-  static int warp_blocks = 0, cta256_blocks = 0, cta1024_blocks = 0;
+  // co-resident group counts and the dynamic shared-memory opt-in are per device
+  static int warp_blocks_of[64] = {}, cta256_blocks_of[64] = {}, cta1024_blocks_of[64] = {};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  const int slot = (cur_dev >= 0 && cur_dev < 64) ? cur_dev : 0;
+  int& warp_blocks = warp_blocks_of[slot];
+  int& cta256_blocks = cta256_blocks_of[slot];
+  int& cta1024_blocks = cta1024_blocks_of[slot];
   if (!warp_blocks) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
