@@ -214,3 +214,32 @@ def test_gpu_payload_device_variants_equal_host_variants(sampling):
         torch.cuda.synchronize()
     assert np.array_equal(d_pnts.cpu().numpy().view(np.uint32), pnts.view(np.uint32))
     assert np.array_equal(d_las.cpu().numpy(), las) and d_headers.tobytes() == headers.tobytes()
+
+
+def test_las_payload_round_trip_matches_the_reference_test(port_oracle):
+    """Port of the expectation in the reference's test/TestLASPersistence.cpp:42-55,68-129: 4096 random points in
+    the unit cube, stored per root octant through LASPersistence and read back (offset + X * scale), come back
+    changed but by less than 0.001."""
+    from oracle import sworacle
+    rng = np.random.default_rng(0)
+    xyz = rng.random((4096, 3))
+    bounds = (np.zeros(3), np.ones(3))
+    keys, _ = port_oracle.index_points(xyz, bounds)
+    order = np.argsort(keys, kind="stable")
+    octant = (keys[order] >> np.uint64(60)).astype(np.int64)
+    nodes = np.zeros(8, sworacle.NODE_DTYPE)
+    for o in range(8):
+        sel = np.nonzero(octant == o)[0]
+        # the reference test hands every octant's points to persist_points with the ROOT bounds
+        # (get_bounds_from_morton_index(..., depth 0)): rows with zero levels
+        nodes[o] = (0, 0, 0, sel[0] if len(sel) else 0, len(sel))
+    las, headers = port_oracle.payload_las(xyz, order.astype(np.uint32), nodes, bounds)
+    worst, changed = 0.0, False
+    for o in range(8):
+        first, count = int(nodes["first"][o]), int(nodes["count"][o])
+        back = headers["offset"][o] + las[first:first + count] * headers["scale"][o]
+        src = xyz[order[first:first + count]]
+        changed |= bool((back != src).any())
+        worst = max(worst, float(np.sqrt(((back - src) ** 2).sum(axis=1)).max()))
+        assert headers["scale"][o] == 0.001  # diagonal sqrt(3) > 1
+    assert changed and worst < 0.001
