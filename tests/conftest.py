@@ -12,6 +12,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built artefacts (they are git-ignored): build the CUDA library once (nvcc
+    cross-compiles without a GPU).  The oracle libraries are built on demand by oracle/sworacle.py."""
+    import shutil
+    import subprocess
+    lib = os.path.join(ROOT, "schwarzwald_b200", "libswgpu.so")
+    if not os.path.exists(lib) and not os.environ.get("SWGPU_LIB") and shutil.which("nvcc"):
+        subprocess.run(["bash", os.path.join(ROOT, "build_native.sh")], check=True)
+
+
 @pytest.fixture(scope="session")
 def port_oracle():
     from oracle import sworacle
