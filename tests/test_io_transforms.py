@@ -243,3 +243,24 @@ def test_las_payload_round_trip_matches_the_reference_test(port_oracle):
         worst = max(worst, float(np.sqrt(((back - src) ** 2).sum(axis=1)).max()))
         assert headers["scale"][o] == 0.001  # diagonal sqrt(3) > 1
     assert changed and worst < 0.001
+
+
+def test_las_positions_match_plain_ieee_arithmetic(port_oracle):
+    """Independent of both C++ builds: offset + X * scale (two roundings), clamp, subtract the centre, round to
+    float32 — spelled out in numpy float64 / float32."""
+    from oracle import sworacle
+    rng = np.random.default_rng(21)
+    las = rng.integers(-2**31, 2**31 - 1, size=(30_000, 3), dtype=np.int64).astype(np.int32)
+    las[::3] = rng.integers(0, 4_000_000, size=(10_000, 3))
+    scale = np.array([0.001, 0.0125, 1e-4])
+    offset = np.array([389000.5, 5705000.25, -3.0])
+    hmin = np.array([389000.0, 5705000.0, -10.0])
+    hmax = np.array([393000.75, 5745000.5, 380.0])
+    center = np.array([391000.375, 5725000.25, 185.0])
+    for shift in (False, True):
+        t = sworacle.make_las_transform(scale, offset, hmin, hmax, center if shift else None)
+        p = offset + las.astype(np.float64) * scale
+        p = np.minimum(hmax, np.maximum(hmin, p))
+        if shift:
+            p = (p - center).astype(np.float32).astype(np.float64)
+        assert np.array_equal(port_oracle.las_positions(las, t), p)
