@@ -50,7 +50,8 @@ typedef struct sw_params {
   float spacing_at_root;        /* TilerMetaParameters::spacing_at_root (float!) */
   uint32_t max_depth;           /* TilerMetaParameters::max_depth; CLI effectively uses 100 */
   uint64_t max_points_per_node; /* default 20000 */
-  double bounds_min[3];         /* cubic dataset bounds (AABB::makeCubic, math/AABB.h:50-61) */
+  double bounds_min[3];         /* cubic dataset bounds (AABB::makeCubic, math/AABB.h:50-61); the tiling entry
+                                 * points refuse boxes whose extents differ (SW_ERR_INVALID_ARGUMENT) */
   double bounds_max[3];
   uint32_t concurrency;         /* FAST: num_indexing_threads of the reference run being matched */
   uint32_t reserved;

@@ -188,9 +188,11 @@ int swgpu_partition_to_peers_device(swgpu_handle h, const uint64_t* keys_device,
 int swgpu_set_shard(swgpu_handle h, uint32_t shard_levels, int32_t start_level, swgpu_allreduce_u32_fn allreduce,
                     void* allreduce_ctx, const uint32_t* global_ids_device);
 
-/* Algorithmic bytes moved by the last index_batch + finalize according to the accounting model
- * of DESIGN.md (used by bench.py for the roofline line), and the per-stage device times in ms
- * when timing was enabled with swgpu_enable_timing (cudaEvents on the handle's stream). */
+/* Algorithmic bytes of the last index_batch + finalize by the accounting model of SURVEY.md section 8(d)
+ * (bytes_index/sort/gather/sample; used by bench.py for the roofline line), the bytes this implementation
+ * actually reads and writes by its own traffic model (bytes_traffic: e.g. the two-pass compaction reads
+ * the keys twice), and the per-stage device times in ms when timing was enabled with swgpu_enable_timing
+ * (cudaEvents on the handle's stream). */
 typedef struct swgpu_stats {
   uint64_t n_points;
   uint64_t n_output_ids;
@@ -209,6 +211,7 @@ typedef struct swgpu_stats {
   float ms_total;
   uint32_t kernel_launches;
   uint32_t min_distance_rounds;
+  uint64_t bytes_traffic;
 } swgpu_stats;
 int swgpu_enable_timing(swgpu_handle h, int enable);
 int swgpu_get_stats(swgpu_handle h, swgpu_stats* out);

@@ -110,6 +110,10 @@ struct Orchestrator
   std::vector<uint32_t> sorted_ids;  /* test hook: sort permutation */
   uint64_t duplicate_keys = 0;
   int32_t start_level = -1; /* FAST: level_of_start_nodes */
+  /* >= 0: FAST uses this start level instead of estimating it from the batch.  Checker hook for subtree parity
+   * (bench.py, tests/test_gpu_fullsize.py): the points of a few level-3 subtrees of a large cloud are tiled
+   * with the start level the WHOLE cloud produced, so that the nodes inside those subtrees are comparable. */
+  int32_t start_level_override = -1;
   std::map<std::pair<uint32_t, uint64_t>, size_t> node_lookup;
 
   /* The reference runs the per-node work as taskflow tasks on its worker threads (one task per start node
@@ -391,7 +395,8 @@ struct Orchestrator
     if (items.size() < params.concurrency)
       throw OracleError(SW_ERR_TOO_FEW_POINTS, "fewer points than indexing threads");
     sort_items(items);
-    const uint32_t S = estimate_start_level(items, params.concurrency);
+    const uint32_t S = start_level_override >= 0 ? static_cast<uint32_t>(start_level_override)
+                                                 : estimate_start_level(items, params.concurrency);
     start_level = static_cast<int32_t>(S);
     const NodeStructure root = make_root();
 

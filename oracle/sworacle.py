@@ -161,10 +161,13 @@ class Oracle:
           [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32,
            C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p])
         f("tile", C.c_int, [C.POINTER(SwParams), C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)])
+        f("tile_repeat", C.c_int, [C.POINTER(SwParams), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p,
+                                   C.POINTER(C.c_void_p)])
         f("tile_batches", C.c_int, [C.POINTER(SwParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
                                     C.POINTER(C.c_void_p)])
         f("set_threads", None, [C.c_uint32])
         f("set_reference_sort", None, [C.c_int32])
+        f("set_start_level_override", None, [C.c_int32])
         f("tile_seconds", C.c_double, [C.c_void_p])
         f("node_count", C.c_uint64, [C.c_void_p])
         f("point_id_count", C.c_uint64, [C.c_void_p])
@@ -285,11 +288,25 @@ class Oracle:
         std::stable_sort that pins the tie order for the parity runs."""
         self._set_reference_sort(1 if on else 0)
 
+    def set_start_level_override(self, level=-1):
+        """FAST: tile with this start level instead of estimating it from the batch (-1 = estimate).  Used by the
+        subtree parity checks, which tile a few level-3 subtrees of a large cloud with the whole cloud's level."""
+        self._set_start_level_override(int(level))
+
     # --- whole batch --------------------------------------------------------------------------
-    def tile(self, params: SwParams, xyz, return_clamped=False):
-        xyz = np.array(xyz, dtype=np.float64, order="C", copy=True).reshape(-1, 3)
+    def tile(self, params: SwParams, xyz, return_clamped=False, passes=1, copy=True, want_keys=True):
+        """One batch through the whole path.  passes > 1 repeats the run over the same point buffer (timing runs:
+        res.pass_seconds holds the time of every pass, the result is the last one's); copy=False lets the oracle
+        clamp `xyz` in place instead of working on a copy (saves 24 B per point of host memory)."""
+        if copy:
+            xyz = np.array(xyz, dtype=np.float64, order="C", copy=True).reshape(-1, 3)
+        else:
+            assert xyz.dtype == np.float64 and xyz.flags["C_CONTIGUOUS"]
+            xyz = xyz.reshape(-1, 3)
         h = C.c_void_p()
-        rc = self._tile(C.byref(params), xyz.ctypes.data, len(xyz), C.byref(h))
+        seconds = np.zeros(max(1, int(passes)), np.float64)
+        rc = self._tile_repeat(C.byref(params), xyz.ctypes.data, len(xyz), int(passes), seconds.ctypes.data,
+                               C.byref(h))
         try:
             if rc != 0:
                 err = self._last_error(h).decode()
@@ -298,13 +315,16 @@ class Oracle:
             ni = self._point_id_count(h)
             nodes = np.empty(nn, NODE_DTYPE)
             ids = np.empty(ni, np.uint32)
-            keys = np.empty(len(xyz), np.uint64)
-            order = np.empty(len(xyz), np.uint32)
+            keys = order = None
             self._get_nodes(h, nodes.ctypes.data, ids.ctypes.data)
-            self._get_keys(h, keys.ctypes.data, order.ctypes.data)
+            if want_keys:
+                keys = np.empty(len(xyz), np.uint64)
+                order = np.empty(len(xyz), np.uint32)
+                self._get_keys(h, keys.ctypes.data, order.ctypes.data)
             res = TileResult(nodes, ids, keys, order, int(self._start_level(h)),
                              int(self._duplicate_keys(h)))
             res.seconds = float(self._tile_seconds(h))  # index + sort + tiling inside the library
+            res.pass_seconds = seconds
         finally:
             self._destroy(h)
         if return_clamped:

@@ -695,25 +695,42 @@ swo_set_reference_sort(int32_t on)
   g_reference_sort = on;
 }
 
+/* >= 0: FAST tiles with this start level instead of estimating it (subtree parity checks), -1 = estimate */
+static int32_t g_start_level_override = -1;
+
+void
+swo_set_start_level_override(int32_t level)
+{
+  g_start_level_override = level;
+}
+
+/* `passes` runs of the whole path over the same points; seconds_out[k] = time of pass k, the handle holds the
+ * result of the last pass (see swr_tile_repeat in ref_driver.cpp) */
 int
-swo_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
+swo_tile_repeat(const sw_params* params, double* xyz, uint64_t n, uint32_t passes, double* seconds_out,
+                void** out_handle)
 {
   auto* h = new Handle();
   h->params = *params;
   *out_handle = h;
   try {
     RestatedPrims prims{ xyz, n, params->sampling, params->max_points_per_node };
-    Orchestrator<RestatedPrims> o(prims, *params, g_threads);
-    o.reference_sort = g_reference_sort != 0;
-    const auto t0 = std::chrono::steady_clock::now();
-    o.run();
-    h->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    h->nodes = std::move(o.nodes);
-    h->ids = std::move(o.ids);
-    h->keys = std::move(o.sorted_keys);
-    h->order = std::move(o.sorted_ids);
-    h->duplicate_keys = o.duplicate_keys;
-    h->start_level = o.start_level;
+    for (uint32_t k = 0; k < (passes ? passes : 1u); ++k) {
+      Orchestrator<RestatedPrims> o(prims, *params, g_threads);
+      o.reference_sort = g_reference_sort != 0;
+      o.start_level_override = g_start_level_override;
+      const auto t0 = std::chrono::steady_clock::now();
+      o.run();
+      h->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (seconds_out)
+        seconds_out[k] = h->seconds;
+      h->nodes = std::move(o.nodes);
+      h->ids = std::move(o.ids);
+      h->keys = std::move(o.sorted_keys);
+      h->order = std::move(o.sorted_ids);
+      h->duplicate_keys = o.duplicate_keys;
+      h->start_level = o.start_level;
+    }
     return SW_OK;
   } catch (const OracleError& e) {
     h->error = e.what();
@@ -722,6 +739,12 @@ swo_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
     h->error = e.what();
     return SW_ERR_STATE;
   }
+}
+
+int
+swo_tile(const sw_params* params, double* xyz, uint64_t n, void** out_handle)
+{
+  return swo_tile_repeat(params, xyz, n, 1, nullptr, out_handle);
 }
 
 double

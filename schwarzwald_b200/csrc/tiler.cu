@@ -43,9 +43,12 @@ struct DevBuf
       return e;
     if (p && keep_bytes) {
       e = cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, stream);
-      if (e != cudaSuccess)
+      if (e == cudaSuccess)
+        e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess) {
+        cudaFree(np);
         return e;
-      cudaStreamSynchronize(stream);
+      }
     }
     if (p)
       cudaFree(p);
@@ -356,7 +359,7 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
     launch_node_rle(in_key, count, node_shift, h->node_start.as<u32>(), h->tile_rank0.as<u32>(), h->d_n_nodes(),
                     h->scan_status.as<u64>(), h->d_tickets(), s);
     h->stats.kernel_launches += 1;
-    h->stats.bytes_sample += 8 * count;
+    h->stats.bytes_traffic += 8 * count;
     rc = sync_scalars(h);
     if (rc)
       return rc;
@@ -374,6 +377,7 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
     node_gcount = h->node_gcount.as<u32>();
   }
 
+  bool reads_positions = false; // does this level's selection read the 24-byte positions
   SwLevelArgs a{};
   a.in_key = in_key;
   a.in_idx = in_idx;
@@ -436,7 +440,8 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
         g.nodes = h->argmin_nodes.as<SwArgminNode>();
         launch_select_argmin(g, h->scan_status.as<u64>(), h->d_tickets(), s);
         h->stats.kernel_launches += 2;
-        h->stats.bytes_sample += (8 + 4 + 24 + 1 + 1) * count;
+        h->stats.bytes_traffic += (8 + 4 + 24 + 1 + 1) * count;
+        reads_positions = true;
         a.sel = h->sel.as<unsigned char>();
         break;
       }
@@ -484,7 +489,8 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
           return fail_cuda(h, e, "run_min_distance");
         h->stats.min_distance_rounds += rounds;
         h->stats.kernel_launches += launches;
-        h->stats.bytes_sample += bytes;
+        h->stats.bytes_traffic += bytes;
+        reads_positions = true;
         a.sel = static_cast<const unsigned char*>(h->md.state.p);
         break;
       }
@@ -526,8 +532,11 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
                   ? "Grids smaller than 16x16 are not supported currently!"
                   : "Node is too small to be sampled with ImprovedPoissonSampling!");
   const u64 n_sel = h->h_scalars->n_selected;
-  // count pass: keys; scatter pass: keys + ids in, (key, id) out
-  h->stats.bytes_sample += (16 + (in_idx ? 4 : 0)) * count + 12 * n_sel + (rem_key ? 12 * (count - n_sel) : 0);
+  // algorithmic bytes of the level by SURVEY 8(d): read key + id (+ position), write the compacted remainder,
+  // write the selected ids
+  h->stats.bytes_sample += (12 + (reads_positions ? 24 : 0)) * count + (rem_key ? 12 * (count - n_sel) : 0) + 4 * n_sel;
+  // what this design really moves: count pass reads the keys, scatter pass reads keys + ids, writes (key, id)
+  h->stats.bytes_traffic += (16 + (in_idx ? 4 : 0)) * count + 12 * n_sel + (rem_key ? 12 * (count - n_sel) : 0);
   if (n_nodes_next_out)
     *n_nodes_next_out = want_children ? h->h_scalars->n_nodes_next : 0u;
   if (want_children) // the next level reads its node boundaries from node_start
@@ -625,11 +634,25 @@ run_batch(swgpu_tiler* h)
   h->start_level = -1;
   h->batch_done = false;
   h->finalized = false;
+  h->n_clamped = 0;
+  h->h_scalars->n_clamped = 0; // an empty shard never refreshes the pinned copy
   std::memset(&h->stats, 0, sizeof(h->stats));
   h->stats.n_points = n;
 
   if (n >= (1ull << 30))
     return fail(h, SW_ERR_INVALID_ARGUMENT, "a batch is limited to 2^30 - 1 points per GPU");
+  // The level tables, the MIN_DISTANCE cell size and the jitter grid are derived from the x extent, as in the
+  // reference, which always tiles against AABB::makeCubic bounds (process/Tiler.cpp:185-187).  Non-cubic bounds
+  // would silently break the 27-neighbour search, so tiling refuses them (extents may differ by rounding only);
+  // the stand-alone indexing / sort primitives accept any box, like index_point.
+  {
+    const double ex = h->prm.bounds_max[0] - h->prm.bounds_min[0];
+    for (int a = 1; a < 3; ++a) {
+      const double e = h->prm.bounds_max[a] - h->prm.bounds_min[a];
+      if (std::fabs(e - ex) > 1e-9 * std::fabs(ex))
+        return fail(h, SW_ERR_INVALID_ARGUMENT, "tiling needs cubic bounds (AABB::makeCubic)");
+    }
+  }
   const bool sharded = h->shard_levels > 0; // the caller checked the GLOBAL point count
   if (!sharded && h->prm.tiling == SW_FAST && n < h->prm.concurrency)
     return fail(h, SW_ERR_TOO_FEW_POINTS, "Can't scatter a range that has less than 'scatter_factor' elements!");
@@ -647,10 +670,12 @@ run_batch(swgpu_tiler* h)
   if (h->d_las) { // K1-LAS: 12 B record in, 24 B position + 8 B key out
     launch_las_encode(h->d_las, n, h->las_t, h->bounds, h->d_xyz, unsorted_keys, h->hist.as<u32>(),
                       h->d_n_clamped(), s);
-    h->stats.bytes_index = 44 * n;
+    h->stats.bytes_index = 48 * n; // 12 B record + 24 B position + 8 B key + 4 B id
+    h->stats.bytes_traffic += 44 * n; // the ids are generated by the first sort pass, never written here
   } else {
     launch_morton_encode(h->d_xyz, n, h->bounds, unsorted_keys, h->hist.as<u32>(), h->d_n_clamped(), s);
-    h->stats.bytes_index = 32 * n;
+    h->stats.bytes_index = 36 * n; // 24 B position + 8 B key + 4 B id
+    h->stats.bytes_traffic += 32 * n;
   }
   h->stats.kernel_launches += 1;
   record(h, 1);
@@ -658,13 +683,15 @@ run_batch(swgpu_tiler* h)
   launch_radix_sort(h->keys[0].as<u64>(), h->keys[1].as<u64>(), h->vals[0].as<u32>(), h->vals[1].as<u32>(), n,
                     h->hist.as<u32>(), h->sort_status.as<u32>(), h->d_tickets() + 8, s);
   h->stats.kernel_launches += 1 + sort_passes();
-  h->stats.bytes_sort = ((u64)sort_passes() * 24 - 4) * n;
+  h->stats.bytes_sort = (8 + (u64)sort_passes() * 24) * n; // histogram read + passes x 2 x 12 B
+  h->stats.bytes_traffic += ((u64)sort_passes() * 24 - 4) * n; // histograms come from K1, pass 0 reads no ids
   record(h, 2);
   // K4
   if (needs_positions(h->prm.sampling)) {
     launch_gather_positions(h->d_xyz, h->vals[0].as<u32>(), n, h->pos_sorted.as<double>(), s);
     h->stats.kernel_launches += 1;
-    h->stats.bytes_gather = (4 + 24 + 24) * n;
+    h->stats.bytes_gather = 2 * 24 * n; // SURVEY 8(d) K4 without attribute bytes
+    h->stats.bytes_traffic += (4 + 24 + 24) * n;
   }
   record(h, 3);
   CK(cudaGetLastError());
@@ -1435,8 +1462,8 @@ swgpu_partition_device(swgpu_handle h, const uint64_t* keys_device, const double
   if (!h || !first_prefix || !send_counts_host || n_ranks == 0 || n_ranks > SWGPU_MAX_RANKS ||
       (n && (!keys_device || !xyz_device || !out_xyz_device || !out_id_device)))
     return SW_ERR_INVALID_ARGUMENT;
-  if (n >= (1ull << 32))
-    return fail(h, SW_ERR_INVALID_ARGUMENT, "a partition is limited to 2^32 - 1 points per GPU");
+  if (n >= (1ull << 32) || (u64)id_base + n > (1ull << 32))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "global point ids are 32 bit: id_base + n must not exceed 2^32");
   cudaSetDevice(h->device);
   CK(h->part_tile_counts.ensure(partition_tiles(n) * SW_MAX_RANKS * 4));
   CK(h->part_send_counts.ensure(SW_MAX_RANKS * 8));
@@ -1461,8 +1488,8 @@ swgpu_partition_to_peers_device(swgpu_handle h, const uint64_t* keys_device, con
   if (!h || !first_prefix || !peer_xyz_device || !peer_ids_device || !dst_offsets || n_ranks == 0 ||
       n_ranks > SWGPU_MAX_RANKS || (n && (!keys_device || !xyz_device)))
     return SW_ERR_INVALID_ARGUMENT;
-  if (n >= (1ull << 32))
-    return fail(h, SW_ERR_INVALID_ARGUMENT, "a partition is limited to 2^32 - 1 points per GPU");
+  if (n >= (1ull << 32) || (u64)id_base + n > (1ull << 32))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "global point ids are 32 bit: id_base + n must not exceed 2^32");
   cudaSetDevice(h->device);
   CK(h->part_tile_counts.ensure(partition_tiles(n) * SW_MAX_RANKS * 4));
   CK(h->part_send_counts.ensure(SW_MAX_RANKS * 8));

@@ -410,6 +410,7 @@ class ShardedTiler:
                     phases[name] = e0.elapsed_time(e1)
             self.last = {"phase_ms": phases, "n_local": n, "n_shard": m, "n_global": n_global,
                          "start_level": t.start_level(), "first_prefix": first_prefix, "send_counts": sc, "recv_counts": rc,
+                         "shard_levels": shard_levels,
                          "exchange": "peer kernel (swgpu_partition_to_peers_device over symmetric memory)",
                          "bytes_sent_off_gpu": int(sum(c for r, c in enumerate(sc) if r != comm.rank)) * 28}
             return n
@@ -442,7 +443,7 @@ class ShardedTiler:
             for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
                 phases[name] = e0.elapsed_time(e1)
         self.last = {"phase_ms": phases, "n_local": n, "n_shard": m, "n_global": n_global, "start_level": t.start_level(),
-                     "first_prefix": first_prefix, "send_counts": sc, "recv_counts": recv_counts,
+                     "shard_levels": shard_levels, "first_prefix": first_prefix, "send_counts": sc, "recv_counts": recv_counts,
                      "exchange": "nccl all_to_all" + (" (peer mapping unavailable: %s)" % self._peer_failed
                                                       if self._peer_failed else ""),
                      "bytes_sent_off_gpu": int(sum(c for r, c in enumerate(sc) if r != comm.rank)) * 28}
@@ -458,6 +459,9 @@ class ShardedTiler:
 
     def result_size(self):
         return self.tiler.result_size()
+
+    def result_device_ids(self, ids_device_ptr):
+        return self.tiler.result_device_ids(ids_device_ptr)
 
     def stats(self):
         return self.tiler.stats()

@@ -57,6 +57,7 @@ class SwgpuStats(C.Structure):
         ("ms_total", C.c_float),
         ("kernel_launches", C.c_uint32),
         ("min_distance_rounds", C.c_uint32),
+        ("bytes_traffic", C.c_uint64),
     ]
 
 
