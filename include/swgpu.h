@@ -58,6 +58,20 @@ int swgpu_index_batch_device(swgpu_handle h, double* xyz_device, uint64_t n);
  * children (reconstruct_left_out_nodes, TilingAlgorithms.cpp:1717-1784); no-op for ACCURATE. */
 int swgpu_finalize(swgpu_handle h);
 
+/* Multi-batch mode (the reference's default: internal_cache_size = 10 M points per batch,
+ * executable/main.cpp:233-236).  After swgpu_set_multi_batch(h, 1) every swgpu_index_batch* call is one
+ * build_execution_graph of TilingAlgorithmV1 / V3 against what the earlier batches stored: a node that is
+ * reached again gets its stored points back, re-keyed relative to the node bounds (read_pnts_from_disk,
+ * TilingAlgorithms.cpp:50-109), merged with the incoming ones (incoming first on equal keys, tiling/Node.cpp:3-34)
+ * and is sampled again with AlwaysAdhereToMinSpacing (:272-275); FAST fixes its start level on the first batch
+ * (:1250-1360), cuts later batches at it (:1362-1453) and reconstructs the upper levels in swgpu_finalize from
+ * everything stored (:1717-1784).  The store (all positions, clamped, and the node tables) lives in device
+ * memory; point ids are global: the i-th point of a batch has id (points of all earlier batches) + i, all
+ * batches together must stay below 2^32 points.  swgpu_result_size / swgpu_get_nodes* then return the final
+ * content of every node, ordered by (levels, index).  Switching the mode (on or off) empties the store.
+ * Not combinable with swgpu_set_shard. */
+int swgpu_set_multi_batch(swgpu_handle h, int enable);
+
 /* The hand-off that replaces the per-node persist_points() calls (io/PointsPersistence.h:23-31):
  * a node table plus one node-major array of ORIGINAL point indices, Morton-ordered inside each
  * node.  The adapter turns row i into persist_points(refs[first..first+count), bounds, name). */

@@ -157,3 +157,71 @@ shift_for_levels(int levels)
 
 // bit 63 of a working key is never part of a MortonIndex64 (63 bits)
 #define SW_KEY_MASK 0x7FFFFFFFFFFFFFFFull
+
+// calculate_morton_index<21> (tiling/OctreeAlgorithms.h:64-87) against any box `b` (min + scale = 2^21 / extent)
+__device__ __forceinline__ u64
+morton_from_position(double x, double y, double z, const SwBounds& b)
+{
+  // (p - min) * scale: subtract then multiply, two roundings (no FMA), then truncate toward zero
+  // and cap at 2^21 - 1 (OctreeAlgorithms.h:71-79).
+  const double nx = (x - b.min[0]) * b.scale[0];
+  const double ny = (y - b.min[1]) * b.scale[1];
+  const double nz = (z - b.min[2]) * b.scale[2];
+  const u64 cap = (1u << 21) - 1;
+  u64 bx = __double2ull_rz(nx);
+  u64 by = __double2ull_rz(ny);
+  u64 bz = __double2ull_rz(nz);
+  bx = bx < cap ? bx : cap;
+  by = by < cap ? by : cap;
+  bz = bz < cap ? bz : cap;
+  return expand_bits_by_3(bz) | (expand_bits_by_3(by) << 1) | (expand_bits_by_3(bx) << 2);
+}
+
+// get_octant_bounds recurrence, tiling/OctreeAlgorithms.cpp:3-18, applied `depth` times from the
+// root (get_bounds_from_morton_index, OctreeAlgorithms.h:104-116).  ext/2 is exact.
+__device__ __forceinline__ void
+bounds_from_key(u64 key, int depth, const SwBounds& b, double mn[3], double mx[3])
+{
+  mn[0] = b.min[0];
+  mn[1] = b.min[1];
+  mn[2] = b.min[2];
+  mx[0] = b.max[0];
+  mx[1] = b.max[1];
+  mx[2] = b.max[2];
+  for (int level = 0; level < depth; ++level) {
+    const u32 oct = (u32)(key >> (3 * (20 - level))) & 7u;
+    const double hx = (mx[0] - mn[0]) * 0.5;
+    const double hy = (mx[1] - mn[1]) * 0.5;
+    const double hz = (mx[2] - mn[2]) * 0.5;
+    if (oct & 4u)
+      mn[0] = mn[0] + hx;
+    if (oct & 2u)
+      mn[1] = mn[1] + hy;
+    if (oct & 1u)
+      mn[2] = mn[2] + hz;
+    mx[0] = mn[0] + hx;
+    mx[1] = mn[1] + hy;
+    mx[2] = mn[2] + hz;
+  }
+}
+
+// the same recurrence continued from bounds that already hold `from_depth` levels
+__device__ __forceinline__ void
+bounds_continue(u64 key, int from_depth, int depth, double mn[3], double mx[3])
+{
+  for (int level = from_depth; level < depth; ++level) {
+    const u32 oct = (u32)(key >> (3 * (20 - level))) & 7u;
+    const double hx = (mx[0] - mn[0]) * 0.5;
+    const double hy = (mx[1] - mn[1]) * 0.5;
+    const double hz = (mx[2] - mn[2]) * 0.5;
+    if (oct & 4u)
+      mn[0] = mn[0] + hx;
+    if (oct & 2u)
+      mn[1] = mn[1] + hy;
+    if (oct & 1u)
+      mn[2] = mn[2] + hz;
+    mx[0] = mn[0] + hx;
+    mx[1] = mn[1] + hy;
+    mx[2] = mn[2] + hz;
+  }
+}

@@ -28,24 +28,6 @@
 #define RS_PASSES ((63 + RS_BITS - 1) / RS_BITS)
 #define RS_DIGIT_MASK ((u32)(RS_RADIX - 1))
 
-__device__ __forceinline__ u64
-morton_from_position(double x, double y, double z, const SwBounds& b)
-{
-  // (p - min) * scale: subtract then multiply, two roundings (no FMA), then truncate toward zero
-  // and cap at 2^21 - 1 (OctreeAlgorithms.h:71-79).
-  const double nx = (x - b.min[0]) * b.scale[0];
-  const double ny = (y - b.min[1]) * b.scale[1];
-  const double nz = (z - b.min[2]) * b.scale[2];
-  const u64 cap = (1u << 21) - 1;
-  u64 bx = __double2ull_rz(nx);
-  u64 by = __double2ull_rz(ny);
-  u64 bz = __double2ull_rz(nz);
-  bx = bx < cap ? bx : cap;
-  by = by < cap ? by : cap;
-  bz = bz < cap ? bz : cap;
-  return expand_bits_by_3(bz) | (expand_bits_by_3(by) << 1) | (expand_bits_by_3(bx) << 2);
-}
-
 // std::min(bmax, std::max(bmin, p)) with the exact comparison order of libstdc++
 __device__ __forceinline__ double
 clamp_like_reference(double p, double bmin, double bmax)

@@ -726,55 +726,6 @@ argmin_op(const ArgminVal& earlier, const ArgminVal& later)
   return (later.d < earlier.d) ? later : earlier; // strict: ties keep the earlier point
 }
 
-// get_octant_bounds recurrence, tiling/OctreeAlgorithms.cpp:3-18, applied `depth` times from the
-// root (get_bounds_from_morton_index, OctreeAlgorithms.h:104-116).  ext/2 is exact.
-__device__ __forceinline__ void
-bounds_from_key(u64 key, int depth, const SwBounds& b, double mn[3], double mx[3])
-{
-  mn[0] = b.min[0];
-  mn[1] = b.min[1];
-  mn[2] = b.min[2];
-  mx[0] = b.max[0];
-  mx[1] = b.max[1];
-  mx[2] = b.max[2];
-  for (int level = 0; level < depth; ++level) {
-    const u32 oct = (u32)(key >> (3 * (20 - level))) & 7u;
-    const double hx = (mx[0] - mn[0]) * 0.5;
-    const double hy = (mx[1] - mn[1]) * 0.5;
-    const double hz = (mx[2] - mn[2]) * 0.5;
-    if (oct & 4u)
-      mn[0] = mn[0] + hx;
-    if (oct & 2u)
-      mn[1] = mn[1] + hy;
-    if (oct & 1u)
-      mn[2] = mn[2] + hz;
-    mx[0] = mn[0] + hx;
-    mx[1] = mn[1] + hy;
-    mx[2] = mn[2] + hz;
-  }
-}
-
-// the same recurrence continued from bounds that already hold `from_depth` levels
-__device__ __forceinline__ void
-bounds_continue(u64 key, int from_depth, int depth, double mn[3], double mx[3])
-{
-  for (int level = from_depth; level < depth; ++level) {
-    const u32 oct = (u32)(key >> (3 * (20 - level))) & 7u;
-    const double hx = (mx[0] - mn[0]) * 0.5;
-    const double hy = (mx[1] - mn[1]) * 0.5;
-    const double hz = (mx[2] - mn[2]) * 0.5;
-    if (oct & 4u)
-      mn[0] = mn[0] + hx;
-    if (oct & 2u)
-      mn[1] = mn[1] + hy;
-    if (oct & 1u)
-      mn[2] = mn[2] + hz;
-    mx[0] = mn[0] + hx;
-    mx[1] = mn[1] + hy;
-    mx[2] = mn[2] + hz;
-  }
-}
-
 __device__ __forceinline__ double
 squared_distance(const double p[3], const double t[3])
 {

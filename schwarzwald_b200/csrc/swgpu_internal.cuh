@@ -244,3 +244,37 @@ void launch_payload_pnts(const double* xyz, const u32* perm, const u32* out_idx,
 // output offset per node (bit 63 may carry a flag); node_hdr: 4 doubles per node (offset xyz, scale).
 void launch_payload_las(const double* xyz, const u32* perm, const u32* out_idx, u64 n_out, const u64* node_first,
                         u32 n_nodes, const double* node_hdr, int* out, cudaStream_t stream);
+
+// ---- multi-batch node store (kernels_store.cu) ------------------------------------------
+size_t scan_scratch_words(u64 n);
+// out[0..n] = exclusive scan of in[0..n) as u64 (out[n] = total); scratch: scan_scratch_words(n) u64
+void launch_exclusive_scan_u32(const u32* in, u64 n, u64* out, u64* scratch, cudaStream_t stream);
+// gid[i] = base + order[i]
+void launch_make_gids(const u32* order, u64 n, u32 base, u32* gid, cudaStream_t stream);
+// visited nodes (runs of the incoming list) -> slot in the level's sorted node table (0xFFFFFFFF: new node) and
+// the number of points stored there
+void launch_store_lookup(const u64* in_key, const u32* node_start, u32 n_nodes, int node_shift, const u64* st_index,
+                         u32 st_n, const u64* st_first, u32* slot, u32* cnt, cudaStream_t stream);
+// the stored points of the visited nodes as a (key, gid) list, keys re-derived relative to the node bounds
+// (read_pnts_from_disk, TilingAlgorithms.cpp:50-109); boff = exclusive scan of the stored counts (n_nodes + 1)
+void launch_store_fetch(u64 m, const u64* boff, u32 n_nodes, const u32* slot, const u64* st_first, const u32* st_ids,
+                        const u64* in_key, const u32* node_start, int levels, const double* xyz, const SwBounds& root,
+                        u64* bkey, u32* bidx, cudaStream_t stream);
+// keys of stored ids relative to the root bounds (reconstruct input)
+void launch_store_root_keys(const u32* ids, u64 n, const double* xyz, const SwBounds& root, u64* keys,
+                            cudaStream_t stream);
+void launch_store_merged_nodes(const u32* node_start_a, const u64* boff, u32 n_nodes, u32* node_start_c, u32* gcount,
+                               cudaStream_t stream);
+// C = merge(A, B) by key, A first on ties (merge_node_data_sorted, Node.cpp:3-20)
+void launch_merge_lists(const u64* ak, const u32* ai, u64 na, const u64* bk, const u32* bi, u64 nb, u64* ck, u32* ci,
+                        cudaStream_t stream);
+// per node: A's run, then B's run (merge_node_data_unsorted, Node.cpp:22-34)
+void launch_concat_lists(const u64* ak, const u32* ai, u64 na, const u64* bk, const u32* bi, u64 nb,
+                         const u32* node_start_a, const u64* boff, u32 n_nodes, u64* ck, u32* ci, cudaStream_t stream);
+// store update (see kernels_store.cu)
+void launch_store_match(const u64* vidx, u32 nv, const u64* oidx, u32 no, u32* lo, u32* found, cudaStream_t stream);
+void launch_store_rows(const u64* vidx, const u64* vfirst, u32 nv, u64 chunk_end, u32 chunk_flags, const u32* lo,
+                       const u64* cumf, const u64* oidx, const u64* ofirst, const u32* oflags, u32 no, u64* nidx,
+                       u32* ncnt, u32* nflags, u64* nsrc, cudaStream_t stream);
+void launch_store_copy(u64 total, const u64* nfirst, u32 nn, const u64* nsrc, const u32* old_ids, const u32* chunk_ids,
+                       u32* new_ids, cudaStream_t stream);

@@ -88,6 +88,19 @@ struct HostScalars
   u32 n_nodes_next;
   u64 n_selected;
   u32 scratch[16]; // pinned scratch for the min-distance driver (starts at u32 index 8... see below)
+  u64 store_vals[4]; // read-backs of the multi-batch node store
+};
+
+// One octree level of the multi-batch node store: node table sorted by node index and the
+// stored global point ids, node by node, in stored order.
+struct LevelStore
+{
+  DevBuf index; // u64 n_nodes
+  DevBuf first; // u64 n_nodes + 1 (exclusive scan of the counts)
+  DevBuf flags; // u32 n_nodes
+  DevBuf ids;   // u32 n_ids
+  u64 n_nodes = 0;
+  u64 n_ids = 0;
 };
 
 enum LevelKind
@@ -144,6 +157,18 @@ struct swgpu_tiler
   const u32* global_ids = nullptr; // device: received point -> global point id
   DevBuf dense_counts, node_gcount;
   DevBuf part_tile_counts, part_send_counts;
+
+  // multi-batch mode (swgpu_set_multi_batch): the node store that persists between batches
+  bool multi_batch = false;
+  DevBuf store_xyz;       // positions of every batch, clamped; global point id = row
+  u64 store_points = 0;
+  int32_t store_start_level = -1; // FAST: fixed by the first batch
+  LevelStore store[22];
+  DevBuf list_key[4], list_idx[4]; // (key, gid) lists of the sweep: input, fetched, merged, remainder
+  DevBuf st_slot, st_cnt, st_boff, st_scan, st_gcount, st_lo, st_found, st_cumf;
+  DevBuf st_nidx, st_ncnt, st_nflags, st_nsrc, st_nfirst, st_nids;
+  const double* sample_pos = nullptr; // positions the selection kernels read, indexed by the lists' ids
+  const u32* gcount_override = nullptr;
 
   // stats
   swgpu_stats stats{};
@@ -341,6 +366,13 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
   const int node_shift = shift_for_levels(levels);
   cudaStream_t s = h->stream;
 
+  if (h->multi_batch) { // list lengths are not bounded by the batch size
+    const size_t tiles = sweep_tiles(count);
+    CK(h->tile_rank0.ensure(tiles * 4));
+    CK(h->scan_status.ensure(tiles * 8 * 5));
+    if (needs_positions(h->prm.sampling))
+      CK(h->sel.ensure(count));
+  }
   // grow the append-only outputs before taking pointers into them
   CK(h->out_key.ensure((h->out_count + count) * 8, s, h->out_count * 8));
   CK(h->out_idx.ensure((h->out_count + count) * 4, s, h->out_count * 4));
@@ -369,7 +401,7 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
   CK(h->node_first.ensure((h->node_count + n_nodes + 1) * 8, s, h->node_count * 8));
 
   // nodes above the shard prefix depth span GPUs: take-all needs their global point count
-  const u32* node_gcount = nullptr;
+  const u32* node_gcount = h->gcount_override; // multi-batch: nodes with stored points are never taken whole
   if (allow_take_all && !force_all && spans_shards(h, levels)) {
     rc = exchange_node_counts(h, in_key, n_nodes, levels);
     if (rc)
@@ -420,7 +452,7 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
         g.in_key = in_key;
         g.in_idx = in_idx;
         g.count = count;
-        g.pos_sorted = h->pos_sorted.as<double>();
+        g.pos_sorted = h->sample_pos;
         g.sampling = h->prm.sampling;
         g.node_shift = node_shift;
         g.node_level = node_level;
@@ -451,7 +483,7 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
         m.in_key = in_key;
         m.in_idx = in_idx;
         m.count = count;
-        m.pos_sorted = h->pos_sorted.as<double>();
+        m.pos_sorted = h->sample_pos;
         m.node_shift = node_shift;
         m.node_levels = levels;
         const double spacing_at_node = h->prm.spacing_at_root / std::pow(2, node_level + 1);
@@ -696,6 +728,8 @@ run_batch(swgpu_tiler* h)
   record(h, 3);
   CK(cudaGetLastError());
 
+  h->sample_pos = h->pos_sorted.as<double>();
+  h->gcount_override = nullptr;
   int first_levels = 0; // ACCURATE: root has 0 levels
   if (h->prm.tiling == SW_FAST) {
     int S = 0;
@@ -809,11 +843,411 @@ run_finalize(swgpu_tiler* h)
   return SW_OK;
 }
 
+
+// =============================================================================================
+// multi-batch mode: TilingAlgorithmV1 / V3 over several batches against a node store in HBM
+// =============================================================================================
+int
+read_store_vals(swgpu_tiler* h, const u64* a, const u64* b)
+{
+  CK(cudaMemcpyAsync(&h->h_scalars->store_vals[0], a, 8, cudaMemcpyDeviceToHost, h->stream));
+  if (b)
+    CK(cudaMemcpyAsync(&h->h_scalars->store_vals[1], b, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SW_OK;
+}
+
+// The selection of one sweep level (the last chunk) replaces what the visited nodes stored; every other node of
+// the level keeps its points.  Table and id pool are rebuilt in node-index order.
+int
+store_update(swgpu_tiler* h, int levels, const Chunk& c)
+{
+  LevelStore& L = h->store[levels];
+  cudaStream_t s = h->stream;
+  const u32 nv = c.n_nodes, no = (u32)L.n_nodes;
+  if (!nv)
+    return SW_OK;
+  const u64* vidx = h->node_index.as<u64>() + c.node_base;
+  const u64* vfirst = h->node_first.as<u64>() + c.node_base;
+  const size_t nn_max = (size_t)nv + no;
+  CK(h->st_lo.ensure((size_t)nv * 4));
+  CK(h->st_found.ensure((size_t)nv * 4));
+  CK(h->st_cumf.ensure(((size_t)nv + 1) * 8));
+  CK(h->st_scan.ensure(scan_scratch_words(nn_max) * 8));
+  CK(h->st_nidx.ensure(nn_max * 8));
+  CK(h->st_ncnt.ensure(nn_max * 4));
+  CK(h->st_nflags.ensure(nn_max * 4));
+  CK(h->st_nsrc.ensure(nn_max * 8));
+  CK(h->st_nfirst.ensure((nn_max + 1) * 8));
+  launch_store_match(vidx, nv, L.index.as<u64>(), no, h->st_lo.as<u32>(), h->st_found.as<u32>(), s);
+  launch_exclusive_scan_u32(h->st_found.as<u32>(), nv, h->st_cumf.as<u64>(), h->st_scan.as<u64>(), s);
+  CK(cudaMemsetAsync(h->st_ncnt.p, 0, nn_max * 4, s)); // rows past the real table count nothing
+  launch_store_rows(vidx, vfirst, nv, c.out_offset + c.count, c.flags, h->st_lo.as<u32>(), h->st_cumf.as<u64>(),
+                    L.index.as<u64>(), L.first.as<u64>(), L.flags.as<u32>(), no, h->st_nidx.as<u64>(),
+                    h->st_ncnt.as<u32>(), h->st_nflags.as<u32>(), h->st_nsrc.as<u64>(), s);
+  launch_exclusive_scan_u32(h->st_ncnt.as<u32>(), nn_max, h->st_nfirst.as<u64>(), h->st_scan.as<u64>(), s);
+  h->stats.kernel_launches += 8;
+  CK(cudaGetLastError());
+  int rc = read_store_vals(h, h->st_cumf.as<u64>() + nv, h->st_nfirst.as<u64>() + nn_max);
+  if (rc)
+    return rc;
+  const u64 n_found = h->h_scalars->store_vals[0], total = h->h_scalars->store_vals[1];
+  const u64 nn = nn_max - n_found;
+  CK(h->st_nids.ensure(std::max<u64>(total, 1) * 4));
+  launch_store_copy(total, h->st_nfirst.as<u64>(), (u32)nn, h->st_nsrc.as<u64>(), L.ids.as<u32>(),
+                    h->out_idx.as<u32>(), h->st_nids.as<u32>(), s);
+  h->stats.kernel_launches += 1;
+  h->stats.bytes_traffic += 8 * total;
+  CK(cudaGetLastError());
+  std::swap(L.index, h->st_nidx);
+  std::swap(L.first, h->st_nfirst);
+  std::swap(L.flags, h->st_nflags);
+  std::swap(L.ids, h->st_nids);
+  L.n_nodes = nn;
+  L.n_ids = total;
+  return SW_OK;
+}
+
+// One sweep level of a batch against the store.  cur: slot of list_key / list_idx that holds the input list
+// (Morton ordered, node boundaries in h->node_start); on return the slot of the remainder list.
+int
+store_level(swgpu_tiler* h, int* cur, u64* count_io, int levels, bool terminal, u32 n_nodes, u32* n_nodes_next)
+{
+  cudaStream_t s = h->stream;
+  LevelStore& L = h->store[levels];
+  int free_slots[3], nf = 0;
+  for (int i = 0; i < 4; ++i)
+    if (i != *cur)
+      free_slots[nf++] = i;
+  const int sb = free_slots[0], sc = free_slots[1];
+  int sr = free_slots[2];
+  u64 count = *count_io;
+  const u64* in_key = h->list_key[*cur].as<u64>();
+  const u32* in_idx = h->list_idx[*cur].as<u32>();
+  int in_slot = *cur;
+
+  u64 m = 0;
+  if (L.n_nodes) { // which of the visited nodes hold points from earlier batches
+    CK(h->st_slot.ensure((size_t)n_nodes * 4));
+    CK(h->st_cnt.ensure((size_t)n_nodes * 4));
+    CK(h->st_boff.ensure(((size_t)n_nodes + 1) * 8));
+    CK(h->st_scan.ensure(scan_scratch_words(n_nodes) * 8));
+    launch_store_lookup(in_key, h->node_start.as<u32>(), n_nodes, shift_for_levels(levels), L.index.as<u64>(),
+                        (u32)L.n_nodes, L.first.as<u64>(), h->st_slot.as<u32>(), h->st_cnt.as<u32>(), s);
+    launch_exclusive_scan_u32(h->st_cnt.as<u32>(), n_nodes, h->st_boff.as<u64>(), h->st_scan.as<u64>(), s);
+    h->stats.kernel_launches += 4;
+    CK(cudaGetLastError());
+    const int rc = read_store_vals(h, h->st_boff.as<u64>() + n_nodes, nullptr);
+    if (rc)
+      return rc;
+    m = h->h_scalars->store_vals[0];
+  }
+  h->gcount_override = nullptr;
+  if (m) {
+    if (count + m >= (1ull << 30))
+      return fail(h, SW_ERR_INVALID_ARGUMENT, "a sweep list is limited to 2^30 - 1 points (batch + revisited nodes)");
+    CK(h->list_key[sb].ensure(m * 8));
+    CK(h->list_idx[sb].ensure(m * 4));
+    CK(h->list_key[sc].ensure((count + m) * 8));
+    CK(h->list_idx[sc].ensure((count + m) * 4));
+    CK(h->node_start_next.ensure((count + m + 1) * 4));
+    CK(h->st_gcount.ensure((size_t)n_nodes * 4));
+    launch_store_fetch(m, h->st_boff.as<u64>(), n_nodes, h->st_slot.as<u32>(), L.first.as<u64>(), L.ids.as<u32>(),
+                       in_key, h->node_start.as<u32>(), levels, h->store_xyz.as<double>(), h->bounds,
+                       h->list_key[sb].as<u64>(), h->list_idx[sb].as<u32>(), s);
+    if (terminal) // merge_node_data_unsorted, Node.cpp:22-34
+      launch_concat_lists(in_key, in_idx, count, h->list_key[sb].as<u64>(), h->list_idx[sb].as<u32>(), m,
+                          h->node_start.as<u32>(), h->st_boff.as<u64>(), n_nodes, h->list_key[sc].as<u64>(),
+                          h->list_idx[sc].as<u32>(), s);
+    else // merge_node_data_sorted, Node.cpp:3-20
+      launch_merge_lists(in_key, in_idx, count, h->list_key[sb].as<u64>(), h->list_idx[sb].as<u32>(), m,
+                         h->list_key[sc].as<u64>(), h->list_idx[sc].as<u32>(), s);
+    launch_store_merged_nodes(h->node_start.as<u32>(), h->st_boff.as<u64>(), n_nodes, h->node_start_next.as<u32>(),
+                              h->st_gcount.as<u32>(), s);
+    std::swap(h->node_start, h->node_start_next);
+    h->stats.kernel_launches += 3;
+    h->stats.bytes_traffic += (24 + 12 + 4) * m + 24 * (count + m);
+    CK(cudaGetLastError());
+    count += m;
+    in_key = h->list_key[sc].as<u64>();
+    in_idx = h->list_idx[sc].as<u32>();
+    in_slot = sc;
+    h->gcount_override = h->st_gcount.as<u32>();
+  }
+  if (sr == in_slot)
+    sr = *cur;
+  CK(h->list_key[sr].ensure(count * 8));
+  CK(h->list_idx[sr].ensure(count * 4));
+  CK(h->node_start_next.ensure((count + 1) * 4));
+
+  u64 n_sel = 0;
+  int rc = sweep_level(h, in_key, in_idx, count, levels, /*allow_take_all=*/true, terminal, h->list_key[sr].as<u64>(),
+                       h->list_idx[sr].as<u32>(), 0u, &n_sel, false, 0, true, n_nodes, n_nodes_next);
+  h->gcount_override = nullptr;
+  if (rc)
+    return rc;
+  rc = store_update(h, levels, h->chunks.back());
+  if (rc)
+    return rc;
+  // the output arrays were scratch for this level only
+  h->chunks.clear();
+  h->out_count = 0;
+  h->node_count = 0;
+  *cur = sr;
+  *count_io = count - n_sel;
+  return SW_OK;
+}
+
+int
+run_batch_store(swgpu_tiler* h)
+{
+  const u64 n = h->n;
+  cudaStream_t s = h->stream;
+  h->chunks.clear();
+  h->out_count = 0;
+  h->node_count = 0;
+  h->batch_done = false;
+  h->finalized = false;
+  h->n_clamped = 0;
+  h->h_scalars->n_clamped = 0;
+  std::memset(&h->stats, 0, sizeof(h->stats));
+  h->stats.n_points = n;
+  if (h->shard_levels)
+    return fail(h, SW_ERR_STATE, "multi-batch mode and sharding cannot be combined");
+  if (n >= (1ull << 30))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "a batch is limited to 2^30 - 1 points per GPU");
+  if (h->store_points + n >= (1ull << 32))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "global point ids are 32 bit: all batches together must stay below 2^32");
+  {
+    const double ex = h->prm.bounds_max[0] - h->prm.bounds_min[0];
+    for (int a = 1; a < 3; ++a) {
+      const double e = h->prm.bounds_max[a] - h->prm.bounds_min[a];
+      if (std::fabs(e - ex) > 1e-9 * std::fabs(ex))
+        return fail(h, SW_ERR_INVALID_ARGUMENT, "tiling needs cubic bounds (AABB::makeCubic)");
+    }
+  }
+  if (h->prm.tiling == SW_FAST && n < h->prm.concurrency)
+    return fail(h, SW_ERR_TOO_FEW_POINTS, "Can't scatter a range that has less than 'scatter_factor' elements!");
+  if (n == 0)
+    return fail(h, SW_ERR_EMPTY_NODE, "tile_internal_node: Got zero points to tile @ node r");
+  int rc = ensure_batch_buffers(h, n);
+  if (rc)
+    return rc;
+
+  record(h, 0);
+  CK(cudaMemsetAsync(h->hist.p, 0, sort_hist_words() * 4, s));
+  CK(cudaMemsetAsync(h->scalars.p, 0, 128, s));
+  u64* unsorted_keys = h->keys[sort_input_buffer()].as<u64>();
+  if (h->d_las) {
+    launch_las_encode(h->d_las, n, h->las_t, h->bounds, h->d_xyz, unsorted_keys, h->hist.as<u32>(), h->d_n_clamped(),
+                      s);
+    h->stats.bytes_index = 48 * n;
+  } else {
+    launch_morton_encode(h->d_xyz, n, h->bounds, unsorted_keys, h->hist.as<u32>(), h->d_n_clamped(), s);
+    h->stats.bytes_index = 36 * n;
+  }
+  record(h, 1);
+  launch_radix_sort(h->keys[0].as<u64>(), h->keys[1].as<u64>(), h->vals[0].as<u32>(), h->vals[1].as<u32>(), n,
+                    h->hist.as<u32>(), h->sort_status.as<u32>(), h->d_tickets() + 8, s);
+  h->stats.kernel_launches += 2 + sort_passes();
+  h->stats.bytes_sort = (8 + (u64)sort_passes() * 24) * n;
+  record(h, 2);
+  // the batch joins the point store (clamped positions, like the PointBuffer after index_point)
+  const u64 base = h->store_points;
+  CK(h->store_xyz.ensure((base + n) * 24, s, base * 24));
+  CK(cudaMemcpyAsync(h->store_xyz.as<double>() + 3 * base, h->d_xyz, n * 24, cudaMemcpyDeviceToDevice, s));
+  h->store_points = base + n;
+  h->sample_pos = h->store_xyz.as<double>();
+  int cur = 0;
+  CK(h->list_key[0].ensure(n * 8));
+  CK(h->list_idx[0].ensure(n * 4));
+  CK(cudaMemcpyAsync(h->list_key[0].p, h->keys[0].p, n * 8, cudaMemcpyDeviceToDevice, s));
+  launch_make_gids(h->vals[0].as<u32>(), n, (u32)base, h->list_idx[0].as<u32>(), s);
+  h->stats.kernel_launches += 1;
+  record(h, 3);
+  CK(cudaGetLastError());
+
+  int first_levels = 0;
+  if (h->prm.tiling == SW_FAST) {
+    if (h->store_start_level < 0) { // the first batch fixes the start level (TilingAlgorithms.cpp:1250-1360)
+      int S = 0;
+      rc = estimate_start_level(h, &S);
+      if (rc)
+        return rc;
+      h->store_start_level = S;
+    } else { // later batches are cut at it (:1362-1453)
+      launch_level5_bins(h->keys[0].as<u64>(), n, h->bins.as<u32>(), s);
+      h->stats.kernel_launches += 1;
+    }
+    h->start_level = h->store_start_level;
+    first_levels = h->store_start_level;
+  }
+  u64 count = n;
+  u32 n_nodes = 0;
+  if (first_levels == 0) {
+    launch_root_node(h->node_start.as<u32>(), count, s);
+    n_nodes = 1;
+  } else {
+    launch_start_nodes(h->bins.as<u32>(), first_levels, count, h->node_start.as<u32>(), h->d_n_nodes(), s);
+    h->stats.kernel_launches += 1;
+    rc = sync_scalars(h);
+    if (rc)
+      return rc;
+    n_nodes = h->h_scalars->n_nodes;
+  }
+  for (int levels = first_levels; count > 0; ++levels) {
+    const LevelKind kind = level_kind(h, levels - 1);
+    if (kind == KIND_REROOT || levels > 21)
+      return fail(h, SW_ERR_DEEP_REROOT, "deep re-root path (TilingAlgorithms.cpp:444-483) is not supported");
+    const bool terminal = (kind == KIND_TERMINAL);
+    if (!terminal && levels >= 21)
+      return fail(h, SW_ERR_DEEP_REROOT, "child level exceeds MortonIndex64 capacity");
+    u32 n_nodes_next = 0;
+    rc = store_level(h, &cur, &count, levels, terminal, n_nodes, &n_nodes_next);
+    if (rc)
+      return rc;
+    h->stats.n_levels += 1;
+    n_nodes = n_nodes_next;
+  }
+  record(h, 4);
+  CK(cudaGetLastError());
+  rc = sync_scalars(h);
+  if (rc)
+    return rc;
+  h->n_clamped = h->h_scalars->n_clamped;
+  h->batch_done = true;
+  return SW_OK;
+}
+
+// FAST finalize over the store: reconstruct_left_out_nodes for every start node the store holds
+// (TilingAlgorithms.cpp:1717-1784); the input of level lv is the whole pool of level lv + 1 in node order.
+int
+run_finalize_store(swgpu_tiler* h)
+{
+  if (!h->batch_done || h->prm.tiling != SW_FAST || h->finalized)
+    return SW_OK;
+  cudaStream_t s = h->stream;
+  const int S = h->store_start_level;
+  h->sample_pos = h->store_xyz.as<double>();
+  h->gcount_override = nullptr;
+  for (int lv = S - 1; lv >= 0; --lv) {
+    LevelStore& C = h->store[lv + 1];
+    if (!C.n_nodes)
+      continue;
+    const u64 count = C.n_ids;
+    if (count >= (1ull << 30))
+      return fail(h, SW_ERR_INVALID_ARGUMENT, "a sweep list is limited to 2^30 - 1 points");
+    CK(h->list_key[0].ensure(count * 8));
+    CK(h->node_start.ensure((std::max<u64>(count, C.n_nodes) + 1) * 4));
+    CK(h->node_start_next.ensure((count + 1) * 4));
+    launch_store_root_keys(C.ids.as<u32>(), count, h->store_xyz.as<double>(), h->bounds, h->list_key[0].as<u64>(), s);
+    launch_parent_nodes(C.index.as<u64>(), C.first.as<u64>(), (u32)C.n_nodes, 0, count, h->node_start.as<u32>(),
+                        h->d_n_nodes(), s);
+    h->stats.kernel_launches += 2;
+    int rc = sync_scalars(h);
+    if (rc)
+      return rc;
+    const u32 n_parents = h->h_scalars->n_nodes;
+    h->store[lv].n_nodes = 0; // levels above the start level only ever hold reconstructed nodes
+    h->store[lv].n_ids = 0;
+    u64 n_sel = 0;
+    rc = sweep_level(h, h->list_key[0].as<u64>(), C.ids.as<u32>(), count, lv, /*allow_take_all=*/false, false, nullptr,
+                     nullptr, SW_NODE_RECONSTRUCTED, &n_sel, false, 0, true, n_parents, nullptr);
+    if (rc)
+      return rc;
+    rc = store_update(h, lv, h->chunks.back());
+    if (rc)
+      return rc;
+    h->chunks.clear();
+    h->out_count = 0;
+    h->node_count = 0;
+    h->stats.n_reconstruct_levels += 1;
+  }
+  record(h, 5);
+  h->finalized = true;
+  return SW_OK;
+}
+
+u64
+store_node_total(const swgpu_tiler* h)
+{
+  u64 t = 0;
+  for (const LevelStore& L : h->store)
+    t += L.n_nodes;
+  return t;
+}
+
+u64
+store_id_total(const swgpu_tiler* h)
+{
+  u64 t = 0;
+  for (const LevelStore& L : h->store)
+    t += L.n_ids;
+  return t;
+}
+
+// final content of the store: nodes by (levels, index), ids node-major
+int
+store_get_nodes(swgpu_tiler* h, sw_node* nodes, u32* ids, bool ids_on_device)
+{
+  u64 row = 0, off = 0;
+  for (int lv = 0; lv < 22; ++lv) {
+    const LevelStore& L = h->store[lv];
+    if (!L.n_nodes)
+      continue;
+    if (nodes) {
+      std::vector<u64> index(L.n_nodes), first(L.n_nodes + 1);
+      std::vector<u32> flags(L.n_nodes);
+      CK(cudaMemcpyAsync(index.data(), L.index.p, L.n_nodes * 8, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(first.data(), L.first.p, (L.n_nodes + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(flags.data(), L.flags.p, L.n_nodes * 4, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      for (u64 k = 0; k < L.n_nodes; ++k) {
+        sw_node& nd = nodes[row + k];
+        nd.index = index[k];
+        nd.levels = (uint32_t)lv;
+        nd.flags = flags[k];
+        nd.first = off + first[k];
+        nd.count = first[k + 1] - first[k];
+      }
+    }
+    if (ids && L.n_ids)
+      CK(cudaMemcpyAsync(ids + off, L.ids.p, L.n_ids * 4, ids_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                         h->stream));
+    row += L.n_nodes;
+    off += L.n_ids;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return SW_OK;
+}
+
+int
+tile_current_batch(swgpu_tiler* h)
+{
+  return h->multi_batch ? run_batch_store(h) : run_batch(h);
+}
+
 } // namespace
 
 // =============================================================================================
 // C ABI
 // =============================================================================================
+static void
+release_store(swgpu_tiler* h)
+{
+  for (LevelStore& L : h->store) {
+    L.index.release();
+    L.first.release();
+    L.flags.release();
+    L.ids.release();
+    L.n_nodes = 0;
+    L.n_ids = 0;
+  }
+  h->store_xyz.release();
+  h->store_points = 0;
+  h->store_start_level = -1;
+}
+
 extern "C" {
 
 int
@@ -879,6 +1313,15 @@ swgpu_destroy(swgpu_handle h)
                      &h->part_tile_counts, &h->part_send_counts };
   for (DevBuf* b : bufs)
     b->release();
+  release_store(h);
+  for (int i = 0; i < 4; ++i) {
+    h->list_key[i].release();
+    h->list_idx[i].release();
+  }
+  DevBuf* st_bufs[] = { &h->st_slot, &h->st_cnt,  &h->st_boff,   &h->st_scan, &h->st_gcount, &h->st_lo,    &h->st_found,
+                        &h->st_cumf, &h->st_nidx, &h->st_ncnt,   &h->st_nflags, &h->st_nsrc, &h->st_nfirst, &h->st_nids };
+  for (DevBuf* b : st_bufs)
+    b->release();
   free_min_distance_scratch(h->md);
   if (h->h_scalars)
     cudaFreeHost(h->h_scalars);
@@ -900,6 +1343,23 @@ swgpu_set_stream(swgpu_handle h, void* cuda_stream)
   if (!h)
     return SW_ERR_INVALID_ARGUMENT;
   h->stream = static_cast<cudaStream_t>(cuda_stream);
+  return SW_OK;
+}
+
+int
+swgpu_set_multi_batch(swgpu_handle h, int enable)
+{
+  if (!h)
+    return SW_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  release_store(h);
+  h->multi_batch = enable != 0;
+  h->batch_done = false;
+  h->finalized = false;
+  h->out_count = 0;
+  h->node_count = 0;
+  h->chunks.clear();
   return SW_OK;
 }
 
@@ -930,7 +1390,7 @@ swgpu_index_batch_device(swgpu_handle h, double* xyz_device, uint64_t n)
   h->d_las = nullptr;
   h->d_xyz = xyz_device;
   h->n = n;
-  return run_batch(h);
+  return tile_current_batch(h);
 }
 
 int
@@ -944,7 +1404,7 @@ swgpu_index_batch(swgpu_handle h, double* xyz_host, uint64_t n)
   h->d_las = nullptr;
   h->d_xyz = h->xyz_own.as<double>();
   h->n = n;
-  const int rc = run_batch(h);
+  const int rc = tile_current_batch(h);
   if (rc)
     return rc;
   if (h->n_clamped) { // index_point wrote clamped coordinates back into the PointBuffer
@@ -960,7 +1420,7 @@ swgpu_finalize(swgpu_handle h)
   if (!h)
     return SW_ERR_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
-  return run_finalize(h);
+  return h->multi_batch ? run_finalize_store(h) : run_finalize(h);
 }
 
 static int
@@ -990,7 +1450,7 @@ swgpu_index_batch_las_device(swgpu_handle h, const int32_t* las_xyz_device, uint
   h->d_las = las_xyz_device;
   h->d_xyz = h->xyz_own.as<double>();
   h->n = n;
-  const int rc = run_batch(h);
+  const int rc = tile_current_batch(h);
   h->d_las = nullptr; // the positions now live in xyz_own
   return rc;
 }
@@ -1025,9 +1485,9 @@ swgpu_result_size(swgpu_handle h, uint64_t* n_nodes, uint64_t* n_point_ids)
   if (!h)
     return SW_ERR_INVALID_ARGUMENT;
   if (n_nodes)
-    *n_nodes = h->node_count;
+    *n_nodes = h->multi_batch ? store_node_total(h) : h->node_count;
   if (n_point_ids)
-    *n_point_ids = h->out_count;
+    *n_point_ids = h->multi_batch ? store_id_total(h) : h->out_count;
   return SW_OK;
 }
 
@@ -1074,6 +1534,8 @@ swgpu_get_nodes_device_ids(swgpu_handle h, sw_node* nodes, uint32_t* point_ids_d
   if (!h->batch_done)
     return fail(h, SW_ERR_STATE, "no batch has been indexed");
   cudaSetDevice(h->device);
+  if (h->multi_batch)
+    return store_get_nodes(h, nodes, point_ids_device, true);
   if (point_ids_device && h->out_count) {
     compose_output_ids(h, point_ids_device);
     CK(cudaGetLastError());
@@ -1089,6 +1551,8 @@ swgpu_get_nodes(swgpu_handle h, sw_node* nodes, uint32_t* point_ids)
   if (!h->batch_done)
     return fail(h, SW_ERR_STATE, "no batch has been indexed");
   cudaSetDevice(h->device);
+  if (h->multi_batch)
+    return store_get_nodes(h, nodes, point_ids, false);
   if (point_ids && h->out_count) {
     CK(h->ids_tmp.ensure(h->out_count * 4));
     compose_output_ids(h, h->ids_tmp.as<u32>());

@@ -175,6 +175,11 @@ class GpuTiler:
     def reserve(self, n):
         self._check(self._lib.swgpu_reserve(self._h, int(n)))
 
+    def set_multi_batch(self, on=True):
+        """Every later build_execution_graph() is one batch of a multi-batch run against the device-resident
+        node store (TilingAlgorithms.cpp:351-492 with cached points); results carry global point ids."""
+        self._check(self._lib.swgpu_set_multi_batch(self._h, 1 if on else 0))
+
     def enable_timing(self, on=True):
         self._check(self._lib.swgpu_enable_timing(self._h, 1 if on else 0))
 
