@@ -202,6 +202,25 @@ int swgpu_partition_to_peers_device(swgpu_handle h, const uint64_t* keys_device,
 int swgpu_set_shard(swgpu_handle h, uint32_t shard_levels, int32_t start_level, swgpu_allreduce_u32_fn allreduce,
                     void* allreduce_ctx, const uint32_t* global_ids_device);
 
+/* MIN_DISTANCE / MIN_DISTANCE_FAST on nodes that span shards (fewer than shard_levels levels; FAST's reconstructed
+ * levels as well).  PoissonDiskSampling (core/tiling/Sampling.h:421-471, core/datastructures/SparseGrid.cpp:116-146)
+ * is ONE greedy over all points of a node in Morton order; running it in rank order would serialise the GPUs.
+ * With this hook every shard samples its part of the node on its own (exact inside the part), the accepted points
+ * that have another shard within the spacing are all-gathered (32 bytes each: key + position), and a point that is
+ * closer than the spacing to an accepted point of a LOWER rank (earlier in Morton order) is rejected and moves on
+ * to the child nodes.  The merged node then keeps the reference's invariant — no two stored points closer than
+ * the spacing — and may hold slightly fewer points than the sequential greedy (north_star's relaxed mode; the
+ * stated bound of 1 % per node is checked by tests/test_gpu_sharded.py).  Nodes inside one shard stay exact.
+ * Without the hook, spanning nodes are sampled per shard with no exchange (the invariant can then fail across
+ * shard faces).  first_prefix / n_ranks: the splitters of swgpu_choose_splitters; rank: this shard.
+ * The hook gathers `send_bytes` bytes of every rank, in rank order, into a device buffer it owns and that stays
+ * valid until its next call: *recv_device = that buffer, recv_bytes[r] = bytes of rank r; all work on
+ * cuda_stream.  Collective: the library calls it once per sampled spanning level on every rank. */
+typedef int (*swgpu_allgatherv_fn)(void* ctx, const void* send_device, uint64_t send_bytes, void** recv_device,
+                                   uint64_t* recv_bytes, void* cuda_stream);
+int swgpu_set_shard_faces(swgpu_handle h, const uint32_t* first_prefix, uint32_t n_ranks, uint32_t rank,
+                          swgpu_allgatherv_fn allgatherv, void* ctx);
+
 /* Algorithmic bytes of the last index_batch + finalize by the accounting model of SURVEY.md section 8(d)
  * (bytes_index/sort/gather/sample; used by bench.py for the roofline line), the bytes this implementation
  * actually reads and writes by its own traffic model (bytes_traffic: e.g. the two-pass compaction reads

@@ -442,3 +442,160 @@ launch_compose_ids_mapped(const u32* perm, const u32* idx, const u32* map, u64 n
   const u64 want = (n + 255) / 256, cap = (u64)sms * 8;
   compose_ids_mapped_kernel<<<(u32)(want < cap ? want : cap), 256, 0, stream>>>(perm, idx, map, n, out);
 }
+
+// =============================================================================================
+// MIN_DISTANCE across shard faces
+// =============================================================================================
+// A node above the shard prefix depth spans GPUs.  PoissonDiskSampling (Sampling.h:421-471, SparseGrid.cpp:
+// 116-146) is one greedy over ALL points of the node in Morton order, so an accepted point on one GPU can
+// lie within the spacing of an accepted point on the neighbouring GPU.  Running the greedy in rank order
+// would serialise the GPUs; instead every GPU samples its part on its own (exact inside the part), then
+//   face_flag     marks its accepted points that have another shard within the spacing,
+//   face_collect  packs them (key, position) in Morton order,
+//   (all-gather of those few points through the caller's hook)
+//   face_resolve  rejects every own accepted point that is closer than the spacing to an accepted point of
+//                 a LOWER rank (the lower rank comes first in Morton order, as in the sequential greedy).
+// Rejected points move on to the child nodes like any other point that was not selected.  The merged node
+// then satisfies the reference's invariant (no two stored points closer than the spacing); it can hold
+// slightly fewer points than the sequential greedy would (north_star's relaxed mode: stated 1 % bound,
+// checked by tests/test_gpu_sharded.py).
+__global__ void __launch_bounds__(256)
+face_flag_kernel(const u32* __restrict__ in_idx, const double* __restrict__ pos, const unsigned char* __restrict__ state,
+                 u64 count, SwBounds b, double reach, SwSplitters sp, u32 my_rank, u32* __restrict__ flags)
+{
+  const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+  if (i >= count)
+    return;
+  u32 f = 0;
+  if (state[i] == 1) {
+    const u64 idx = in_idx ? in_idx[i] : i;
+    const double p[3] = { pos[3 * idx], pos[3 * idx + 1], pos[3 * idx + 2] };
+    // the owner cells (shard-level subtrees) are at least `reach` wide, so the 27 points p + {-r, 0, r}^3 hit
+    // every owner cell the cube [p - r, p + r]^3 overlaps
+    for (int dx = -1; dx <= 1 && !f; ++dx)
+      for (int dy = -1; dy <= 1 && !f; ++dy)
+        for (int dz = -1; dz <= 1 && !f; ++dz) {
+          double q[3] = { p[0] + dx * reach, p[1] + dy * reach, p[2] + dz * reach };
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+            q[a] = q[a] < b.min[a] ? b.min[a] : (q[a] > b.max[a] ? b.max[a] : q[a]);
+          if (dest_of(morton_from_position(q[0], q[1], q[2], b), sp) != my_rank)
+            f = 1;
+        }
+  }
+  flags[i] = f;
+}
+
+__global__ void __launch_bounds__(256)
+face_collect_kernel(const u64* __restrict__ in_key, const u32* __restrict__ in_idx, const double* __restrict__ pos,
+                    u64 count, const u32* __restrict__ flags, const u64* __restrict__ offs, SwFaceRecord* __restrict__ rec,
+                    u32* __restrict__ rec_src)
+{
+  const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+  if (i >= count || !flags[i])
+    return;
+  const u64 idx = in_idx ? in_idx[i] : i;
+  SwFaceRecord r;
+  r.key = in_key[i] & SW_KEY_MASK;
+  r.x = pos[3 * idx];
+  r.y = pos[3 * idx + 1];
+  r.z = pos[3 * idx + 2];
+  rec[offs[i]] = r;
+  rec_src[offs[i]] = (u32)i;
+}
+
+__device__ __forceinline__ u64
+face_lower_bound(const SwFaceRecord* __restrict__ a, u64 n, u64 key)
+{
+  u64 lo = 0, hi = n;
+  while (lo < hi) {
+    const u64 mid = (lo + hi) >> 1;
+    if (a[mid].key < key)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(128)
+face_resolve_kernel(const SwFaceRecord* __restrict__ mine, const u32* __restrict__ mine_src, u32 n_mine,
+                    const SwFaceRecord* __restrict__ all, SwFaceRanks fr, u32 my_rank, int cell_levels, int node_levels,
+                    double threshold, unsigned char* __restrict__ state)
+{
+  const u32 j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= n_mine)
+    return;
+  const SwFaceRecord me = mine[j];
+  const int node_shift = shift_for_levels(node_levels);
+  const u64 node_lo = node_levels ? ((me.key >> node_shift) << node_shift) : 0ull;
+  const u64 node_hi = node_levels ? node_lo + (1ull << node_shift) : (1ull << 63);
+  const int below = cell_levels - node_levels;
+  bool hit = false;
+  for (u32 q = 0; q < my_rank && !hit; ++q) {
+    const SwFaceRecord* list = all + fr.first[q];
+    const u64 len = fr.first[q + 1] - fr.first[q];
+    if (!len)
+      continue;
+    if (below <= 0) { // the node is not larger than a search cell: every point of the node is a candidate
+      for (u64 k = face_lower_bound(list, len, node_lo); k < len && list[k].key < node_hi && !hit; ++k) {
+        const double dx = me.x - list[k].x, dy = me.y - list[k].y, dz = me.z - list[k].z;
+        hit = dx * dx + dy * dy + dz * dz < threshold;
+      }
+      continue;
+    }
+    const int cell_shift = shift_for_levels(cell_levels);
+    const u64 code = me.key >> cell_shift;
+    const long long side = 1ll << cell_levels;
+    const long long x = (long long)contract_bits_by_3(code >> 2);
+    const long long y = (long long)contract_bits_by_3(code >> 1);
+    const long long z = (long long)contract_bits_by_3(code);
+    for (int dx = -1; dx <= 1 && !hit; ++dx)
+      for (int dy = -1; dy <= 1 && !hit; ++dy)
+        for (int dz = -1; dz <= 1 && !hit; ++dz) {
+          const long long X = x + dx, Y = y + dy, Z = z + dz;
+          if (X < 0 || Y < 0 || Z < 0 || X >= side || Y >= side || Z >= side)
+            continue;
+          const u64 nc = expand_bits_by_3((u64)Z) | (expand_bits_by_3((u64)Y) << 1) | (expand_bits_by_3((u64)X) << 2);
+          if ((nc >> (3 * below)) != (code >> (3 * below)))
+            continue; // another node: the greedy is per node
+          const u64 lo = nc << cell_shift, hi = cell_shift ? lo + (1ull << cell_shift) : lo + 1;
+          for (u64 k = face_lower_bound(list, len, lo); k < len && list[k].key < hi && !hit; ++k) {
+            const double ex = me.x - list[k].x, ey = me.y - list[k].y, ez = me.z - list[k].z;
+            hit = ex * ex + ey * ey + ez * ez < threshold;
+          }
+        }
+  }
+  if (hit)
+    state[mine_src[j]] = 2;
+}
+
+void
+launch_face_flag(const u32* in_idx, const double* pos, const unsigned char* state, u64 count, const SwBounds& b,
+                 double reach, const u32* first_prefix, u32 n_ranks, u32 my_rank, u32* flags, cudaStream_t stream)
+{
+  if (!count)
+    return;
+  const SwSplitters sp = make_splitters(first_prefix, n_ranks);
+  face_flag_kernel<<<(u32)((count + 255) / 256), 256, 0, stream>>>(in_idx, pos, state, count, b, reach, sp, my_rank,
+                                                                  flags);
+}
+
+void
+launch_face_collect(const u64* in_key, const u32* in_idx, const double* pos, u64 count, const u32* flags,
+                    const u64* offs, SwFaceRecord* rec, u32* rec_src, cudaStream_t stream)
+{
+  if (count)
+    face_collect_kernel<<<(u32)((count + 255) / 256), 256, 0, stream>>>(in_key, in_idx, pos, count, flags, offs, rec,
+                                                                       rec_src);
+}
+
+void
+launch_face_resolve(const SwFaceRecord* mine, const u32* mine_src, u32 n_mine, const SwFaceRecord* all,
+                    const SwFaceRanks& fr, u32 my_rank, int cell_levels, int node_levels, double threshold,
+                    unsigned char* state, cudaStream_t stream)
+{
+  if (n_mine && my_rank)
+    face_resolve_kernel<<<(n_mine + 127) / 128, 128, 0, stream>>>(mine, mine_src, n_mine, all, fr, my_rank,
+                                                                  cell_levels, node_levels, threshold, state);
+}

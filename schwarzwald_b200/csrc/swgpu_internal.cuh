@@ -218,6 +218,25 @@ void launch_node_counts_from_dense(const u64* keys, const u32* node_start, u32 n
 // out[i] = map[perm[idx[i]]]
 void launch_compose_ids_mapped(const u32* perm, const u32* idx, const u32* map, u64 n, u32* out, cudaStream_t stream);
 
+// MIN_DISTANCE across shard faces (see kernels_shard.cu): accepted points that have another shard within the
+// spacing, exchanged between the ranks; a point loses against a conflicting accepted point of a lower rank
+struct SwFaceRecord
+{
+  u64 key;
+  double x, y, z;
+};
+struct SwFaceRanks
+{
+  u64 first[SW_MAX_RANKS + 1]; // records of rank r = [first[r], first[r + 1]) of the gathered array
+};
+void launch_face_flag(const u32* in_idx, const double* pos, const unsigned char* state, u64 count, const SwBounds& b,
+                      double reach, const u32* first_prefix, u32 n_ranks, u32 my_rank, u32* flags, cudaStream_t stream);
+void launch_face_collect(const u64* in_key, const u32* in_idx, const double* pos, u64 count, const u32* flags,
+                         const u64* offs, SwFaceRecord* rec, u32* rec_src, cudaStream_t stream);
+void launch_face_resolve(const SwFaceRecord* mine, const u32* mine_src, u32 n_mine, const SwFaceRecord* all,
+                         const SwFaceRanks& fr, u32 my_rank, int cell_levels, int node_levels, double threshold,
+                         unsigned char* state, cudaStream_t stream);
+
 // ---- LAS input transform (kernels_index_sort.cu) and writer payloads (kernels_payload.cu) ------------
 // device-side copy of sw_las_transform (include/sw_types.h)
 struct SwLasTransform

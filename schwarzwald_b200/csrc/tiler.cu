@@ -157,6 +157,13 @@ struct swgpu_tiler
   const u32* global_ids = nullptr; // device: received point -> global point id
   DevBuf dense_counts, node_gcount;
   DevBuf part_tile_counts, part_send_counts;
+  // MIN_DISTANCE across shard faces (swgpu_set_shard_faces)
+  swgpu_allgatherv_fn face_fn = nullptr;
+  void* face_ctx = nullptr;
+  u32 face_first_prefix[SW_MAX_RANKS + 1] = {};
+  u32 face_n_ranks = 0, face_rank = 0;
+  DevBuf face_flags, face_offs, face_scan, face_rec, face_src;
+  u64 face_points_sent = 0, face_points_rejected_upper_bound = 0;
 
   // multi-batch mode (swgpu_set_multi_batch): the node store that persists between batches
   bool multi_batch = false;
@@ -354,6 +361,80 @@ exchange_node_counts(swgpu_tiler* h, const u64* in_key, u32 n_nodes, int levels)
   return SW_OK;
 }
 
+int
+read_store_vals(swgpu_tiler* h, const u64* a, const u64* b)
+{
+  CK(cudaMemcpyAsync(&h->h_scalars->store_vals[0], a, 8, cudaMemcpyDeviceToHost, h->stream));
+  if (b)
+    CK(cudaMemcpyAsync(&h->h_scalars->store_vals[1], b, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return SW_OK;
+}
+
+// does the selection of this node level run the minimum-distance greedy (sweep_level's switch)
+bool
+level_uses_min_distance(const swgpu_tiler* h, int node_level)
+{
+  if (h->prm.sampling == SW_MIN_DISTANCE)
+    return true;
+  if (h->prm.sampling == SW_MIN_DISTANCE_FAST)
+    return cand_level_sampler(h, node_level) >= 0;
+  return false;
+}
+
+// MIN_DISTANCE on a node that spans GPUs: accepted points near a shard face are exchanged, the point of the
+// higher rank loses a conflict (kernels_shard.cu).  Collective: every rank calls it once per spanning level
+// that is sampled, m == nullptr when it has no points there.
+int
+resolve_shard_faces(swgpu_tiler* h, const SwMinDistArgs* m)
+{
+  cudaStream_t s = h->stream;
+  u64 n_mine = 0;
+  const u64 count = m ? m->count : 0;
+  unsigned char* state = static_cast<unsigned char*>(h->md.state.p);
+  if (count) {
+    CK(h->face_flags.ensure(count * 4));
+    CK(h->face_offs.ensure((count + 1) * 8));
+    CK(h->face_scan.ensure(scan_scratch_words(count) * 8));
+    const double reach = std::sqrt(m->threshold) * (1.0 + 1e-6);
+    launch_face_flag(m->in_idx, m->pos_sorted, state, count, h->bounds, reach, h->face_first_prefix, h->face_n_ranks,
+                     h->face_rank, h->face_flags.as<u32>(), s);
+    launch_exclusive_scan_u32(h->face_flags.as<u32>(), count, h->face_offs.as<u64>(), h->face_scan.as<u64>(), s);
+    h->stats.kernel_launches += 4;
+    CK(cudaGetLastError());
+    const int rc = read_store_vals(h, h->face_offs.as<u64>() + count, nullptr);
+    if (rc)
+      return rc;
+    n_mine = h->h_scalars->store_vals[0];
+    CK(h->face_rec.ensure(std::max<u64>(n_mine, 1) * sizeof(SwFaceRecord)));
+    CK(h->face_src.ensure(std::max<u64>(n_mine, 1) * 4));
+    launch_face_collect(m->in_key, m->in_idx, m->pos_sorted, count, h->face_flags.as<u32>(), h->face_offs.as<u64>(),
+                        h->face_rec.as<SwFaceRecord>(), h->face_src.as<u32>(), s);
+    h->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+  } else {
+    CK(h->face_rec.ensure(sizeof(SwFaceRecord)));
+  }
+  void* all = nullptr;
+  uint64_t bytes[SW_MAX_RANKS] = {};
+  if (h->face_fn(h->face_ctx, h->face_rec.p, n_mine * sizeof(SwFaceRecord), &all, bytes, s) != 0)
+    return fail(h, SW_ERR_COLLECTIVE, "the caller's all-gather hook failed (shard faces)");
+  h->face_points_sent += n_mine;
+  if (!n_mine || !h->face_rank)
+    return SW_OK;
+  SwFaceRanks fr{};
+  for (u32 r = 0; r < h->face_n_ranks; ++r)
+    fr.first[r + 1] = fr.first[r] + bytes[r] / sizeof(SwFaceRecord);
+  if (fr.first[h->face_rank] == 0)
+    return SW_OK; // no lower rank has points near a face
+  launch_face_resolve(h->face_rec.as<SwFaceRecord>(), h->face_src.as<u32>(), (u32)n_mine,
+                      static_cast<const SwFaceRecord*>(all), fr, h->face_rank, m->cell_levels, m->node_levels,
+                      m->threshold, state, s);
+  h->stats.kernel_launches += 1;
+  CK(cudaGetLastError());
+  return SW_OK;
+}
+
 // One sampling level over the list [in_key, in_idx) of `count` points whose nodes have `levels`
 // levels (reference node level = levels - 1).  Appends the selected points to the output arrays
 // and, if rem_key != nullptr, writes the remainder list.
@@ -522,6 +603,11 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
         h->stats.min_distance_rounds += rounds;
         h->stats.kernel_launches += launches;
         h->stats.bytes_traffic += bytes;
+        if (spans_shards(h, levels) && h->face_fn) {
+          rc = resolve_shard_faces(h, &m);
+          if (rc)
+            return rc;
+        }
         reads_positions = true;
         a.sel = static_cast<const unsigned char*>(h->md.state.p);
         break;
@@ -783,6 +869,11 @@ run_batch(swgpu_tiler* h)
         rc = exchange_node_counts(h, in_key, 0, levels);
         if (rc)
           return rc;
+        if (h->face_fn && level_uses_min_distance(h, node_level)) {
+          rc = resolve_shard_faces(h, nullptr);
+          if (rc)
+            return rc;
+        }
       }
       continue;
     }
@@ -815,7 +906,13 @@ run_finalize(swgpu_tiler* h)
   if (h->prm.tiling != SW_FAST || h->finalized)
     return SW_OK;
   const int S = h->start_level;
-  if (h->chunks.empty()) { // empty shard
+  if (h->chunks.empty()) { // empty shard: only the collectives of the spanning levels
+    for (int lv = S - 1; lv >= 0; --lv)
+      if (spans_shards(h, lv) && h->face_fn && level_uses_min_distance(h, lv - 1)) {
+        const int rc = resolve_shard_faces(h, nullptr);
+        if (rc)
+          return rc;
+      }
     h->finalized = true;
     return SW_OK;
   }
@@ -847,16 +944,6 @@ run_finalize(swgpu_tiler* h)
 // =============================================================================================
 // multi-batch mode: TilingAlgorithmV1 / V3 over several batches against a node store in HBM
 // =============================================================================================
-int
-read_store_vals(swgpu_tiler* h, const u64* a, const u64* b)
-{
-  CK(cudaMemcpyAsync(&h->h_scalars->store_vals[0], a, 8, cudaMemcpyDeviceToHost, h->stream));
-  if (b)
-    CK(cudaMemcpyAsync(&h->h_scalars->store_vals[1], b, 8, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  return SW_OK;
-}
-
 // The selection of one sweep level (the last chunk) replaces what the visited nodes stored; every other node of
 // the level keeps its points.  Table and id pool are rebuilt in node-index order.
 int
@@ -1318,6 +1405,9 @@ swgpu_destroy(swgpu_handle h)
     h->list_key[i].release();
     h->list_idx[i].release();
   }
+  DevBuf* face_bufs[] = { &h->face_flags, &h->face_offs, &h->face_scan, &h->face_rec, &h->face_src };
+  for (DevBuf* b : face_bufs)
+    b->release();
   DevBuf* st_bufs[] = { &h->st_slot, &h->st_cnt,  &h->st_boff,   &h->st_scan, &h->st_gcount, &h->st_lo,    &h->st_found,
                         &h->st_cumf, &h->st_nidx, &h->st_ncnt,   &h->st_nflags, &h->st_nsrc, &h->st_nfirst, &h->st_nids };
   for (DevBuf* b : st_bufs)
@@ -1910,9 +2000,13 @@ swgpu_max_shard_levels(swgpu_handle h, uint32_t* shard_levels)
       depth = std::min(6, cells ? (int)std::log2(cells) : 0);
       break;
     }
-    default: // MIN_DISTANCE: no cell structure; nodes above the shard depth are sampled per shard
-      depth = 6;
+    default: { // MIN_DISTANCE: no cell structure; nodes above the shard depth are sampled per shard and the
+               // shard faces resolved afterwards (swgpu_set_shard_faces), which needs shard subtrees that are at
+               // least one spacing wide
+      const double ratio = root_extent_x(h) / ((double)h->prm.spacing_at_root * (1.0 + 1e-6));
+      depth = std::min(6, ratio >= 1.0 ? (int)std::floor(std::log2(ratio)) : 0);
       break;
+    }
   }
   *shard_levels = (uint32_t)std::max(depth, 0);
   return SW_OK;
@@ -1991,6 +2085,28 @@ swgpu_set_shard(swgpu_handle h, uint32_t shard_levels, int32_t start_level, swgp
   h->allreduce = shard_levels ? allreduce : nullptr;
   h->allreduce_ctx = allreduce_ctx;
   h->global_ids = shard_levels ? reinterpret_cast<const u32*>(global_ids_device) : nullptr;
+  return SW_OK;
+}
+
+int
+swgpu_set_shard_faces(swgpu_handle h, const uint32_t* first_prefix, uint32_t n_ranks, uint32_t rank,
+                      swgpu_allgatherv_fn allgatherv, void* ctx)
+{
+  if (!h)
+    return SW_ERR_INVALID_ARGUMENT;
+  if (!allgatherv) {
+    h->face_fn = nullptr;
+    h->face_ctx = nullptr;
+    return SW_OK;
+  }
+  if (!first_prefix || n_ranks == 0 || n_ranks > SWGPU_MAX_RANKS || rank >= n_ranks)
+    return SW_ERR_INVALID_ARGUMENT;
+  for (u32 r = 0; r <= n_ranks; ++r)
+    h->face_first_prefix[r] = first_prefix[r];
+  h->face_n_ranks = n_ranks;
+  h->face_rank = rank;
+  h->face_fn = allgatherv;
+  h->face_ctx = ctx;
   return SW_OK;
 }
 

@@ -251,6 +251,11 @@ class ShardedTiler:
         # device scratch owned here (torch tensors): histogram, node-count exchange buffer
         self._bins = torch.zeros(8 ** COARSE_LEVELS, dtype=torch.int32, device=self.device)
         self._hook = native.ALLREDUCE_FN(self._allreduce_hook)  # keep the callback object alive
+        self._face_hook = native.ALLGATHERV_FN(self._allgatherv_hook)
+        self._face_keep = None
+        # MIN_DISTANCE on nodes that span shards: "faces" = per-shard greedy + conflict resolution across the shard
+        # faces (min-spacing invariant holds on the merged node); "none" = per-shard greedy only (round-1 behaviour)
+        self.min_distance_faces = "faces"
         self._keep = {}
         self._views = {}
         self.last = {}
@@ -263,10 +268,22 @@ class ShardedTiler:
         self._peer = None  # dict(cap, xyz, ids, xyz_ptrs, ids_ptrs, handles)
         self._peer_failed = None
         self._tiny = None
+        self._stream_handle = 0
 
     # -- plumbing -----------------------------------------------------------------------------------
     def set_stream(self, cuda_stream_handle):
+        """The stream of the library kernels AND of every torch-side step of the exchange (histogram reset,
+        all-gather, barrier all-reduce, all-to-all, the all-reduce hook): they run in one stream order."""
         self.tiler.set_stream(cuda_stream_handle)
+        self._stream_handle = int(cuda_stream_handle)
+
+    def _stream_ctx(self, handle=None):
+        """torch.cuda.stream context of the handle's stream (0 = the device's default stream)."""
+        torch = self._torch
+        h = self._stream_handle if handle is None else int(handle or 0)
+        if h:
+            return torch.cuda.stream(torch.cuda.ExternalStream(h, device=self.device))
+        return torch.cuda.stream(torch.cuda.default_stream(self.device))
 
     def enable_timing(self, on=True):
         self.tiler.enable_timing(on)
@@ -288,12 +305,52 @@ class ShardedTiler:
             if t is None:  # the library's counter buffer is stable: wrap it once, no copy
                 t = self._torch.as_tensor(_DeviceArray(ptr, int(count)), device=self.device)
                 self._views[key] = t
-            self.comm.all_reduce_sum(t)
+            with self._stream_ctx(stream):  # the library's stream: ordered after its counter kernel
+                self.comm.all_reduce_sum(t)
             return 0
         except Exception:  # never let an exception cross the C boundary
             import traceback
             traceback.print_exc()
             return 1
+
+    def _allgatherv_hook(self, ctx, send_ptr, send_bytes, recv_ptr_out, recv_bytes_out, stream):
+        """swgpu_allgatherv_fn: gathers `send_bytes` bytes of every rank in rank order into a buffer owned here."""
+        try:
+            torch = self._torch
+            n = int(send_bytes)
+            with self._stream_ctx(stream):
+                mine = torch.tensor([n], dtype=torch.int64, device=self.device)
+                sizes = [int(x) for x in self.comm.all_gather(mine).flatten().cpu().tolist()]
+                width = max(max(sizes), 8)
+                pad = torch.zeros(width, dtype=torch.uint8, device=self.device)
+                if n:
+                    pad[:n] = torch.as_tensor(_DeviceBytes(send_ptr, n), device=self.device)
+                gathered = self.comm.all_gather(pad)  # (world, width)
+                out = torch.empty(max(sum(sizes), 8), dtype=torch.uint8, device=self.device)
+                off = 0
+                for r, sz in enumerate(sizes):
+                    if sz:
+                        out[off:off + sz] = gathered[r, :sz]
+                    off += sz
+                self._face_keep = out  # valid until the next call
+            recv_ptr_out[0] = out.data_ptr()
+            for r, sz in enumerate(sizes):
+                recv_bytes_out[r] = sz
+            self.last_face_bytes = self.__dict__.get("last_face_bytes", 0) + n
+            return 0
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def _set_shard(self, shard_levels, start_level, ids_ptr, first_prefix):
+        t, lib = self.tiler, self.tiler._lib
+        t._check(lib.swgpu_set_shard(t._h, shard_levels, int(start_level), self._hook, None, C.c_void_p(ids_ptr)))
+        if self.min_distance_faces == "faces" and self.sampling.startswith("MIN_DISTANCE"):
+            t._check(lib.swgpu_set_shard_faces(t._h, C.c_void_p(first_prefix.ctypes.data), self.comm.world,
+                                               self.comm.rank, self._face_hook, None))
+        else:
+            t._check(lib.swgpu_set_shard_faces(t._h, None, 0, 0, native.ALLGATHERV_FN(), None))
 
     def _peer_wanted(self):
         if self.exchange == "nccl" or self.comm.world < 2 or not hasattr(self.comm, "peer_buffers"):
@@ -322,6 +379,10 @@ class ShardedTiler:
 
     # -- the two calls of TilingAlgorithmBase --------------------------------------------------------
     def build_execution_graph(self, xyz, id_base=None):
+        with self._stream_ctx():
+            return self._build_execution_graph(xyz, id_base)
+
+    def _build_execution_graph(self, xyz, id_base=None):
         torch = self._torch
         t, lib, comm = self.tiler, self.tiler._lib, self.comm
         n = xyz.numel() // 3
@@ -397,8 +458,7 @@ class ShardedTiler:
             comm.all_reduce_sum(self._tiny)
             m = int(recv_totals[comm.rank])
             mark("barrier")
-            t._check(lib.swgpu_set_shard(t._h, shard_levels, int(start_level), self._hook, None,
-                                         C.c_void_p(pk["ids_ptrs"][comm.rank] if m else 0)))
+            self._set_shard(shard_levels, start_level, pk["ids_ptrs"][comm.rank] if m else 0, first_prefix)
             self._keep = {"xyz": pk["xyz"][:m * 24].view(torch.float64).view(m, 3),
                           "ids": pk["ids"][:m * 4].view(torch.int32)}
             t._check(lib.swgpu_index_batch_device(t._h, C.c_void_p(pk["xyz_ptrs"][comm.rank] if m else 0), m))
@@ -432,8 +492,7 @@ class ShardedTiler:
         m = int(recv_xyz.shape[0])
         mark("all_to_all")
         # 6. the single-GPU pipeline on the shard
-        t._check(lib.swgpu_set_shard(t._h, shard_levels, int(start_level), self._hook, None,
-                                     C.c_void_p(recv_ids.data_ptr() if m else 0)))
+        self._set_shard(shard_levels, start_level, recv_ids.data_ptr() if m else 0, first_prefix)
         self._keep = {"xyz": recv_xyz, "ids": recv_ids}
         t._check(lib.swgpu_index_batch_device(t._h, C.c_void_p(recv_xyz.data_ptr() if m else 0), m))
         mark("tile")
@@ -472,6 +531,14 @@ class ShardedTiler:
     def shard_positions(self):
         """The received (shard-resident) positions and their global ids."""
         return self._keep.get("xyz"), self._keep.get("ids")
+
+
+class _DeviceBytes:
+    """__cuda_array_interface__ view of `count` bytes at a raw device pointer (no copy)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
 
 
 class _DeviceArray:

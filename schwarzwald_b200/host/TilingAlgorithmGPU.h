@@ -12,8 +12,24 @@
 //   TilingAlgorithmV3::finalize                tiling/TilingAlgorithms.cpp:1239-1248, 1717-1784
 //   tile_terminal_node / tile_internal_node    the persist_points + increment_progress calls at
 //                                              :232-240 and :330-345
-// Scope: the single-batch regime (internal_cache_size >= number of points).  A second batch throws,
-// because merging with persisted nodes (TilingAlgorithms.cpp:50-109) is not part of this library.
+//   tile_node with cached points               :351-492 / read_pnts_from_disk :50-109 (several batches)
+// Batches: Tiler::run hands over at most internal_cache_size points per call.  A first batch that is shorter
+// than that is the whole cloud: it runs through the single-batch pipeline and is handed to the sink at once.
+// A full first batch may be followed by more: the library then keeps every node's points in device memory
+// (swgpu_set_multi_batch), later batches are merged with them exactly like tile_node does with the points it
+// reads back from the persistence, and the FINAL content of every node is handed to the sink once, in
+// finalize() — the reference rewrites a node's file on every visit (PointsPersistence.h:23-31 "overwrites"),
+// so the files end up the same.  The adapter keeps a host copy of every batch (all attributes) for that
+// hand-off, because Tiler reuses its two PointBuffers (process/Tiler.h:135).
+//
+// Lossy sinks (LAS / LAZ / ENTWINE_*: PointsPersistence::is_lossless() == false).  Where the reference READS
+// POINTS BACK from the persistence it sees quantised, clamped positions and re-sorts them: reconstruct_single_node
+// (FAST, TilingAlgorithms.cpp:1661-1691) and read_pnts_from_disk (several batches, :50-109).  This adapter samples
+// those nodes from the original doubles still held in device memory, so for FAST or multi-batch runs into a
+// lossy sink the reconstructed / revisited nodes can differ from the reference's in points whose quantised
+// position changes a cell winner (the nodes at and below the start level of a single-batch run are identical).
+// The adapter says so once on stderr, or throws when constructed with refuse_lossy_read_back = true.
+// Lossless sinks (3DTILES, BINARY, in-memory) are bit-identical in every mode.
 #pragma once
 
 #include "swgpu_tiler.hpp"
@@ -24,6 +40,7 @@
 #include "tiling/Sampling.h"
 #include "tiling/TilingAlgorithms.h"
 
+#include <cstdio>
 #include <memory>
 #include <optional>
 #include <string>
@@ -36,9 +53,11 @@ struct TilingAlgorithmGPU : TilingAlgorithmBase
                      ProgressReporter* progress_reporter,
                      PointsPersistence& persistence,
                      TilerMetaParameters meta_parameters,
-                     int cuda_device = 0)
+                     int cuda_device = 0,
+                     bool refuse_lossy_read_back = false)
     : TilingAlgorithmBase(sampling_strategy, progress_reporter, persistence, meta_parameters)
     , _cuda_device(cuda_device)
+    , _refuse_lossy_read_back(refuse_lossy_read_back)
   {}
 
   std::pair<tf::Task, tf::Task> build_execution_graph(util::Range<PointBuffer::PointIterator> points,
@@ -49,40 +68,66 @@ struct TilingAlgorithmGPU : TilingAlgorithmBase
     // one task, like the single-threaded sort task of V1 (TilingAlgorithms.cpp:600-604); the GPU does
     // index + sort + every sampling level inside it
     auto task = tf.emplace([this, points, bounds, num_indexing_threads]() mutable {
-      if (_batches_done++)
-        throw std::runtime_error{ "TilingAlgorithmGPU: only single-batch runs are supported; raise "
-                                  "--internal-cache-size to the number of points" };
-      _root_bounds = bounds;
-      const double bmin[3] = { bounds.min.x, bounds.min.y, bounds.min.z };
-      const double bmax[3] = { bounds.max.x, bounds.max.y, bounds.max.z };
-      _tiler = std::make_unique<swgpu::Tiler>(sampling_enum(),
-                                              _meta_parameters.tiling_strategy == TilingStrategy::Fast ? SW_FAST
-                                                                                                       : SW_ACCURATE,
-                                              _meta_parameters.spacing_at_root,
-                                              _meta_parameters.max_depth,
-                                              _meta_parameters.max_points_per_node,
-                                              bmin,
-                                              bmax,
-                                              num_indexing_threads,
-                                              _cuda_device);
-      _points.emplace(points);
       const auto n = static_cast<uint64_t>(points.size());
+      if (!_batches_done++) {
+        _root_bounds = bounds;
+        const double bmin[3] = { bounds.min.x, bounds.min.y, bounds.min.z };
+        const double bmax[3] = { bounds.max.x, bounds.max.y, bounds.max.z };
+        _tiler = std::make_unique<swgpu::Tiler>(sampling_enum(),
+                                                _meta_parameters.tiling_strategy == TilingStrategy::Fast ? SW_FAST
+                                                                                                         : SW_ACCURATE,
+                                                _meta_parameters.spacing_at_root,
+                                                _meta_parameters.max_depth,
+                                                _meta_parameters.max_points_per_node,
+                                                bmin,
+                                                bmax,
+                                                num_indexing_threads,
+                                                _cuda_device);
+        // a full batch may be followed by more (Tiler::run fills internal_cache_size points per batch)
+        _multi_batch = n >= _meta_parameters.internal_cache_size;
+        if (_multi_batch)
+          _tiler->set_multi_batch(true);
+        if (!_persistence.is_lossless() &&
+            (_multi_batch || _meta_parameters.tiling_strategy == TilingStrategy::Fast)) {
+          const char* msg = "TilingAlgorithmGPU: the output format is lossy; nodes the reference would re-read from "
+                            "disk (FAST reconstruction, later batches) are sampled from the original positions "
+                            "instead of the quantised ones";
+          if (_refuse_lossy_read_back)
+            throw std::runtime_error{ msg };
+          std::fprintf(stderr, "warning: %s\n", msg);
+        }
+      } else if (!_multi_batch) {
+        throw std::runtime_error{ "TilingAlgorithmGPU: a batch followed a batch shorter than internal_cache_size" };
+      }
       // PointBuffer::positions() is a std::vector<Vector3<double>>: AoS x,y,z doubles (PointBuffer.h:291)
       double* xyz = n ? &(*std::begin(points)).position().x : nullptr;
       _tiler->index_batch(xyz, n); // clamps outliers in place, as index_point does
-      // ACCURATE is complete here; FAST still owes the reconstructed upper levels (finalize)
-      if (_meta_parameters.tiling_strategy != TilingStrategy::Fast)
-        hand_off(/*count_progress=*/true);
+      if (_multi_batch) {
+        // keep the batch (positions after clamping, every attribute) for the hand-off in finalize()
+        std::vector<PointBuffer::PointReference> refs(std::begin(points), std::end(points));
+        _stored_points.append_buffer(PointBuffer{ gsl::span<PointBuffer::PointReference>{ refs.data(), refs.size() } });
+        // every point of the batch ends up in exactly one node (TilingAlgorithms.cpp:238-240, 336-345)
+        if (_progress_reporter)
+          _progress_reporter->increment_progress<size_t>(progress::INDEXING, n);
+        return;
+      }
+      // a batch shorter than internal_cache_size is the only one: FAST's reconstruction of the upper levels
+      // (TilingAlgorithmV3::finalize) runs right here, while the caller's PointBuffer is still alive
+      _tiler->finalize();
+      hand_off(std::begin(points), /*count_progress=*/true);
     });
     return { task, task };
   }
 
   void finalize(const AABB& bounds) override
   {
-    if (!_tiler || _meta_parameters.tiling_strategy != TilingStrategy::Fast)
+    if (!_tiler)
       return;
-    _tiler->finalize();
-    hand_off(/*count_progress=*/true);
+    if (_multi_batch) {
+      _tiler->finalize();
+      hand_off(std::begin(_stored_points), /*count_progress=*/false);
+      return;
+    }
   }
 
 private:
@@ -109,13 +154,12 @@ private:
 
   // The per-node persist_points calls of tile_terminal_node / tile_internal_node /
   // reconstruct_single_node, driven from the node table instead of the recursion.
-  void hand_off(bool count_progress)
+  void hand_off(PointBuffer::PointIterator first_point, bool count_progress)
   {
     const auto result = _tiler->result();
     const double rmin[3] = { _root_bounds.min.x, _root_bounds.min.y, _root_bounds.min.z };
     const double rmax[3] = { _root_bounds.max.x, _root_bounds.max.y, _root_bounds.max.z };
     std::vector<PointBuffer::PointReference> refs;
-    const auto first_point = std::begin(*_points);
     for (const sw_node& node : result.nodes) {
       refs.clear();
       refs.reserve(node.count);
@@ -133,8 +177,10 @@ private:
   }
 
   int _cuda_device;
+  bool _refuse_lossy_read_back;
   size_t _batches_done = 0;
+  bool _multi_batch = false;
+  PointBuffer _stored_points; // multi-batch: host copy of every batch, indexed by global point id
   AABB _root_bounds;
-  std::optional<util::Range<PointBuffer::PointIterator>> _points; // PointIterator has no default ctor
   std::unique_ptr<swgpu::Tiler> _tiler;
 };

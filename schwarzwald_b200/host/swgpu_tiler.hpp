@@ -128,6 +128,10 @@ public:
   // PointBuffer positions of the last batch (n x 3 doubles, original order, after index_point's clamping)
   void positions(double* xyz_host) { check(swgpu_get_positions(_handle, xyz_host)); }
   void finalize() { check(swgpu_finalize(_handle)); }
+  // Multi-batch mode: every later index_batch is one build_execution_graph against what the earlier batches
+  // stored (tile_node with cached points, core/tiling/TilingAlgorithms.cpp:351-492); result() then returns the
+  // final content of every node with GLOBAL point ids (points of earlier batches + index in the batch).
+  void set_multi_batch(bool on) { check(swgpu_set_multi_batch(_handle, on ? 1 : 0)); }
 
   struct Result
   {

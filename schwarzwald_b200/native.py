@@ -63,6 +63,9 @@ class SwgpuStats(C.Structure):
 
 # swgpu_allreduce_u32_fn: int (*)(void* ctx, uint32_t* device_counters, uint64_t count, void* cuda_stream)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
+# swgpu_allgatherv_fn: int (*)(void* ctx, const void* send, uint64_t send_bytes, void** recv, uint64_t* recv_bytes, void* stream)
+ALLGATHERV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                            C.c_void_p)
 MAX_RANKS = 16
 PREFIX_BINS = 262144
 
@@ -103,6 +106,7 @@ SYMBOLS = [
     ("swgpu_partition_to_peers_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
                                                   C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swgpu_set_shard", C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, ALLREDUCE_FN, C.c_void_p, C.c_void_p]),
+    ("swgpu_set_shard_faces", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, ALLGATHERV_FN, C.c_void_p]),
     ("swgpu_enable_timing", C.c_int, [C.c_void_p, C.c_int]),
     ("swgpu_get_stats", C.c_int, [C.c_void_p, C.POINTER(SwgpuStats)]),
 ]

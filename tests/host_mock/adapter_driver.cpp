@@ -6,6 +6,7 @@
 // Prints one line per persisted node: "<name> <count> <fnv1a of the stored positions>".
 #include "TilingAlgorithmGPU.h"
 
+#include <algorithm>
 #include <cinttypes>
 #include <cstdio>
 #include <cstring>
@@ -26,7 +27,8 @@ int
 main(int argc, char** argv)
 {
   if (argc < 7) {
-    std::fprintf(stderr, "usage: adapter_driver n seed SAMPLING TILING max_points_per_node indexing_threads\n");
+    std::fprintf(stderr,
+                 "usage: adapter_driver n seed SAMPLING TILING max_points_per_node indexing_threads [batch_size]\n");
     return 2;
   }
   const size_t n = std::strtoull(argv[1], nullptr, 10);
@@ -34,6 +36,8 @@ main(int argc, char** argv)
   const std::string sampling = argv[3], tiling = argv[4];
   const size_t max_points = std::strtoull(argv[5], nullptr, 10);
   const uint32_t threads = static_cast<uint32_t>(std::strtoul(argv[6], nullptr, 10));
+  // internal_cache_size: Tiler::run hands the algorithm at most this many points per batch (Tiler.cpp:499-527)
+  const size_t batch = argc > 7 ? std::strtoull(argv[7], nullptr, 10) : 0;
 
   std::vector<Vector3<double>> positions(n);
   for (auto& p : positions) { // xorshift64*, coordinates on a millimetre lattice in [0, 100) m
@@ -53,7 +57,7 @@ main(int argc, char** argv)
   meta.spacing_at_root = static_cast<float>(bounds.extent().length() / 250.0); // TilerProcess.cpp:598-604
   meta.max_depth = 100;
   meta.max_points_per_node = max_points;
-  meta.internal_cache_size = n;
+  meta.internal_cache_size = batch ? batch : n + 1;
   meta.tiling_strategy = tiling == "FAST" ? TilingStrategy::Fast : TilingStrategy::Accurate;
 
   // the switch of TilerProcess::make_sampling_strategy (core/process/TilerProcess.cpp:491-516)
@@ -69,10 +73,17 @@ main(int argc, char** argv)
   PointsPersistence sink;
   try {
     TilingAlgorithmGPU algorithm(strategy, &progress, sink, meta);
-    tf::Taskflow taskflow;
-    algorithm.build_execution_graph({ std::begin(buffer), std::end(buffer) }, bounds, threads, taskflow);
-    for (auto& work : taskflow.work) // the executor
-      work();
+    const size_t step = batch ? batch : n;
+    for (size_t lo = 0; lo < n; lo += step) { // Tiler::run: one execution graph per batch, run to completion
+      // Tiler reuses its point caches: the batch lives in its own buffer that is gone after the batch
+      const size_t hi = std::min(n, lo + step);
+      std::vector<PointBuffer::PointReference> refs(std::begin(buffer) + lo, std::begin(buffer) + hi);
+      PointBuffer cache{ gsl::span<PointBuffer::PointReference>{ refs.data(), refs.size() } };
+      tf::Taskflow taskflow;
+      algorithm.build_execution_graph({ std::begin(cache), std::end(cache) }, bounds, threads, taskflow);
+      for (auto& work : taskflow.work) // the executor
+        work();
+    }
     algorithm.finalize(bounds);
   } catch (const std::exception& e) {
     std::printf("EXCEPTION %s\n", e.what());

@@ -108,3 +108,38 @@ def test_adapter_end_to_end_matches_oracle(port_oracle, sampling, tiling):
     for name, ids in want.items():
         assert got[name][0] == len(ids), name
         assert got[name][1] == _fnv1a(np.ascontiguousarray(xyz[ids.astype(np.int64)]).tobytes()), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sampling,tiling", [("RANDOM_GRID", "ACCURATE"), ("GRID_CENTER", "FAST"),
+                                             ("JITTERED", "ACCURATE"), ("MIN_DISTANCE", "FAST")])
+def test_adapter_multi_batch_matches_oracle(port_oracle, sampling, tiling):
+    """internal_cache_size smaller than the cloud (the reference's default regime, executable/main.cpp:233-236):
+    the adapter feeds every batch to the device-resident node store and hands the FINAL content of every node to
+    the sink; it equals the oracle's tile_batches (tile_node with cached points, TilingAlgorithms.cpp:351-492)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if not os.path.exists(DRIVER):
+        pytest.skip("oracle/_ref/adapter_driver was not built (needs /root/reference at build time)")
+    from oracle import sworacle
+    import schwarzwald_b200 as sw
+    n, seed, max_pts, threads, batch = 40_000, 7, 300, 2, 15_000
+    out = subprocess.run([DRIVER, str(n), str(seed), sampling, tiling, str(max_pts), str(threads), str(batch)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[-1] == "PROGRESS %d of %d" % (n, n)
+    got = {}
+    for ln in lines[:-1]:
+        name, count, digest = ln.split()
+        got[name] = (int(count), int(digest, 16))
+    xyz = _driver_points(n, seed)
+    bmin, bmax = np.zeros(3), np.full(3, 100.0)
+    spacing = sw.spacing_from_diagonal_fraction(bmin, bmax)
+    params = sworacle.make_params(sampling, tiling, spacing, bmin, bmax, max_points_per_node=max_pts, concurrency=threads)
+    want = port_oracle.tile_batches(params, xyz, [15_000, 15_000, 10_000]).as_dict()
+    assert sorted(got) == sorted(want)
+    for name, ids in want.items():
+        assert got[name][0] == len(ids), name
+        assert got[name][1] == _fnv1a(np.ascontiguousarray(xyz[ids.astype(np.int64)]).tobytes()), name
