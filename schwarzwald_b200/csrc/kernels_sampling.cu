@@ -859,155 +859,171 @@ struct ArgminDesc
   u32 has_head;
 };
 
+// Layout: keys, node ranks and head / tail flags are worked out in the BLOCKED layout (thread t owns elements
+// [8t, 8t + 8) of the tile: runs are thread-local bit operations); the distances are evaluated in the STRIPED
+// layout (element j * 256 + t: coalesced id / position loads) and handed over through shared memory; the
+// segmented min-scan then runs thread-locally over 8 elements, across the 32 thread aggregates of a warp with
+// 5 shuffle steps, across the warps through shared memory and across tiles by the decoupled look-back.
 __global__ void __launch_bounds__(SWP_THREADS, 4)
 select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__ ticket)
 {
+  __shared__ u64 s_k[BLK_SLOTS]; // keys, then the distances (double bits) of the same elements
+  __shared__ u32 s_r[BLK_SLOTS]; // node rank of every element, bit 31 = its node is not sampled
+  __shared__ u64 s_prev, s_next;
   __shared__ u32 s_slot;
   __shared__ u32 s_w[SWP_WARPS];
   __shared__ ArgminDesc s_wagg[SWP_WARPS];
   __shared__ ArgminDesc s_tile_carry;
-  const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const u32 tile = take_ticket(ticket, &s_slot);
   const u64 base = (u64)tile * SW_SWEEP_TILE;
-  const u32 lt = lanemask_lt();
+  const u64 e0 = base + 8ull * tid;
   const size_t n_tiles = (size_t)((a.count + SW_SWEEP_TILE - 1) / SW_SWEEP_TILE);
   u32* flags = reinterpret_cast<u32*>(status);                            // n_tiles u32 (padded to u64)
   ArgminDesc* agg = reinterpret_cast<ArgminDesc*>(status + n_tiles);      // n_tiles x 16 B
   ArgminDesc* pfx = reinterpret_cast<ArgminDesc*>(status + 3 * n_tiles);  // n_tiles x 16 B
 
-  // ---- phase 1: keys and node heads ------------------------------------------------------------
-  u64 key[SWP_ITEMS];
-  u32 nmask[SWP_ITEMS];
-  u32 wheads = 0;
-#pragma unroll
-  for (int j = 0; j < SWP_ITEMS; ++j) {
-    const u64 i = base + item_pos(warp, lane, j);
-    bool nh = false;
-    key[j] = 0;
-    if (i < a.count) {
-      key[j] = a.in_key[i] & SW_KEY_MASK;
-      nh = (i == 0) || ((key[j] >> a.node_shift) != ((a.in_key[i - 1] & SW_KEY_MASK) >> a.node_shift));
-    }
-    nmask[j] = __ballot_sync(0xffffffffu, nh);
-    wheads += __popc(nmask[j]);
-  }
-  u32 heads_total;
-  const u32 hexcl = warp_totals_exclusive(wheads, warp, lane, s_w, heads_total);
-
-  // ---- phase 2: per point head / tail flags and distance ------------------------------------------
-  ArgminVal val[SWP_ITEMS];
-  u32 hbits = 0, tbits = 0; // per item: this lane's element is a segment head / tail
+  // ---- phase 0 (blocked): node ranks, which nodes are sampled, cell heads and tails --------------------------
+  u32 hbits = 0, tbits = 0, abits = 0; // per element: starts a cell, ends a cell, its node is sampled
   {
-    u32 run = a.tile_rank0[tile] + hexcl;
+    u64 k[BLK_ITEMS];
+    u64 prev;
+    if (tid == 0)
+      s_next = (base + SW_SWEEP_TILE < a.count) ? (a.in_key[base + SW_SWEEP_TILE] & SW_KEY_MASK) : ~0ull;
+    load_keys_blocked(a.in_key, base, a.count, s_k, &s_prev, k, prev); // keys past the end read as ~0
+    const u64 next = (tid + 1 < SWP_THREADS) ? s_k[9 * (tid + 1)] : s_next;
+    const u32 nvalid = e0 >= a.count ? 0u : (a.count - e0 < 8 ? (u32)(a.count - e0) : 8u);
+    const u32 valid = (1u << nvalid) - 1u;
+    u32 nh, unused;
+    head_bits2(k, prev, a.node_shift, a.node_shift, e0 == 0, nh, unused);
+    nh &= valid;
+    u32 hexcl;
+    block_scan_packed(__popc(nh), s_w, hexcl);
+    u32 rank = a.tile_rank0[tile] + hexcl - 1u; // node of the element before my first one
+    bool active = true;
+    int es = a.node_shift; // effective shift of the selection cells of the current node
 #pragma unroll
-    for (int j = 0; j < SWP_ITEMS; ++j) {
-      const u64 i = base + item_pos(warp, lane, j);
-      const u32 node_rank = run + __popc(nmask[j] & (lt | (1u << lane))) - 1;
-      run += __popc(nmask[j]);
-      val[j].d = 0.0;
-      val[j].pos = (u32)i;
-      bool head = true, tail = true;
-      if (i < a.count) {
-        bool active = true;
-        if (a.allow_take_all) {
-          const u32 cnt = node_point_count(a.node_start, a.node_gcount, node_rank);
-          active = (u64)cnt > a.max_points_per_node;
-        }
-        if (active) {
-          const u64 k = key[j];
-          const u32 idx = a.in_idx ? a.in_idx[i] : (u32)i;
-          const double p[3] = { a.pos_sorted[3 * (u64)idx], a.pos_sorted[3 * (u64)idx + 1],
-                                a.pos_sorted[3 * (u64)idx + 2] };
-          double t[3];
-          int cshift;
-          const SwArgminNode* nd = a.nodes + node_rank;
-          if (a.sampling == SW_JITTERED) {
-            JitterNode jn;
-            jn.shift = nd->shift;
-            jn.levels = nd->levels;
-            jn.cells = nd->cells;
-            jn.node_min[0] = nd->mn[0];
-            jn.node_min[1] = nd->mn[1];
-            jn.node_min[2] = nd->mn[2];
-            jn.grid_cell_size = nd->grid_cell_size;
-            jn.permutation_cell_size = nd->permutation_cell_size;
-            cshift = jn.shift;
-            jitter_target(k, a, jn, t);
-          } else {
-            cshift = a.cell_shift;
-            double mn[3], mx[3];
-            if (a.cand_level >= a.node_level) { // the usual case: continue from the node's bounds
-              mn[0] = nd->mn[0];
-              mn[1] = nd->mn[1];
-              mn[2] = nd->mn[2];
-              mx[0] = nd->mx[0];
-              mx[1] = nd->mx[1];
-              mx[2] = nd->mx[2];
-              bounds_continue(k, a.node_level + 1, a.cand_level + 1, mn, mx);
-            } else { // spacing coarser than the node: the candidate cell is an ancestor of the node
-              bounds_from_key(k, a.cand_level + 1, a.bounds, mn, mx);
-            }
-            // AABB::getCenter = min + extent()/2 (math/AABB.h:70)
-            t[0] = mn[0] + (mx[0] - mn[0]) * 0.5;
-            t[1] = mn[1] + (mx[1] - mn[1]) * 0.5;
-            t[2] = mn[2] + (mx[2] - mn[2]) * 0.5;
-          }
-          val[j].d = squared_distance(p, t);
-          const bool nh = (nmask[j] >> lane) & 1u;
-          if (!nh) {
-            const u64 pk = a.in_key[i - 1] & SW_KEY_MASK;
-            head = (k >> cshift) != (pk >> cshift);
-          }
-          if (i + 1 < a.count) {
-            const u64 nk = a.in_key[i + 1] & SW_KEY_MASK;
-            tail = ((nk >> a.node_shift) != (k >> a.node_shift)) || ((nk >> cshift) != (k >> cshift));
-          }
-        }
+    for (int j = 0; j < BLK_ITEMS; ++j) {
+      const bool is_valid = (valid >> j) & 1u;
+      const bool node_head = (nh >> j) & 1u;
+      if (node_head)
+        ++rank;
+      if (is_valid && (node_head || j == 0)) {
+        active = true;
+        if (a.allow_take_all)
+          active = (u64)node_point_count(a.node_start, a.node_gcount, rank) > a.max_points_per_node;
+        const int cs = (a.sampling == SW_JITTERED) ? a.nodes[rank].shift : a.cell_shift;
+        es = cs < a.node_shift ? cs : a.node_shift;
       }
-      hbits |= (head ? 1u : 0u) << j;
-      tbits |= (tail ? 1u : 0u) << j;
+      const u64 x_prev = k[j] ^ (j ? k[j - 1] : prev);
+      const u64 x_next = k[j] ^ (j + 1 < BLK_ITEMS ? k[j + 1] : next);
+      const bool first = (e0 + j == 0);
+      const bool head = !active || node_head || first || ((x_prev >> es) != 0ull);
+      const bool tail = !active || ((x_next >> es) != 0ull); // keys past the end differ in bit 63
+      if (is_valid) {
+        hbits |= (head ? 1u : 0u) << j;
+        tbits |= (tail ? 1u : 0u) << j;
+        abits |= (active ? 1u : 0u) << j;
+      } else {
+        hbits |= 1u << j; // padding behaves like a run of its own
+      }
+      s_r[BLK_PAD(8 * tid + j)] = rank | (active ? 0u : 0x80000000u);
     }
   }
-  // ---- phase 3: segmented inclusive min-scan inside the warp (items in order, lanes in order) -----
-  // seen[j]: a head exists between the start of the warp's range and this element (inclusive)
-  u32 seen_bits = 0;
-  ArgminVal carry;
-  carry.d = 0.0;
-  carry.pos = 0;
-  bool carry_valid = false; // false until the warp has processed its first element
-  bool warp_seen = false;
+  __syncthreads();
+
+  // ---- phase 1 (striped): squared distance of every sampled point to the target of its cell ------------------
 #pragma unroll
   for (int j = 0; j < SWP_ITEMS; ++j) {
-    ArgminVal v = val[j];
-    bool f = (hbits >> j) & 1u;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      ArgminVal up;
-      up.d = __shfl_up_sync(0xffffffffu, v.d, o);
-      up.pos = __shfl_up_sync(0xffffffffu, v.pos, o);
-      const bool fup = __shfl_up_sync(0xffffffffu, (int)f, o) != 0;
-      if (lane >= (u32)o) {
-        if (!f)
-          v = argmin_op(up, v);
-        f = f || fup;
+    const u32 p = j * SWP_THREADS + tid;
+    const u64 i = base + p;
+    double d = 0.0;
+    if (i < a.count) {
+      const u32 r = s_r[BLK_PAD(p)];
+      if (!(r & 0x80000000u)) {
+        const u64 k = s_k[BLK_PAD(p)];
+        const u32 idx = a.in_idx ? a.in_idx[i] : (u32)i;
+        const double pt[3] = { a.pos_sorted[3 * (u64)idx], a.pos_sorted[3 * (u64)idx + 1],
+                               a.pos_sorted[3 * (u64)idx + 2] };
+        double t[3];
+        const SwArgminNode* nd = a.nodes + r;
+        if (a.sampling == SW_JITTERED) {
+          JitterNode jn;
+          jn.shift = nd->shift;
+          jn.levels = nd->levels;
+          jn.cells = nd->cells;
+          jn.node_min[0] = nd->mn[0];
+          jn.node_min[1] = nd->mn[1];
+          jn.node_min[2] = nd->mn[2];
+          jn.grid_cell_size = nd->grid_cell_size;
+          jn.permutation_cell_size = nd->permutation_cell_size;
+          jitter_target(k, a, jn, t);
+        } else {
+          double mn[3], mx[3];
+          if (a.cand_level >= a.node_level) { // the usual case: continue from the node's bounds
+            mn[0] = nd->mn[0];
+            mn[1] = nd->mn[1];
+            mn[2] = nd->mn[2];
+            mx[0] = nd->mx[0];
+            mx[1] = nd->mx[1];
+            mx[2] = nd->mx[2];
+            bounds_continue(k, a.node_level + 1, a.cand_level + 1, mn, mx);
+          } else { // spacing coarser than the node: the candidate cell is an ancestor of the node
+            bounds_from_key(k, a.cand_level + 1, a.bounds, mn, mx);
+          }
+          // AABB::getCenter = min + extent()/2 (math/AABB.h:70)
+          t[0] = mn[0] + (mx[0] - mn[0]) * 0.5;
+          t[1] = mn[1] + (mx[1] - mn[1]) * 0.5;
+          t[2] = mn[2] + (mx[2] - mn[2]) * 0.5;
+        }
+        d = squared_distance(pt, t);
       }
     }
-    // lanes before the first head of this item continue the run of the previous item
-    if (!f && carry_valid)
-      v = argmin_op(carry, v);
-    const bool seen = f || warp_seen;
-    seen_bits |= (seen ? 1u : 0u) << j;
-    val[j] = v;
-    // carry for the next item = value at lane 31
-    carry.d = __shfl_sync(0xffffffffu, v.d, 31);
-    carry.pos = __shfl_sync(0xffffffffu, v.pos, 31);
-    carry_valid = true;
-    warp_seen = __shfl_sync(0xffffffffu, (int)seen, 31) != 0;
+    s_k[BLK_PAD(p)] = (u64)__double_as_longlong(d); // the slot's key is not needed any more
   }
+  __syncthreads();
+
+  // ---- phase 2 (blocked): segmented first-arg-min ----------------------------------------------------------------
+  double d[BLK_ITEMS];
+#pragma unroll
+  for (int j = 0; j < BLK_ITEMS; ++j)
+    d[j] = __longlong_as_double((long long)s_k[9 * tid + j]);
+  // thread aggregate: running minimum of the run that is open at the end of my 8 elements
+  ArgminVal run;
+  run.d = d[0];
+  run.pos = (u32)e0;
+#pragma unroll
+  for (int j = 1; j < BLK_ITEMS; ++j) {
+    ArgminVal v;
+    v.d = d[j];
+    v.pos = (u32)(e0 + j);
+    run = ((hbits >> j) & 1u) ? v : argmin_op(run, v);
+  }
+  const bool my_head = hbits != 0;
+  // inclusive segmented scan of the thread aggregates inside the warp
+  ArgminVal inc = run;
+  bool finc = my_head;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    ArgminVal up;
+    up.d = __shfl_up_sync(0xffffffffu, inc.d, o);
+    up.pos = __shfl_up_sync(0xffffffffu, inc.pos, o);
+    const bool fup = __shfl_up_sync(0xffffffffu, (int)finc, o) != 0;
+    if (lane >= (u32)o) {
+      if (!finc)
+        inc = argmin_op(up, inc);
+      finc = finc || fup;
+    }
+  }
+  // what reaches my first element from the earlier lanes of the warp
+  ArgminVal lane_in;
+  lane_in.d = __shfl_up_sync(0xffffffffu, inc.d, 1);
+  lane_in.pos = __shfl_up_sync(0xffffffffu, inc.pos, 1);
+  const bool lane_in_cut = __shfl_up_sync(0xffffffffu, (int)finc, 1) != 0; // a head in the earlier lanes
   if (lane == 31) {
-    s_wagg[warp].d = carry.d;
-    s_wagg[warp].pos = carry.pos;
-    s_wagg[warp].has_head = warp_seen ? 1u : 0u;
+    s_wagg[warp].d = inc.d;
+    s_wagg[warp].pos = inc.pos;
+    s_wagg[warp].has_head = finc ? 1u : 0u;
   }
   __syncthreads();
 
@@ -1089,7 +1105,7 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
   }
   __syncthreads();
 
-  // ---- carry into this warp = (tile carry, previous warps), then winners -------------------------
+  // ---- carry into my first element = (tile carry, previous warps, previous lanes), then the winners ------------
   ArgminVal cin;
   cin.d = s_tile_carry.d;
   cin.pos = s_tile_carry.pos;
@@ -1104,15 +1120,28 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
       cin = argmin_op(cin, wv);
     cin_valid = true;
   }
+  if (lane > 0) {
+    if (lane_in_cut || !cin_valid)
+      cin = lane_in;
+    else
+      cin = argmin_op(cin, lane_in);
+    cin_valid = true;
+  }
+  const u32 nvalid = e0 >= a.count ? 0u : (a.count - e0 < 8 ? (u32)(a.count - e0) : 8u);
+  bool open = cin_valid; // `cur` continues a run that started before my first element
+  ArgminVal cur = cin;
 #pragma unroll
-  for (int j = 0; j < SWP_ITEMS; ++j) {
-    const u64 i = base + item_pos(warp, lane, j);
-    if (i < a.count && ((tbits >> j) & 1u)) {
-      ArgminVal v = val[j];
-      if (!((seen_bits >> j) & 1u) && cin_valid)
-        v = argmin_op(cin, v);
-      a.sel[v.pos] = 1;
-    }
+  for (int j = 0; j < BLK_ITEMS; ++j) {
+    ArgminVal v;
+    v.d = d[j];
+    v.pos = (u32)(e0 + j);
+    if (((hbits >> j) & 1u) || !open)
+      cur = v;
+    else
+      cur = argmin_op(cur, v);
+    open = true;
+    if ((u32)j < nvalid && ((tbits >> j) & 1u) && ((abits >> j) & 1u))
+      a.sel[cur.pos] = 1;
   }
 }
 
