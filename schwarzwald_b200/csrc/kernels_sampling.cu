@@ -778,37 +778,47 @@ jitter_node_setup(const double mn[3], const double mx[3], const SwArgminArgs& a,
   return err;
 }
 
+// The three permutation rows a launch needs (they depend on the node LEVEL only: start_index = 3 * (level + 1)
+// mod 16, Sampling.h:684-693) for the three table sizes, staged in shared memory: lanes index them with
+// different cells, which a __constant__ table would serialise.
+#define JIT_ROW 64
+#define JIT_TABLE_WORDS (3 * 3 * JIT_ROW) /* [size class 16 / 32 / 64][row][entry] */
+
 __device__ __forceinline__ void
-jitter_target(u64 key, const SwArgminArgs& a, const JitterNode& jn, double t[3])
+jitter_stage_tables(int node_level, u32* s_perm)
+{
+  const u32 start_index = (3u * (u32)(node_level + 1)) % 16u;
+  for (u32 e = threadIdx.x; e < JIT_TABLE_WORDS; e += blockDim.x) {
+    const u32 cls = e / (3 * JIT_ROW), row = (e / JIT_ROW) % 3, i = e % JIT_ROW;
+    const u32 t = (start_index + row) % 16u;
+    u32 v = 0;
+    if (cls == 0)
+      v = i < 16 ? PERMUTATIONS_16[t][i] : 0u;
+    else if (cls == 1)
+      v = i < 32 ? PERMUTATIONS_32[t][i] : 0u;
+    else
+      v = PERMUTATIONS_64[t][i];
+    s_perm[e] = v;
+  }
+}
+
+__device__ __forceinline__ void
+jitter_target(u64 key, const JitterNode& jn, const u32* __restrict__ s_perm, double t[3])
 {
   const u64 rel = key >> jn.shift;
   const u64 grid_mask = (1ull << (3 * jn.levels)) - 1ull;
   const u64 idx = rel & grid_mask;
-  const u64 lmask = (1ull << jn.levels) - 1ull;
-  const u64 gz = contract_bits_by_3(idx) & lmask; // OctreeNodeIndex::to_grid_index, OctreeNodeIndex.h:357-363
-  const u64 gy = contract_bits_by_3(idx >> 1) & lmask;
-  const u64 gx = contract_bits_by_3(idx >> 2) & lmask;
-  const u32 start_index = (3u * (u32)(a.node_level + 1)) % 16u;
-  const u32 t0 = start_index, t1 = (start_index + 1) % 16u, t2 = (start_index + 2) % 16u;
+  const u32 lmask = (1u << jn.levels) - 1u;
+  const u32 gz = (u32)contract_bits_by_3(idx) & lmask; // OctreeNodeIndex::to_grid_index, OctreeNodeIndex.h:357-363
+  const u32 gy = (u32)contract_bits_by_3(idx >> 1) & lmask;
+  const u32 gx = (u32)contract_bits_by_3(idx >> 2) & lmask;
+  // len = min(cells, 64) is a power of two (cells = get_prev_power_of_two): x % len == x & (len - 1)
   const u32 len = jn.cells < 64u ? jn.cells : 64u;
-  const u32 ix = (u32)((gy + gz) % len), iy = (u32)((gx + gz) % len), iz = (u32)((gx + gy) % len);
-  u32 px, py, pz;
-  if (jn.cells <= 16u) {
-    px = PERMUTATIONS_16[t0][ix];
-    py = PERMUTATIONS_16[t1][iy];
-    pz = PERMUTATIONS_16[t2][iz];
-  } else if (jn.cells <= 32u) {
-    px = PERMUTATIONS_32[t0][ix];
-    py = PERMUTATIONS_32[t1][iy];
-    pz = PERMUTATIONS_32[t2][iz];
-  } else {
-    px = PERMUTATIONS_64[t0][ix];
-    py = PERMUTATIONS_64[t1][iy];
-    pz = PERMUTATIONS_64[t2][iz];
-  }
-  px -= 1;
-  py -= 1;
-  pz -= 1;
+  const u32 ix = (gy + gz) & (len - 1u), iy = (gx + gz) & (len - 1u), iz = (gx + gy) & (len - 1u);
+  const u32* tab = s_perm + (jn.cells <= 16u ? 0u : (jn.cells <= 32u ? 1u : 2u)) * (3 * JIT_ROW);
+  const u32 px = tab[ix] - 1u;
+  const u32 py = tab[JIT_ROW + iy] - 1u;
+  const u32 pz = tab[2 * JIT_ROW + iz] - 1u;
   // target = node_min + (g * cell + p * sub), Sampling.h:735-739 (mul, mul, add, add: no FMA)
   t[0] = jn.node_min[0] + ((double)gx * jn.grid_cell_size + (double)px * jn.permutation_cell_size);
   t[1] = jn.node_min[1] + ((double)gy * jn.grid_cell_size + (double)py * jn.permutation_cell_size);
@@ -874,7 +884,10 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
   __shared__ u32 s_w[SWP_WARPS];
   __shared__ ArgminDesc s_wagg[SWP_WARPS];
   __shared__ ArgminDesc s_tile_carry;
+  __shared__ u32 s_perm[JIT_TABLE_WORDS];
   const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (a.sampling == SW_JITTERED)
+    jitter_stage_tables(a.node_level, s_perm); // visible after the barriers of phase 0
   const u32 tile = take_ticket(ticket, &s_slot);
   const u64 base = (u64)tile * SW_SWEEP_TILE;
   const u64 e0 = base + 8ull * tid;
@@ -957,7 +970,7 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
           jn.node_min[2] = nd->mn[2];
           jn.grid_cell_size = nd->grid_cell_size;
           jn.permutation_cell_size = nd->permutation_cell_size;
-          jitter_target(k, a, jn, t);
+          jitter_target(k, jn, s_perm, t);
         } else {
           double mn[3], mx[3];
           if (a.cand_level >= a.node_level) { // the usual case: continue from the node's bounds
