@@ -157,6 +157,15 @@ def captured_traffic(n_points):
     return None
 
 
+def same_config_n1(cfg_name):
+    """points/s of the SAME config on one GPU, from the committed profile of this round (None if absent)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_%s_n1.json" % cfg_name)))
+        return {"value": d["value"], "ms_per_step": d["ms_per_step"], "source": "profiles/r02_bench_%s_n1.json" % cfg_name}
+    except Exception:
+        return None
+
+
 def config_block(cfg_name, cfg, n_total, extra=None):
     """The `config` object both arms print (same keys and values for the same workload)."""
     from schwarzwald_b200 import workloads
@@ -473,8 +482,16 @@ def main():
                             return sx[torch.from_numpy(idv.astype(np.int64)).to(dev)].cpu().numpy()
                     # nodes wholly inside this shard (spanning nodes are checked by tests/test_gpu_sharded.py on
                     # the merged result)
-                    local = nodes_host[nodes_host["levels"] >= (int(tiler.last.get("shard_levels", 0)) if world > 1 else 0)]
+                    sl = int(tiler.last.get("shard_levels", 0)) if world > 1 else 0
+                    local = nodes_host[nodes_host["levels"] >= sl]
                     parity = par.min_spacing_check(xyz_of, local, ids_dev[:n_ids_local], spacing)
+                    if world > 1:  # nodes above the shard depth: the invariant on the node merged over all ranks
+                        mine = par.spanning_node_parts(xyz_of, nodes_host, ids_dev[:n_ids_local], min(sl, 3))
+                        everyone = [None] * world if rank == 0 else None
+                        dist.gather_object(mine, everyone, dst=0)
+                        if rank == 0:
+                            parity["spanning_nodes"] = par.merged_min_spacing_check(everyone, spacing)
+                            parity["ok"] = bool(parity["ok"] and parity["spanning_nodes"]["ok"])
                 else:
                     parity = par.subtree_parity(orc, sampling, tiling, spacing, bmin, bmax, conc, maxpts, sx, sids,
                                                 nodes_host, ids_dev[:n_ids_local], int(tiler.start_level()), depth=depth)
@@ -642,6 +659,10 @@ def main():
         "clocks": clocks,
         "parity": parity,
         "parity_checked": bool(parity and parity.get("checked") and parity.get("ok")),
+        "strong_scaling_base": (None if world == 1 else
+                                {"note": "N > 1 runs strong-scale BASELINE configs[2..4]; the N = 1 bench line is configs[1] "
+                                         "(another cloud and strategy), so value(N) / value(1) is NOT a scaling efficiency",
+                                 "same_config_n1": same_config_n1(cfg_name)}),
     }
     if e2e is not None:
         line["e2e"] = e2e

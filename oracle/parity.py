@@ -115,6 +115,55 @@ class _LazyIds:
         return part.cpu().numpy().view(np.uint32)
 
 
+def too_close_pairs(pts, levels, spacing_at_root):
+    """Pairs of `pts` (k, 3) closer than the spacing of a node with `levels` levels, by the reference's own test:
+    spacing_at_root / 2^levels as a double, narrowed to float and squared in float by SparseGrid (Sampling.h:446-449,
+    SparseGrid.cpp:11-14); a pair conflicts when its squared distance is < that (GridCell.cpp:41-58)."""
+    from scipy.spatial import cKDTree
+    if len(pts) < 2:
+        return 0
+    s = np.float32(float(np.float32(spacing_at_root)) / (2.0 ** int(levels)))
+    thr = float(np.float32(s * s))
+    pairs = cKDTree(pts).query_pairs(float(np.sqrt(thr)) * (1.0 + 1e-9), output_type="ndarray")
+    if not len(pairs):
+        return 0
+    d = pts[pairs[:, 0]] - pts[pairs[:, 1]]
+    d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+    return int((d2 < thr).sum())
+
+
+def spanning_node_parts(xyz_of_id, nodes, ids, max_levels, max_points=4_000_000):
+    """This rank's parts of the sampled nodes with fewer than `max_levels` levels: {(levels, index): positions}."""
+    nodes = np.asarray(nodes)
+    out, total = {}, 0
+    for k in np.nonzero((nodes["levels"] < max_levels) & ((nodes["flags"] & 3) == 0) & (nodes["count"] > 0))[0]:
+        f, c = int(nodes["first"][k]), int(nodes["count"][k])
+        if total + c > max_points:
+            continue
+        out[(int(nodes["levels"][k]), int(nodes["index"][k]))] = xyz_of_id(_ids_slice(ids, f, c))
+        total += c
+    return out
+
+
+def merged_min_spacing_check(parts_per_rank, spacing_at_root):
+    """MIN_DISTANCE on nodes that span GPUs: the min-spacing invariant on the MERGED node (all ranks' parts)."""
+    keys = sorted(set(k for parts in parts_per_rank for k in parts))
+    out = {"checked": bool(keys), "ok": True, "method": "min-spacing invariant on nodes merged over all ranks (cKDTree)",
+           "nodes": []}
+    for key in keys:
+        pieces = [parts[key] for parts in parts_per_rank if key in parts]
+        pts = np.concatenate(pieces, axis=0)
+        bad = too_close_pairs(pts, key[0], spacing_at_root)
+        out["nodes"].append({"levels": key[0], "index": key[1], "count": int(len(pts)), "ranks": len(pieces),
+                             "too_close_pairs": bad})
+        out["ok"] = out["ok"] and bad == 0
+    out["n_nodes"] = len(out["nodes"])
+    out["points"] = int(sum(n["count"] for n in out["nodes"]))
+    out["too_close_pairs"] = int(sum(n["too_close_pairs"] for n in out["nodes"]))
+    out["nodes"] = sorted(out["nodes"], key=lambda n: (-n["ranks"], n["levels"], n["index"]))[:6]  # keep the line short
+    return out
+
+
 def min_spacing_check(xyz_of_id, nodes, ids, spacing_at_root, max_nodes=6, max_points=3_000_000):
     """MIN_DISTANCE invariant on whole (merged) nodes: no two stored points of a sampled node closer than the
     node's spacing.  xyz_of_id(ids) -> (k, 3) float64 positions.  Checks the largest sampled nodes first."""
