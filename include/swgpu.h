@@ -195,6 +195,16 @@ int swgpu_partition_to_peers_device(swgpu_handle h, const uint64_t* keys_device,
                                     const uint32_t* first_prefix, uint32_t n_ranks, uint32_t id_base,
                                     void* const* peer_xyz_device, void* const* peer_ids_device,
                                     const uint64_t* dst_offsets, uint64_t* send_counts_host);
+/* Attributes through the exchange (PointBuffer's per-point attributes, core/datastructures/PointBuffer.h:291-304:
+ * 14 bytes per point for LAS point format 2, packed by the caller into one record of 4, 8, 12 or 16 bytes per
+ * point).  The next swgpu_partition_device / swgpu_partition_to_peers_device call moves record i with point i:
+ * into out_attr_device (send buffer, same order as out_xyz_device) or into the ranks' receive buffers
+ * peer_attr_device[r] (same offsets as the positions; the array must stay valid until that call returns).
+ * After the exchange every rank holds the attributes of the points it tiles, indexed like its positions, so
+ * swgpu_gather_attribute_device produces the node-major attribute payload locally.  attr_device = NULL
+ * switches it off. */
+int swgpu_set_partition_attributes(swgpu_handle h, const void* attr_device, uint32_t attr_bytes, void* out_attr_device,
+                                   void* const* peer_attr_device);
 /* Marks the handle as tiling one shard.  start_level: FAST's global start level; -1 = the library estimates
  * it itself: on the GLOBAL level-5 counts (one 1 MB all-reduce through the hook, collective over all ranks)
  * when a hook is given, on the local points otherwise; global_ids_device: id of every received point (returned by swgpu_get_nodes
@@ -220,6 +230,41 @@ typedef int (*swgpu_allgatherv_fn)(void* ctx, const void* send_device, uint64_t 
                                    uint64_t* recv_bytes, void* cuda_stream);
 int swgpu_set_shard_faces(swgpu_handle h, const uint32_t* first_prefix, uint32_t n_ranks, uint32_t rank,
                           swgpu_allgatherv_fn allgatherv, void* ctx);
+
+/* ---- several GPUs from ONE host process ---------------------------------------------------------------------
+ * The reference is one process (core/process/Tiler.cpp:189-198, 499-527); these calls let that process tile a
+ * batch on n GPUs of the box: the batch is cut into n slices, each GPU indexes its slice, the points are shuffled
+ * over NVLink (peer access) so that every GPU owns whole Morton-prefix subtrees, every GPU runs the single-GPU
+ * pipeline on its shard (one host thread per GPU), and the per-GPU node tables are merged (nodes above the shard
+ * depth span GPUs: their parts are concatenated in rank = Morton order).  RANDOM_GRID / GRID_CENTER / JITTERED
+ * results are bit-identical to swgpu_index_batch on one GPU; MIN_DISTANCE as documented at swgpu_set_shard_faces.
+ * `devices` may name a GPU more than once (the ranks then share it).  Single batch per run (the device-resident
+ * node store of swgpu_set_multi_batch is per GPU and not combined with sharding).
+ * attr_host / attr_bytes: optional attribute record per point (4, 8, 12 or 16 bytes) that travels with the point
+ * through the exchange (NULL / 0 = none). */
+typedef struct swgpu_multi* swgpu_multi_handle;
+int swgpu_multi_create(const sw_params* params, const int* devices, uint32_t n_devices, swgpu_multi_handle* out);
+void swgpu_multi_destroy(swgpu_multi_handle m);
+const char* swgpu_multi_last_error(swgpu_multi_handle m);
+/* xyz_host: the whole batch (n x 3 doubles, clamped in place like index_point does) */
+int swgpu_multi_index_batch(swgpu_multi_handle m, double* xyz_host, uint64_t n, const void* attr_host,
+                            uint32_t attr_bytes);
+/* FAST reconstruct on every GPU, then the merge; must be called before the result accessors (ACCURATE too) */
+int swgpu_multi_finalize(swgpu_multi_handle m);
+int swgpu_multi_result_size(swgpu_multi_handle m, uint64_t* n_nodes, uint64_t* n_point_ids);
+/* merged node table + node-major point ids (indices into the batch) */
+int swgpu_multi_get_nodes(swgpu_multi_handle m, sw_node* nodes, uint32_t* point_ids);
+/* start level (FAST), shard prefix depth, clamped points, points per GPU after the exchange (n_devices entries);
+ * any pointer may be NULL */
+int swgpu_multi_get_info(swgpu_multi_handle m, int32_t* start_level, uint32_t* shard_levels, uint64_t* n_clamped,
+                         uint64_t* shard_points);
+/* one GPU's part of the result with the node-major attribute records of its points, gathered on that GPU from
+ * the attributes that arrived with the points (swgpu_gather_attribute_device) */
+int swgpu_multi_rank_result_size(swgpu_multi_handle m, uint32_t rank, uint64_t* n_nodes, uint64_t* n_point_ids);
+int swgpu_multi_get_rank_attributes(swgpu_multi_handle m, uint32_t rank, sw_node* nodes, uint32_t* point_ids,
+                                    void* attr_host);
+/* MIN_DISTANCE on nodes that span GPUs: 1 (default) = resolve the shard faces (swgpu_set_shard_faces), 0 = off */
+int swgpu_multi_set_min_distance_faces(swgpu_multi_handle m, int enable);
 
 /* Algorithmic bytes of the last index_batch + finalize by the accounting model of SURVEY.md section 8(d)
  * (bytes_index/sort/gather/sample; used by bench.py for the roofline line), the bytes this implementation

@@ -13,6 +13,7 @@ from .tiler import (  # noqa: F401
     MIN_DISTANCE,
     RANDOM_GRID,
     GpuTiler,
+    MultiGpuTiler,
     SwgpuError,
     TileResult,
     cubic_bounds,

@@ -820,6 +820,9 @@ launch_gather_bytes(const void* src, const u32* perm, u64 n, u32 width, void* ds
     case 12:
       gather_bytes_kernel<12><<<grid, 256, 0, stream>>>(s, perm, n, d);
       break;
+    case 16:
+      gather_words_kernel<uint4><<<grid, 256, 0, stream>>>((const uint4*)src, perm, n, (uint4*)dst);
+      break;
     default:
       break;
   }

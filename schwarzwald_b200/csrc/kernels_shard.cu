@@ -208,15 +208,21 @@ struct SwPartitionDst
 {
   double* xyz[SW_MAX_RANKS]; // where this source's points for destination d start
   u32* ids[SW_MAX_RANKS];
+  u32* attr[SW_MAX_RANKS];   // optional per-point attribute record (AW 32-bit words), same order as the points
 };
 
+// AW: 32-bit words of the attribute record that travels with every point (0 = none; LAS point format 2 carries
+// 14 attribute bytes per point, core/datastructures/PointBuffer.h:291-304, packed into 16)
+template<int AW>
 __global__ void __launch_bounds__(PT_THREADS)
-partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict__ xyz, u64 n, SwSplitters sp,
-                         const u32* __restrict__ tile_offsets, const u64* __restrict__ send_counts, u32 id_base,
-                         SwPartitionDst dst)
+partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict__ xyz, const u32* __restrict__ attr,
+                         u64 n, SwSplitters sp, const u32* __restrict__ tile_offsets,
+                         const u64* __restrict__ send_counts, u32 id_base, SwPartitionDst dst)
 {
   __shared__ double s_x[3 * PT_TILE];
   __shared__ u32 s_id[PT_TILE];
+  __shared__ u32 s_at[AW ? AW * PT_TILE : 1];
+  __shared__ u32* s_ga[SW_MAX_RANKS];
   __shared__ u32 s_wcnt[PT_WARPS][SW_MAX_RANKS];
   __shared__ u32 s_wbase[PT_WARPS][SW_MAX_RANKS]; // first staged position of (warp, destination)
   __shared__ u32 s_tot[SW_MAX_RANKS];
@@ -282,6 +288,8 @@ partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict_
       // staged element e of this destination's segment goes to pointer[e]: bias by the segment start
       s_gx[r] = dst.xyz[r] + 3 * off - 3 * (u64)seg;
       s_gi[r] = dst.ids[r] + off - seg;
+      if (AW)
+        s_ga[r] = dst.attr[r] + (u64)AW * off - (u64)AW * seg;
     }
   }
   __syncthreads();
@@ -302,6 +310,9 @@ partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict_
       s_x[3 * pos + 1] = xyz[3 * i + 1];
       s_x[3 * pos + 2] = xyz[3 * i + 2];
       s_id[pos] = id_base + (u32)i;
+#pragma unroll
+      for (int w = 0; w < AW; ++w)
+        s_at[AW * pos + w] = attr[(u64)AW * i + w];
     }
   }
   __syncthreads();
@@ -315,6 +326,35 @@ partition_scatter_kernel(const u64* __restrict__ keys, const double* __restrict_
       gx[k] = s_x[k];
     for (u32 k = b + tid; k < e; k += PT_THREADS)
       gi[k] = s_id[k];
+    if (AW) {
+      u32* ga = s_ga[r];
+      for (u32 k = AW * b + tid; k < AW * e; k += PT_THREADS)
+        ga[k] = s_at[k];
+    }
+  }
+}
+
+static void
+launch_partition_scatter(u32 tiles, const u64* keys, const double* xyz, const u32* attr, u32 attr_words, u64 n,
+                         const SwSplitters& sp, const u32* tile_counts, const u64* send_counts, u32 id_base,
+                         const SwPartitionDst& dst, cudaStream_t stream)
+{
+  switch (attr ? attr_words : 0u) {
+    case 0:
+      partition_scatter_kernel<0><<<tiles, PT_THREADS, 0, stream>>>(keys, xyz, nullptr, n, sp, tile_counts, send_counts, id_base, dst);
+      break;
+    case 1:
+      partition_scatter_kernel<1><<<tiles, PT_THREADS, 0, stream>>>(keys, xyz, attr, n, sp, tile_counts, send_counts, id_base, dst);
+      break;
+    case 2:
+      partition_scatter_kernel<2><<<tiles, PT_THREADS, 0, stream>>>(keys, xyz, attr, n, sp, tile_counts, send_counts, id_base, dst);
+      break;
+    case 3:
+      partition_scatter_kernel<3><<<tiles, PT_THREADS, 0, stream>>>(keys, xyz, attr, n, sp, tile_counts, send_counts, id_base, dst);
+      break;
+    default:
+      partition_scatter_kernel<4><<<tiles, PT_THREADS, 0, stream>>>(keys, xyz, attr, n, sp, tile_counts, send_counts, id_base, dst);
+      break;
   }
 }
 
@@ -338,7 +378,7 @@ make_splitters(const u32* first_prefix, u32 n_ranks)
 void
 launch_partition_by_splitters(const u64* keys, const double* xyz, u64 n, const u32* first_prefix, u32 n_ranks,
                               u32 id_base, u32* tile_counts, u64* send_counts, double* out_xyz, u32* out_id,
-                              cudaStream_t stream)
+                              const u32* attr, u32 attr_words, u32* out_attr, cudaStream_t stream)
 {
   const SwSplitters sp = make_splitters(first_prefix, n_ranks);
   const u32 tiles = (u32)partition_tiles(n);
@@ -350,16 +390,19 @@ launch_partition_by_splitters(const u64* keys, const double* xyz, u64 n, const u
   for (u32 r = 0; r < SW_MAX_RANKS; ++r) { // one send buffer: the kernel adds the per-destination prefix
     dst.xyz[r] = out_xyz;
     dst.ids[r] = out_id;
+    dst.attr[r] = out_attr;
   }
   partition_count_kernel<<<tiles, PT_THREADS, 0, stream>>>(keys, n, sp, tile_counts);
   partition_scan_kernel<<<SW_MAX_RANKS, 1024, 0, stream>>>(tile_counts, tiles, send_counts);
-  partition_scatter_kernel<<<tiles, PT_THREADS, 0, stream>>>(keys, xyz, n, sp, tile_counts, send_counts, id_base, dst);
+  launch_partition_scatter(tiles, keys, xyz, out_attr ? attr : nullptr, attr_words, n, sp, tile_counts, send_counts,
+                           id_base, dst, stream);
 }
 
 void
 launch_partition_to_peers(const u64* keys, const double* xyz, u64 n, const u32* first_prefix, u32 n_ranks, u32 id_base,
                           u32* tile_counts, u64* send_counts, double* const* peer_xyz, u32* const* peer_ids,
-                          const u64* dst_offsets, cudaStream_t stream)
+                          const u64* dst_offsets, const u32* attr, u32 attr_words, u32* const* peer_attr,
+                          cudaStream_t stream)
 {
   const SwSplitters sp = make_splitters(first_prefix, n_ranks);
   const u32 tiles = (u32)partition_tiles(n);
@@ -371,10 +414,12 @@ launch_partition_to_peers(const u64* keys, const double* xyz, u64 n, const u32* 
   for (u32 r = 0; r < n_ranks; ++r) { // this source's block inside destination r's receive buffer
     dst.xyz[r] = peer_xyz[r] + 3 * dst_offsets[r];
     dst.ids[r] = peer_ids[r] + dst_offsets[r];
+    dst.attr[r] = (peer_attr && attr) ? peer_attr[r] + (u64)attr_words * dst_offsets[r] : nullptr;
   }
   partition_count_kernel<<<tiles, PT_THREADS, 0, stream>>>(keys, n, sp, tile_counts);
   partition_scan_kernel<<<SW_MAX_RANKS, 1024, 0, stream>>>(tile_counts, tiles, send_counts);
-  partition_scatter_kernel<<<tiles, PT_THREADS, 0, stream>>>(keys, xyz, n, sp, tile_counts, nullptr, id_base, dst);
+  launch_partition_scatter(tiles, keys, xyz, peer_attr ? attr : nullptr, attr_words, n, sp, tile_counts, nullptr,
+                           id_base, dst, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -200,16 +200,19 @@ void launch_bin_counts(const u32* bin_start, u32 n_bins, u32* counts, cudaStream
 // prefixes [first_prefix[r], first_prefix[r+1]).  tile_counts: partition_tiles(n) * SW_MAX_RANKS
 // u32 scratch; send_counts: SW_MAX_RANKS u64 (device).
 size_t partition_tiles(u64 n);
+// attr / attr_words / out_attr: optional attribute record of attr_words (1..4) 32-bit words per point that is
+// partitioned along with the positions (nullptr = none)
 void launch_partition_by_splitters(const u64* keys, const double* xyz, u64 n, const u32* first_prefix, u32 n_ranks,
                                    u32 id_base, u32* tile_counts, u64* send_counts, double* out_xyz, u32* out_id,
-                                   cudaStream_t stream);
+                                   const u32* attr, u32 attr_words, u32* out_attr, cudaStream_t stream);
 // Same partition, written straight into the destinations' receive buffers: peer_xyz[r] / peer_ids[r]
 // are device pointers to rank r's buffers (peer-mapped over NVLink, or local), dst_offsets[r] is the
 // first point of this source's block there.  send_counts (device, SW_MAX_RANKS u64) still receives
 // the per-destination totals.
 void launch_partition_to_peers(const u64* keys, const double* xyz, u64 n, const u32* first_prefix, u32 n_ranks,
                                u32 id_base, u32* tile_counts, u64* send_counts, double* const* peer_xyz,
-                               u32* const* peer_ids, const u64* dst_offsets, cudaStream_t stream);
+                               u32* const* peer_ids, const u64* dst_offsets, const u32* attr, u32 attr_words,
+                               u32* const* peer_attr, cudaStream_t stream);
 // node counts of one sweep level <-> dense per-prefix counters (8^levels entries)
 void launch_node_counts_to_dense(const u64* keys, const u32* node_start, u32 n_nodes, int node_shift, u32* dense,
                                  cudaStream_t stream);

@@ -158,6 +158,11 @@ struct swgpu_tiler
   const u32* global_ids = nullptr; // device: received point -> global point id
   DevBuf dense_counts, node_gcount;
   DevBuf part_tile_counts, part_send_counts;
+  // attribute record that travels with the points through the next partition call (swgpu_set_partition_attributes)
+  const void* part_attr_src = nullptr;
+  u32 part_attr_words = 0;
+  void* part_attr_dst = nullptr;          // swgpu_partition_device: send buffer
+  void* const* part_attr_peers = nullptr; // swgpu_partition_to_peers_device: receive buffers of all ranks
   // MIN_DISTANCE across shard faces (swgpu_set_shard_faces)
   swgpu_allgatherv_fn face_fn = nullptr;
   void* face_ctx = nullptr;
@@ -1861,7 +1866,7 @@ swgpu_gather_attribute_device(swgpu_handle h, const void* src_device, uint32_t w
   if (width == 24)
     launch_gather_positions(static_cast<const double*>(src_device), h->ids_tmp.as<u32>(), h->out_count,
                             static_cast<double*>(dst_device), h->stream);
-  else if (width == 1 || width == 2 || width == 3 || width == 4 || width == 8 || width == 12)
+  else if (width == 1 || width == 2 || width == 3 || width == 4 || width == 8 || width == 12 || width == 16)
     launch_gather_bytes(src_device, h->ids_tmp.as<u32>(), h->out_count, width, dst_device, h->stream);
   else
     return fail(h, SW_ERR_INVALID_ARGUMENT, "unsupported attribute width");
@@ -2028,7 +2033,8 @@ swgpu_partition_device(swgpu_handle h, const uint64_t* keys_device, const double
   CK(h->part_send_counts.ensure(SW_MAX_RANKS * 8));
   launch_partition_by_splitters(reinterpret_cast<const u64*>(keys_device), xyz_device, n, first_prefix, n_ranks, id_base,
                                 h->part_tile_counts.as<u32>(), h->part_send_counts.as<u64>(), out_xyz_device,
-                                out_id_device, h->stream);
+                                out_id_device, static_cast<const u32*>(h->part_attr_src), h->part_attr_words,
+                                static_cast<u32*>(h->part_attr_dst), h->stream);
   CK(cudaGetLastError());
   u64 counts[SW_MAX_RANKS];
   CK(cudaMemcpyAsync(counts, h->part_send_counts.p, SW_MAX_RANKS * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -2060,8 +2066,13 @@ swgpu_partition_to_peers_device(swgpu_handle h, const uint64_t* keys_device, con
     pi[r] = static_cast<u32*>(peer_ids_device[r]);
     off[r] = dst_offsets[r];
   }
+  u32* pa[SW_MAX_RANKS];
+  for (u32 r = 0; r < n_ranks; ++r)
+    pa[r] = h->part_attr_peers ? static_cast<u32*>(h->part_attr_peers[r]) : nullptr;
   launch_partition_to_peers(reinterpret_cast<const u64*>(keys_device), xyz_device, n, first_prefix, n_ranks, id_base,
-                            h->part_tile_counts.as<u32>(), h->part_send_counts.as<u64>(), px, pi, off, h->stream);
+                            h->part_tile_counts.as<u32>(), h->part_send_counts.as<u64>(), px, pi, off,
+                            static_cast<const u32*>(h->part_attr_src), h->part_attr_words,
+                            h->part_attr_peers ? pa : nullptr, h->stream);
   CK(cudaGetLastError());
   if (send_counts_host) { // optional check value; costs a stream synchronisation
     u64 counts[SW_MAX_RANKS];
@@ -2086,6 +2097,28 @@ swgpu_set_shard(swgpu_handle h, uint32_t shard_levels, int32_t start_level, swgp
   h->allreduce = shard_levels ? allreduce : nullptr;
   h->allreduce_ctx = allreduce_ctx;
   h->global_ids = shard_levels ? reinterpret_cast<const u32*>(global_ids_device) : nullptr;
+  return SW_OK;
+}
+
+int
+swgpu_set_partition_attributes(swgpu_handle h, const void* attr_device, uint32_t attr_bytes, void* out_attr_device,
+                               void* const* peer_attr_device)
+{
+  if (!h)
+    return SW_ERR_INVALID_ARGUMENT;
+  if (!attr_device) {
+    h->part_attr_src = nullptr;
+    h->part_attr_words = 0;
+    h->part_attr_dst = nullptr;
+    h->part_attr_peers = nullptr;
+    return SW_OK;
+  }
+  if (attr_bytes == 0 || attr_bytes > 16 || (attr_bytes & 3u))
+    return fail(h, SW_ERR_INVALID_ARGUMENT, "attribute records must be 4, 8, 12 or 16 bytes per point");
+  h->part_attr_src = attr_device;
+  h->part_attr_words = attr_bytes / 4;
+  h->part_attr_dst = out_attr_device;
+  h->part_attr_peers = peer_attr_device;
   return SW_OK;
 }
 

@@ -357,18 +357,20 @@ class ShardedTiler:
             return False
         return self._peer_failed is None
 
-    def _ensure_peer_buffers(self, need_points):
+    def _ensure_peer_buffers(self, need_points, attr_bytes=0):
         """(Re)allocates the symmetric receive buffers for at least need_points points per rank.  Every rank
         calls this with the same value (it comes from the all-gathered count matrix)."""
-        if self._peer is not None and self._peer["cap"] >= need_points:
+        if self._peer is not None and self._peer["cap"] >= need_points and self._peer["attr_bytes"] >= attr_bytes:
             return True
         try:
             cap = int(need_points * 1.1) + (1 << 16)
             self._peer = None  # release the old mapping first
             xyz, xyz_ptrs, hx = self.comm.peer_buffers(cap * 24, self.device)
             ids, ids_ptrs, hi = self.comm.peer_buffers(cap * 4, self.device)
+            att, att_ptrs, ha = (self.comm.peer_buffers(cap * attr_bytes, self.device) if attr_bytes
+                                 else (None, None, None))
             self._peer = {"cap": cap, "xyz": xyz, "ids": ids, "xyz_ptrs": xyz_ptrs, "ids_ptrs": ids_ptrs,
-                          "handles": (hx, hi)}
+                          "attr": att, "attr_ptrs": att_ptrs, "attr_bytes": attr_bytes, "handles": (hx, hi, ha)}
             return True
         except Exception as e:  # no peer mapping on this system: the NCCL exchange does the same job
             if self.exchange == "peer":
@@ -378,12 +380,33 @@ class ShardedTiler:
             return False
 
     # -- the two calls of TilingAlgorithmBase --------------------------------------------------------
-    def build_execution_graph(self, xyz, id_base=None):
+    def build_execution_graph(self, xyz, id_base=None, attributes=None):
+        """attributes: optional (n_local, W) uint8 CUDA tensor, W in {4, 8, 12, 16}: one attribute record per point
+        (PointBuffer's attributes packed by the caller) that travels with the point through the exchange;
+        afterwards gather_attributes() returns this rank's node-major attribute payload."""
         with self._stream_ctx():
-            return self._build_execution_graph(xyz, id_base)
+            return self._build_execution_graph(xyz, id_base, attributes)
 
-    def _build_execution_graph(self, xyz, id_base=None):
+    def gather_attributes(self, out=None):
+        """Node-major attribute records of this rank's result (same order as result().ids)."""
         torch = self._torch
+        att = self._keep.get("attr")
+        if att is None:
+            raise ValueError("build_execution_graph was called without attributes")
+        _, ni = self.tiler.result_size()
+        w = att.shape[1]
+        out = out if out is not None else torch.empty((max(ni, 1), w), dtype=torch.uint8, device=self.device)
+        with self._stream_ctx():
+            self.tiler.gather_attribute_device(att.data_ptr(), w, out.data_ptr())
+        return out[:ni]
+
+    def _build_execution_graph(self, xyz, id_base=None, attributes=None):
+        torch = self._torch
+        attr_bytes = 0
+        if attributes is not None:
+            assert attributes.is_cuda and attributes.dtype == torch.uint8 and attributes.is_contiguous()
+            attr_bytes = int(attributes.shape[1])
+            assert attributes.shape[0] == xyz.numel() // 3 and attr_bytes in (4, 8, 12, 16)
         t, lib, comm = self.tiler, self.tiler._lib, self.comm
         n = xyz.numel() // 3
         assert xyz.is_cuda and xyz.dtype == torch.float64 and xyz.is_contiguous()
@@ -439,7 +462,7 @@ class ShardedTiler:
         sc = [int(x) for x in count_matrix[comm.rank]]
         rc = [int(x) for x in count_matrix[:, comm.rank]]
         recv_totals = count_matrix.sum(axis=0)
-        if self._peer_wanted() and self._ensure_peer_buffers(int(recv_totals.max())):
+        if self._peer_wanted() and self._ensure_peer_buffers(int(recv_totals.max()), attr_bytes):
             # 4+5 in ONE kernel: stable partition written straight into the destinations' receive buffers
             # (peer memory over NVLink).  The all-gather above ordered this step after every rank's previous
             # use of its receive buffer; the tiny all-reduce below orders every rank's tiling after all writes.
@@ -448,6 +471,9 @@ class ShardedTiler:
             dst_offsets = np.array([int(count_matrix[:comm.rank, r].sum()) for r in range(world)], np.uint64)
             px = (C.c_void_p * world)(*pk["xyz_ptrs"])
             pi = (C.c_void_p * world)(*pk["ids_ptrs"])
+            pa = (C.c_void_p * world)(*pk["attr_ptrs"]) if attr_bytes else None
+            t._check(lib.swgpu_set_partition_attributes(t._h, C.c_void_p(attributes.data_ptr() if attr_bytes else 0),
+                                                        attr_bytes, None, pa))
             t._check(lib.swgpu_partition_to_peers_device(
                 t._h, C.c_void_p(keys.data_ptr()), C.c_void_p(xyz.data_ptr()), n, C.c_void_p(first_prefix.ctypes.data),
                 world, int(id_base), px, pi, C.c_void_p(dst_offsets.ctypes.data), None))
@@ -460,7 +486,8 @@ class ShardedTiler:
             mark("barrier")
             self._set_shard(shard_levels, start_level, pk["ids_ptrs"][comm.rank] if m else 0, first_prefix)
             self._keep = {"xyz": pk["xyz"][:m * 24].view(torch.float64).view(m, 3),
-                          "ids": pk["ids"][:m * 4].view(torch.int32)}
+                          "ids": pk["ids"][:m * 4].view(torch.int32),
+                          "attr": pk["attr"][:m * attr_bytes].view(m, attr_bytes) if attr_bytes else None}
             t._check(lib.swgpu_index_batch_device(t._h, C.c_void_p(pk["xyz_ptrs"][comm.rank] if m else 0), m))
             mark("tile")
             phases = {}
@@ -472,12 +499,16 @@ class ShardedTiler:
                          "start_level": t.start_level(), "first_prefix": first_prefix, "send_counts": sc, "recv_counts": rc,
                          "shard_levels": shard_levels,
                          "exchange": "peer kernel (swgpu_partition_to_peers_device over symmetric memory)",
-                         "bytes_sent_off_gpu": int(sum(c for r, c in enumerate(sc) if r != comm.rank)) * 28}
+                         "bytes_sent_off_gpu": int(sum(c for r, c in enumerate(sc) if r != comm.rank)) * (28 + attr_bytes)}
             return n
         # 4. stable partition into the send buffer
         send_xyz = torch.empty((max(n, 1), 3), dtype=torch.float64, device=self.device)
         send_ids = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
         send_counts = np.zeros(comm.world, np.uint64)
+        send_attr = torch.empty((max(n, 1), attr_bytes), dtype=torch.uint8, device=self.device) if attr_bytes else None
+        t._check(lib.swgpu_set_partition_attributes(t._h, C.c_void_p(attributes.data_ptr() if attr_bytes else 0),
+                                                    attr_bytes, C.c_void_p(send_attr.data_ptr() if attr_bytes else 0),
+                                                    None))
         t._check(lib.swgpu_partition_device(t._h, C.c_void_p(keys.data_ptr()), C.c_void_p(xyz.data_ptr()), n,
                                             C.c_void_p(first_prefix.ctypes.data), comm.world, int(id_base),
                                             C.c_void_p(send_xyz.data_ptr()), C.c_void_p(send_ids.data_ptr()),
@@ -488,12 +519,13 @@ class ShardedTiler:
         assert sc == [int(x) for x in send_counts], "partition and histogram disagree"
         recv_xyz, recv_counts = comm.all_to_all_rows(send_xyz[:n], sc, rc)
         recv_ids, _ = comm.all_to_all_rows(send_ids[:n], sc, rc)
-        del send_xyz, send_ids
+        recv_attr = comm.all_to_all_rows(send_attr[:n], sc, rc)[0] if attr_bytes else None
+        del send_xyz, send_ids, send_attr
         m = int(recv_xyz.shape[0])
         mark("all_to_all")
         # 6. the single-GPU pipeline on the shard
         self._set_shard(shard_levels, start_level, recv_ids.data_ptr() if m else 0, first_prefix)
-        self._keep = {"xyz": recv_xyz, "ids": recv_ids}
+        self._keep = {"xyz": recv_xyz, "ids": recv_ids, "attr": recv_attr}
         t._check(lib.swgpu_index_batch_device(t._h, C.c_void_p(recv_xyz.data_ptr() if m else 0), m))
         mark("tile")
         phases = {}
@@ -505,7 +537,7 @@ class ShardedTiler:
                      "shard_levels": shard_levels, "first_prefix": first_prefix, "send_counts": sc, "recv_counts": recv_counts,
                      "exchange": "nccl all_to_all" + (" (peer mapping unavailable: %s)" % self._peer_failed
                                                       if self._peer_failed else ""),
-                     "bytes_sent_off_gpu": int(sum(c for r, c in enumerate(sc) if r != comm.rank)) * 28}
+                     "bytes_sent_off_gpu": int(sum(c for r, c in enumerate(sc) if r != comm.rank)) * (28 + attr_bytes)}
         return n
 
     def finalize(self):
@@ -550,7 +582,7 @@ class _DeviceArray:
 
 
 def tile_with_virtual_ranks(world, xyz_parts, sampling, tiling, bounds_min, bounds_max, spacing_at_root, device=0,
-                            **kw):
+                            attr_parts=None, **kw):
     """Runs `world` virtual ranks as threads on one GPU (ThreadComm) and returns the per-rank
     TileResults plus the per-rank bookkeeping.  Used by the single-GPU parity tests."""
     import torch
@@ -562,10 +594,12 @@ def tile_with_virtual_ranks(world, xyz_parts, sampling, tiling, bounds_min, boun
             torch.cuda.set_device(device)
             with ShardedTiler(sampling, tiling, bounds_min, bounds_max, spacing_at_root, device=device,
                               comm=comms[r], **kw) as st:
-                st.build_execution_graph(xyz_parts[r])
+                st.build_execution_graph(xyz_parts[r], attributes=attr_parts[r] if attr_parts else None)
                 st.finalize()
                 results[r] = st.result()
                 infos[r] = dict(st.last)
+                if attr_parts:
+                    infos[r]["attributes"] = st.gather_attributes().cpu().numpy()
         except BaseException as e:  # noqa: BLE001 - reported to the caller
             errors[r] = e
             comms[r].shared.barrier.abort()

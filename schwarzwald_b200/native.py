@@ -106,7 +106,20 @@ SYMBOLS = [
     ("swgpu_partition_to_peers_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
                                                   C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swgpu_set_shard", C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, ALLREDUCE_FN, C.c_void_p, C.c_void_p]),
+    ("swgpu_set_partition_attributes", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     ("swgpu_set_shard_faces", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, ALLGATHERV_FN, C.c_void_p]),
+    ("swgpu_multi_create", C.c_int, [C.POINTER(SwParams), C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    ("swgpu_multi_destroy", None, [C.c_void_p]),
+    ("swgpu_multi_last_error", C.c_char_p, [C.c_void_p]),
+    ("swgpu_multi_index_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]),
+    ("swgpu_multi_finalize", C.c_int, [C.c_void_p]),
+    ("swgpu_multi_result_size", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("swgpu_multi_get_nodes", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("swgpu_multi_get_info", C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                       C.c_void_p]),
+    ("swgpu_multi_rank_result_size", C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("swgpu_multi_get_rank_attributes", C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("swgpu_multi_set_min_distance_faces", C.c_int, [C.c_void_p, C.c_int]),
     ("swgpu_enable_timing", C.c_int, [C.c_void_p, C.c_int]),
     ("swgpu_get_stats", C.c_int, [C.c_void_p, C.POINTER(SwgpuStats)]),
 ]

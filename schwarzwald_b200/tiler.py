@@ -312,3 +312,104 @@ class GpuTiler:
     def gather_attribute_device(self, src_ptr, width, dst_ptr):
         self._check(self._lib.swgpu_gather_attribute_device(self._h, C.c_void_p(int(src_ptr)), int(width),
                                                             C.c_void_p(int(dst_ptr))))
+
+
+class MultiGpuTiler:
+    """Several GPUs from one process (swgpu_multi_*, include/swgpu.h): the whole batch goes in as one host array,
+    like Tiler::build_execution_graph_for_indexing hands it to a TilingAlgorithmBase (process/Tiler.cpp:499-527);
+    the library cuts it into slices, shuffles the points over NVLink so that every GPU owns whole Morton-prefix
+    subtrees, tiles the shards on one host thread per GPU and merges the node tables."""
+
+    def __init__(self, sampling, tiling, bounds_min, bounds_max, spacing_at_root, devices, max_points_per_node=20000,
+                 max_depth=100, concurrency=8):
+        self._lib = native.load_library()
+        p = native.SwParams()
+        p.sampling = _SAMPLING[sampling]
+        p.tiling = _TILING[tiling]
+        p.spacing_at_root = float(np.float32(spacing_at_root))
+        p.max_depth = int(max_depth)
+        p.max_points_per_node = int(max_points_per_node)
+        for a in range(3):
+            p.bounds_min[a] = float(bounds_min[a])
+            p.bounds_max[a] = float(bounds_max[a])
+        p.concurrency = int(concurrency)
+        self.params = p
+        self.devices = [int(d) for d in devices]
+        dev = (C.c_int * len(self.devices))(*self.devices)
+        self._h = C.c_void_p()
+        rc = self._lib.swgpu_multi_create(C.byref(p), dev, len(self.devices), C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise SwgpuError(rc, "swgpu_multi_create failed (no CUDA device, no peer access, or invalid parameters)")
+        self._attr_bytes = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.swgpu_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SwgpuError(rc, self._lib.swgpu_multi_last_error(self._h).decode())
+
+    def set_min_distance_faces(self, on=True):
+        self._check(self._lib.swgpu_multi_set_min_distance_faces(self._h, 1 if on else 0))
+
+    def build_execution_graph(self, points, attributes=None):
+        """points: host numpy (n, 3) float64, clamped in place; attributes: optional (n, W) uint8, W in 4/8/12/16."""
+        if points.dtype != np.float64 or not points.flags["C_CONTIGUOUS"]:
+            raise ValueError("positions must be C-contiguous float64 (PointBuffer::positions layout)")
+        n = points.size // 3
+        ap, ab = None, 0
+        if attributes is not None:
+            if attributes.dtype != np.uint8 or not attributes.flags["C_CONTIGUOUS"] or attributes.shape[0] != n:
+                raise ValueError("attributes must be a C-contiguous (n, W) uint8 array")
+            ap, ab = C.c_void_p(attributes.ctypes.data), int(attributes.shape[1])
+        self._attr_bytes = ab
+        self._check(self._lib.swgpu_multi_index_batch(self._h, C.c_void_p(points.ctypes.data), n, ap, ab))
+        return n
+
+    def finalize(self):
+        self._check(self._lib.swgpu_multi_finalize(self._h))
+
+    def info(self):
+        s, l, c = C.c_int32(), C.c_uint32(), C.c_uint64()
+        pts = np.zeros(len(self.devices), np.uint64)
+        self._check(self._lib.swgpu_multi_get_info(self._h, C.byref(s), C.byref(l), C.byref(c), C.c_void_p(pts.ctypes.data)))
+        return {"start_level": s.value, "shard_levels": l.value, "clamped": c.value, "shard_points": pts}
+
+    def result(self):
+        nn, ni = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.swgpu_multi_result_size(self._h, C.byref(nn), C.byref(ni)))
+        nodes = np.empty(nn.value, NODE_DTYPE)
+        ids = np.empty(ni.value, np.uint32)
+        self._check(self._lib.swgpu_multi_get_nodes(self._h, C.c_void_p(nodes.ctypes.data), C.c_void_p(ids.ctypes.data)))
+        return TileResult(nodes, ids, self.info()["start_level"])
+
+    def rank_result_with_attributes(self, rank):
+        """(TileResult of GPU `rank`'s part, node-major attribute records gathered on that GPU)."""
+        nn, ni = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.swgpu_multi_rank_result_size(self._h, int(rank), C.byref(nn), C.byref(ni)))
+        nodes = np.empty(nn.value, NODE_DTYPE)
+        ids = np.empty(ni.value, np.uint32)
+        attrs = np.empty((ni.value, self._attr_bytes), np.uint8)
+        self._check(self._lib.swgpu_multi_get_rank_attributes(self._h, int(rank), C.c_void_p(nodes.ctypes.data),
+                                                              C.c_void_p(ids.ctypes.data), C.c_void_p(attrs.ctypes.data)))
+        return TileResult(nodes, ids, self.info()["start_level"]), attrs
+
+    def tile(self, points, attributes=None):
+        self.build_execution_graph(points, attributes)
+        self.finalize()
+        return self.result()

@@ -206,3 +206,26 @@ def test_coarse_prefix_histogram_matches_numpy(levels):
     k = keys.cpu().numpy().view(np.uint64)
     want = np.bincount((k >> np.uint64(63 - 3 * levels)).astype(np.int64), minlength=8 ** levels)
     assert np.array_equal(bins.cpu().numpy().astype(np.int64), 2 * want)
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("width", [4, 16])
+def test_attributes_travel_through_the_exchange(exchange, width):
+    """A per-point attribute record (PointBuffer attributes packed to 4 / 16 bytes, PointBuffer.h:291-304) moves with
+    its point through both exchange paths; every rank then produces the node-major attribute payload of ITS nodes
+    locally (swgpu_gather_attribute_device) and it equals the attributes of the points' global ids."""
+    import torch
+    from schwarzwald_b200 import distributed
+    xyz, bmin, bmax, spacing = _setup("urban", 300_000, 6, side_m=600.0)
+    world = 3
+    rng = np.random.default_rng(5)
+    attrs = rng.integers(0, 256, size=(len(xyz), width), dtype=np.uint8)
+    cuts = np.linspace(0, len(xyz), world + 1).astype(int)
+    parts = [torch.from_numpy(xyz[cuts[r]:cuts[r + 1]].copy()).cuda() for r in range(world)]
+    aparts = [torch.from_numpy(attrs[cuts[r]:cuts[r + 1]].copy()).cuda() for r in range(world)]
+    results, infos = distributed.tile_with_virtual_ranks(world, parts, "GRID_CENTER", "FAST", bmin, bmax, spacing,
+                                                         attr_parts=aparts, max_points_per_node=2500, concurrency=4,
+                                                         exchange=exchange)
+    assert sum(i["n_shard"] for i in infos) == len(xyz)
+    for res, info in zip(results, infos):
+        assert np.array_equal(info["attributes"], attrs[res.ids.astype(np.int64)])
