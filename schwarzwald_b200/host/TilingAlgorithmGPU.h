@@ -60,6 +60,21 @@ struct TilingAlgorithmGPU : TilingAlgorithmBase
     , _refuse_lossy_read_back(refuse_lossy_read_back)
   {}
 
+  // All GPUs of the box from this one process: a batch that is the whole cloud (shorter than
+  // internal_cache_size) is sharded over `cuda_devices` (swgpu_multi_*); a multi-batch run stays on the first one,
+  // because the node store between batches is per GPU.
+  TilingAlgorithmGPU(SamplingStrategy& sampling_strategy,
+                     ProgressReporter* progress_reporter,
+                     PointsPersistence& persistence,
+                     TilerMetaParameters meta_parameters,
+                     std::vector<int> cuda_devices,
+                     bool refuse_lossy_read_back = false)
+    : TilingAlgorithmBase(sampling_strategy, progress_reporter, persistence, meta_parameters)
+    , _cuda_device(cuda_devices.empty() ? 0 : cuda_devices.front())
+    , _refuse_lossy_read_back(refuse_lossy_read_back)
+    , _cuda_devices(std::move(cuda_devices))
+  {}
+
   std::pair<tf::Task, tf::Task> build_execution_graph(util::Range<PointBuffer::PointIterator> points,
                                                       const AABB& bounds,
                                                       uint32_t num_indexing_threads,
@@ -73,6 +88,25 @@ struct TilingAlgorithmGPU : TilingAlgorithmBase
         _root_bounds = bounds;
         const double bmin[3] = { bounds.min.x, bounds.min.y, bounds.min.z };
         const double bmax[3] = { bounds.max.x, bounds.max.y, bounds.max.z };
+        if (_cuda_devices.size() > 1 && n < _meta_parameters.internal_cache_size) {
+          // the whole cloud in one batch: every GPU tiles its Morton-prefix shard
+          swgpu::MultiTiler multi(sampling_enum(),
+                                  _meta_parameters.tiling_strategy == TilingStrategy::Fast ? SW_FAST : SW_ACCURATE,
+                                  _meta_parameters.spacing_at_root,
+                                  _meta_parameters.max_depth,
+                                  _meta_parameters.max_points_per_node,
+                                  bmin,
+                                  bmax,
+                                  num_indexing_threads,
+                                  _cuda_devices);
+          warn_if_lossy(false);
+          double* xyz_all = n ? &(*std::begin(points)).position().x : nullptr;
+          multi.index_batch(xyz_all, n);
+          multi.finalize();
+          hand_off(multi.result(), std::begin(points), /*count_progress=*/true);
+          _done_on_many_gpus = true;
+          return;
+        }
         _tiler = std::make_unique<swgpu::Tiler>(sampling_enum(),
                                                 _meta_parameters.tiling_strategy == TilingStrategy::Fast ? SW_FAST
                                                                                                          : SW_ACCURATE,
@@ -87,16 +121,8 @@ struct TilingAlgorithmGPU : TilingAlgorithmBase
         _multi_batch = n >= _meta_parameters.internal_cache_size;
         if (_multi_batch)
           _tiler->set_multi_batch(true);
-        if (!_persistence.is_lossless() &&
-            (_multi_batch || _meta_parameters.tiling_strategy == TilingStrategy::Fast)) {
-          const char* msg = "TilingAlgorithmGPU: the output format is lossy; nodes the reference would re-read from "
-                            "disk (FAST reconstruction, later batches) are sampled from the original positions "
-                            "instead of the quantised ones";
-          if (_refuse_lossy_read_back)
-            throw std::runtime_error{ msg };
-          std::fprintf(stderr, "warning: %s\n", msg);
-        }
-      } else if (!_multi_batch) {
+        warn_if_lossy(_multi_batch);
+      } else if (_done_on_many_gpus || !_multi_batch) {
         throw std::runtime_error{ "TilingAlgorithmGPU: a batch followed a batch shorter than internal_cache_size" };
       }
       // PointBuffer::positions() is a std::vector<Vector3<double>>: AoS x,y,z doubles (PointBuffer.h:291)
@@ -114,7 +140,7 @@ struct TilingAlgorithmGPU : TilingAlgorithmBase
       // a batch shorter than internal_cache_size is the only one: FAST's reconstruction of the upper levels
       // (TilingAlgorithmV3::finalize) runs right here, while the caller's PointBuffer is still alive
       _tiler->finalize();
-      hand_off(std::begin(points), /*count_progress=*/true);
+      hand_off(_tiler->result(), std::begin(points), /*count_progress=*/true);
     });
     return { task, task };
   }
@@ -125,7 +151,7 @@ struct TilingAlgorithmGPU : TilingAlgorithmBase
       return;
     if (_multi_batch) {
       _tiler->finalize();
-      hand_off(std::begin(_stored_points), /*count_progress=*/false);
+      hand_off(_tiler->result(), std::begin(_stored_points), /*count_progress=*/false);
       return;
     }
   }
@@ -154,9 +180,20 @@ private:
 
   // The per-node persist_points calls of tile_terminal_node / tile_internal_node /
   // reconstruct_single_node, driven from the node table instead of the recursion.
-  void hand_off(PointBuffer::PointIterator first_point, bool count_progress)
+  void warn_if_lossy(bool multi_batch)
   {
-    const auto result = _tiler->result();
+    if (_persistence.is_lossless() || !(multi_batch || _meta_parameters.tiling_strategy == TilingStrategy::Fast))
+      return;
+    const char* msg = "TilingAlgorithmGPU: the output format is lossy; nodes the reference would re-read from "
+                      "disk (FAST reconstruction, later batches) are sampled from the original positions "
+                      "instead of the quantised ones";
+    if (_refuse_lossy_read_back)
+      throw std::runtime_error{ msg };
+    std::fprintf(stderr, "warning: %s\n", msg);
+  }
+
+  void hand_off(const swgpu::Tiler::Result& result, PointBuffer::PointIterator first_point, bool count_progress)
+  {
     const double rmin[3] = { _root_bounds.min.x, _root_bounds.min.y, _root_bounds.min.z };
     const double rmax[3] = { _root_bounds.max.x, _root_bounds.max.y, _root_bounds.max.z };
     std::vector<PointBuffer::PointReference> refs;
@@ -180,6 +217,8 @@ private:
   bool _refuse_lossy_read_back;
   size_t _batches_done = 0;
   bool _multi_batch = false;
+  bool _done_on_many_gpus = false;
+  std::vector<int> _cuda_devices;
   PointBuffer _stored_points; // multi-batch: host copy of every batch, indexed by global point id
   AABB _root_bounds;
   std::unique_ptr<swgpu::Tiler> _tiler;

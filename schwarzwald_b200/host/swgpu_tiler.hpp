@@ -200,4 +200,58 @@ private:
   swgpu_handle _handle = nullptr;
 };
 
+// Several GPUs from the one process the reference is (core/process/Tiler.cpp:189-198): swgpu_multi_* cuts the
+// batch into slices, shuffles the points over NVLink so that every GPU owns whole Morton-prefix subtrees, tiles
+// the shards on one host thread per GPU and merges the node tables.  Same result type as Tiler.
+class MultiTiler
+{
+public:
+  MultiTiler(sw_sampling sampling, sw_tiling tiling, float spacing_at_root, uint32_t max_depth,
+             uint64_t max_points_per_node, const double bounds_min[3], const double bounds_max[3],
+             uint32_t num_indexing_threads, const std::vector<int>& devices)
+  {
+    _params.sampling = sampling;
+    _params.tiling = tiling;
+    _params.spacing_at_root = spacing_at_root;
+    _params.max_depth = max_depth;
+    _params.max_points_per_node = max_points_per_node;
+    for (int a = 0; a < 3; ++a) {
+      _params.bounds_min[a] = bounds_min[a];
+      _params.bounds_max[a] = bounds_max[a];
+    }
+    _params.concurrency = num_indexing_threads;
+    _params.reserved = 0;
+    const int rc = swgpu_multi_create(&_params, devices.data(), static_cast<uint32_t>(devices.size()), &_handle);
+    if (rc != SW_OK)
+      throw Error(rc,
+                  rc == SW_ERR_CUDA ? "swgpu_multi_create: a CUDA device is missing or the GPUs cannot access each other"
+                                    : "swgpu_multi_create: invalid tiler parameters");
+  }
+  ~MultiTiler() { swgpu_multi_destroy(_handle); }
+  MultiTiler(const MultiTiler&) = delete;
+  MultiTiler& operator=(const MultiTiler&) = delete;
+
+  void index_batch(double* xyz_host, uint64_t n) { check(swgpu_multi_index_batch(_handle, xyz_host, n, nullptr, 0)); }
+  void finalize() { check(swgpu_multi_finalize(_handle)); }
+  Tiler::Result result()
+  {
+    uint64_t n_nodes = 0, n_ids = 0;
+    check(swgpu_multi_result_size(_handle, &n_nodes, &n_ids));
+    Tiler::Result r;
+    r.nodes.resize(n_nodes);
+    r.point_ids.resize(n_ids);
+    check(swgpu_multi_get_nodes(_handle, r.nodes.data(), r.point_ids.data()));
+    return r;
+  }
+
+private:
+  void check(int rc)
+  {
+    if (rc != SW_OK)
+      throw Error(rc, swgpu_multi_last_error(_handle));
+  }
+  sw_params _params{};
+  swgpu_multi_handle _handle = nullptr;
+};
+
 } // namespace swgpu

@@ -28,7 +28,7 @@ main(int argc, char** argv)
 {
   if (argc < 7) {
     std::fprintf(stderr,
-                 "usage: adapter_driver n seed SAMPLING TILING max_points_per_node indexing_threads [batch_size]\n");
+                 "usage: adapter_driver n seed SAMPLING TILING max_points_per_node indexing_threads [batch_size] [n_gpu_ranks]\n");
     return 2;
   }
   const size_t n = std::strtoull(argv[1], nullptr, 10);
@@ -38,6 +38,8 @@ main(int argc, char** argv)
   const uint32_t threads = static_cast<uint32_t>(std::strtoul(argv[6], nullptr, 10));
   // internal_cache_size: Tiler::run hands the algorithm at most this many points per batch (Tiler.cpp:499-527)
   const size_t batch = argc > 7 ? std::strtoull(argv[7], nullptr, 10) : 0;
+  // > 1: the adapter shards a single-batch run over that many ranks (GPUs 0, 1, ... modulo the GPUs of the box)
+  const size_t gpu_ranks = argc > 8 ? std::strtoull(argv[8], nullptr, 10) : 1;
 
   std::vector<Vector3<double>> positions(n);
   for (auto& p : positions) { // xorshift64*, coordinates on a millimetre lattice in [0, 100) m
@@ -72,7 +74,15 @@ main(int argc, char** argv)
   progress.register_progress_counter<size_t>(progress::INDEXING, n);
   PointsPersistence sink;
   try {
-    TilingAlgorithmGPU algorithm(strategy, &progress, sink, meta);
+    std::vector<int> devices;
+    int n_gpus = 1;
+    if (gpu_ranks > 1) {
+      const char* env = std::getenv("SWGPU_TEST_GPUS");
+      n_gpus = env ? std::max(1, std::atoi(env)) : 1;
+    }
+    for (size_t q = 0; q < gpu_ranks; ++q)
+      devices.push_back(static_cast<int>(q % static_cast<size_t>(n_gpus)));
+    TilingAlgorithmGPU algorithm(strategy, &progress, sink, meta, devices);
     const size_t step = batch ? batch : n;
     for (size_t lo = 0; lo < n; lo += step) { // Tiler::run: one execution graph per batch, run to completion
       // Tiler reuses its point caches: the batch lives in its own buffer that is gone after the batch

@@ -143,3 +143,37 @@ def test_adapter_multi_batch_matches_oracle(port_oracle, sampling, tiling):
     for name, ids in want.items():
         assert got[name][0] == len(ids), name
         assert got[name][1] == _fnv1a(np.ascontiguousarray(xyz[ids.astype(np.int64)]).tobytes()), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sampling,tiling", [("GRID_CENTER", "FAST"), ("JITTERED", "ACCURATE")])
+def test_adapter_on_several_gpus_matches_oracle(port_oracle, sampling, tiling):
+    """TilingAlgorithmGPU constructed with a device list: the single process shards the batch over 3 ranks
+    (swgpu_multi_*; the GPUs of the box, shared when there are fewer) and hands the merged nodes to the sink."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if not os.path.exists(DRIVER):
+        pytest.skip("oracle/_ref/adapter_driver was not built (needs /root/reference at build time)")
+    from oracle import sworacle
+    import schwarzwald_b200 as sw
+    n, seed, max_pts, threads = 60_000, 9, 300, 2
+    env = dict(os.environ, SWGPU_TEST_GPUS=str(torch.cuda.device_count()))
+    out = subprocess.run([DRIVER, str(n), str(seed), sampling, tiling, str(max_pts), str(threads), "0", "3"],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[-1] == "PROGRESS %d of %d" % (n, n)
+    got = {}
+    for ln in lines[:-1]:
+        name, count, digest = ln.split()
+        got[name] = (int(count), int(digest, 16))
+    xyz = _driver_points(n, seed)
+    bmin, bmax = np.zeros(3), np.full(3, 100.0)
+    spacing = sw.spacing_from_diagonal_fraction(bmin, bmax)
+    params = sworacle.make_params(sampling, tiling, spacing, bmin, bmax, max_points_per_node=max_pts, concurrency=threads)
+    want = port_oracle.tile(params, xyz).as_dict()
+    assert sorted(got) == sorted(want)
+    for name, ids in want.items():
+        assert got[name][0] == len(ids), name
+        assert got[name][1] == _fnv1a(np.ascontiguousarray(xyz[ids.astype(np.int64)]).tobytes()), name
