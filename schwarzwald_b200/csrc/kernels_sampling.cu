@@ -1336,15 +1336,42 @@ md_hash_insert_kernel(const u64* __restrict__ in_key, const u32* __restrict__ ce
 // nbr row: [0] = earlier count | later count << 8, [1 ...] = earlier cells, then later cells.
 // counters: [0] pop ticket, [1] next free slot of acc_xyz, [2] error flag, [3] active points,
 //           [4] cell count (node_rle), [5] analysed cells, [6] push ticket
-__global__ void __launch_bounds__(256)
-md_neighbors_kernel(const u64* __restrict__ in_key, const u32* __restrict__ cell_start, u32 n_cells, int cell_shift,
-                    int cell_levels, int node_levels, const unsigned char* __restrict__ cell_active,
-                    const u64* __restrict__ hkeys, const u32* __restrict__ hvals, u32 mask, u32* __restrict__ nbr,
-                    u32* __restrict__ deps, u32* __restrict__ queue, u32* __restrict__ counters)
+// The ready queue is split into mq.n independent queues (cell c belongs to queue (c / 64) mod n), each with its
+// own ticket, push and analysed-cell counters on separate 128-byte lines: at the deep levels a sweep level has
+// tens of millions of cells, and one pop and one push per cell on a single address serialise in one L2 slice
+// (measured: 204 -> 75 ms for 54 M cells).  Queue q owns queue[q * cap, (q + 1) * cap).
+#define MD_QUEUE_CHUNK 64
+#define MD_MAX_QUEUES 64
+#define MDQ_POP 0
+#define MDQ_PUSH 32
+#define MDQ_ANALYSED 64
+#define MDQ_STRIDE 96
+#define MDQ_BASE 32 /* u32 index of queue 0's counters inside `counters` */
+struct MdQueues
 {
-  const u32 c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= n_cells || !cell_active[c])
-    return;
+  u32 n;   // number of queues (1 .. MD_MAX_QUEUES)
+  u32 cap; // entries per queue
+};
+
+__device__ __forceinline__ u32
+md_queue_of(u32 cell, const MdQueues& mq)
+{
+  return (cell / MD_QUEUE_CHUNK) % mq.n;
+}
+
+__device__ __forceinline__ u32*
+md_queue_counters(u32* counters, u32 q)
+{
+  return counters + MDQ_BASE + q * MDQ_STRIDE;
+}
+
+// neighbour row + dependency counter of one analysed cell; returns the number of earlier neighbours
+__device__ __forceinline__ u32
+md_neighbors_of(u32 c, const u64* __restrict__ in_key, const u32* __restrict__ cell_start, int cell_shift,
+                int cell_levels, int node_levels, const unsigned char* __restrict__ cell_active,
+                const u64* __restrict__ hkeys, const u32* __restrict__ hvals, u32 mask, u32* __restrict__ nbr,
+                u32* __restrict__ deps)
+{
   u32* out = nbr + (size_t)c * MD_NBR_SLOTS;
   u32 later[26];
   u32 n_early = 0, n_late = 0;
@@ -1390,9 +1417,38 @@ md_neighbors_kernel(const u64* __restrict__ in_key, const u32* __restrict__ cell
     out[1 + n_early + k] = later[k];
   out[0] = n_early | (n_late << 8);
   deps[c] = n_early;
-  atomicAdd(&counters[5], 1u);
-  if (n_early == 0)
-    queue[atomicAdd(&counters[6], 1u)] = c;
+  return n_early;
+}
+
+__global__ void __launch_bounds__(256)
+md_neighbors_kernel(const u64* __restrict__ in_key, const u32* __restrict__ cell_start, u32 n_cells, int cell_shift,
+                    int cell_levels, int node_levels, const unsigned char* __restrict__ cell_active,
+                    const u64* __restrict__ hkeys, const u32* __restrict__ hvals, u32 mask, u32* __restrict__ nbr,
+                    u32* __restrict__ deps, u32* __restrict__ queue, u32* __restrict__ counters, MdQueues mq)
+{
+  const u32 c = blockIdx.x * 256 + threadIdx.x;
+  const bool act = c < n_cells && cell_active[c];
+  u32 n_early_out = 1;
+  if (act)
+    n_early_out = md_neighbors_of(c, in_key, cell_start, cell_shift, cell_levels, node_levels, cell_active, hkeys, hvals,
+                                  mask, nbr, deps);
+  // the 32 cells of a warp belong to one queue (MD_QUEUE_CHUNK = 64 consecutive cells): one atomic per warp for
+  // the analysed-cell count and one for the cells that are ready at once
+  const u32 lane = threadIdx.x & 31;
+  const u32 q = md_queue_of(c, mq);
+  u32* qc = md_queue_counters(counters, q);
+  const u32 am = __ballot_sync(0xffffffffu, act);
+  const u32 rm = __ballot_sync(0xffffffffu, act && n_early_out == 0);
+  u32 base = 0;
+  if (lane == 0) {
+    if (am)
+      atomicAdd(qc + MDQ_ANALYSED, (u32)__popc(am));
+    if (rm)
+      base = atomicAdd(qc + MDQ_PUSH, (u32)__popc(rm));
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (act && n_early_out == 0)
+    queue[(size_t)q * mq.cap + base + __popc(rm & lanemask_lt())] = c;
 }
 
 #define MD_QUEUE_EMPTY 0xffffffffu
@@ -1411,30 +1467,49 @@ st_release_u32(u32* p, u32 v)
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Takes the next ready cell.  Every analysed cell is pushed exactly once (when its last earlier neighbour
-// finishes, or by md_neighbors_kernel when it has none), so tickets below the analysed-cell count are
-// always served; whoever waits, waits on its own queue slot.  Returns MD_QUEUE_EMPTY when all cells are
-// handed out.  Called by one thread.
+// Takes the next ready cell of queue q.  Every analysed cell is pushed exactly once (when its last earlier
+// neighbour finishes, or by md_neighbors_kernel when it has none), so tickets below the queue's analysed-cell
+// count are always served; whoever waits, waits on its own queue slot.  Returns MD_QUEUE_EMPTY when all cells of
+// the queue are handed out.  Called by one thread.
 __device__ __forceinline__ u32
-md_pop_cell(const u32* queue, u32* counters)
+md_pop_cell(const u32* queue, u32* counters, u32 q, const MdQueues& mq)
 {
-  const u32 t = atomicAdd(&counters[0], 1u);
-  if (t >= __ldcg(&counters[5]))
+  u32* qc = md_queue_counters(counters, q);
+  const u32 t = atomicAdd(qc + MDQ_POP, 1u);
+  if (t >= __ldcg(qc + MDQ_ANALYSED))
     return MD_QUEUE_EMPTY;
   u32 c;
-  while ((c = ld_acquire_u32(queue + t)) == MD_QUEUE_EMPTY)
+  const u32* slot = queue + (size_t)q * mq.cap + t;
+  while ((c = ld_acquire_u32(slot)) == MD_QUEUE_EMPTY)
     __nanosleep(100);
   return c;
+}
+
+// The same over all queues, starting at the caller's home queue `q` (updated): a group works on its home queue
+// until that is handed out, then helps with the next one.  Every queue keeps its home groups until it is empty,
+// so a pushed cell is always claimed.
+__device__ __forceinline__ u32
+md_pop_any(const u32* queue, u32* counters, u32& q, u32& visited, const MdQueues& mq)
+{
+  while (visited < mq.n) {
+    const u32 c = md_pop_cell(queue, counters, q, mq);
+    if (c != MD_QUEUE_EMPTY)
+      return c;
+    q = (q + 1) % mq.n;
+    ++visited;
+  }
+  return MD_QUEUE_EMPTY;
 }
 
 // This cell is finished (its accepted points and descriptor are written and fenced): release the later
 // neighbours, queue those that have become ready.  Called by up to 26 threads, one per later neighbour.
 __device__ __forceinline__ void
-md_release_later(u32 cell, u32* deps, u32* queue, u32* counters)
+md_release_later(u32 cell, u32* deps, u32* queue, u32* counters, const MdQueues& mq)
 {
   if (atomicSub(&deps[cell], 1u) == 1u) {
     __threadfence(); // everything the other earlier neighbours published is visible before the push
-    st_release_u32(queue + atomicAdd(&counters[6], 1u), cell);
+    const u32 q = md_queue_of(cell, mq);
+    st_release_u32(queue + (size_t)q * mq.cap + atomicAdd(md_queue_counters(counters, q) + MDQ_PUSH, 1u), cell);
   }
 }
 
@@ -1503,16 +1578,17 @@ md_resolve_warp(bool cand, double px, double py, double pz, double threshold, do
 __global__ void __launch_bounds__(256)
 md_wave_warp_kernel(const double* __restrict__ P, const u32* __restrict__ cell_start, const u32* __restrict__ nbr,
                     unsigned char* __restrict__ state, u64* desc, double* acc_xyz, u32* deps, u32* queue,
-                    u32* counters, double threshold)
+                    u32* counters, double threshold, MdQueues mq)
 {
   __shared__ double s_acc[8][MDW_WARP_CAP * 3];
   const u32 lane = threadIdx.x & 31;
   double* own = s_acc[threadIdx.x >> 5];  // own accepted points first: they reject most of a dense cell
   double* nacc = own + MD_OWN_CAP * 3;    // then the neighbours' accepted points
+  u32 home = (blockIdx.x * 8u + (threadIdx.x >> 5)) % mq.n, visited = 0;
   while (true) {
     u32 c = 0;
     if (lane == 0)
-      c = md_pop_cell(queue, counters);
+      c = md_pop_any(queue, counters, home, visited, mq);
     c = __shfl_sync(0xffffffffu, c, 0);
     if (c == MD_QUEUE_EMPTY)
       break;
@@ -1572,12 +1648,10 @@ md_wave_warp_kernel(const double* __restrict__ P, const u32* __restrict__ cell_s
       if (valid)
         state[i] = accepted ? MD_ACCEPTED : MD_REJECTED;
     }
-    // publish the accepted points of this cell
-    u32 off = 0;
+    // publish the accepted points of this cell in the cell's own range of acc_xyz (one slot per point of the
+    // level, so no allocation is needed)
+    const u32 off = b;
     if (n_own) {
-      if (lane == 0)
-        off = atomicAdd(&counters[1], n_own);
-      off = __shfl_sync(0xffffffffu, off, 0);
       for (u32 k = lane; k < n_own; k += 32) {
         double* dst = acc_xyz + 3 * (size_t)(off + k);
         __stcg(dst, own[3 * k]);
@@ -1591,7 +1665,81 @@ md_wave_warp_kernel(const double* __restrict__ P, const u32* __restrict__ cell_s
     __threadfence();
     __syncwarp();
     if (lane < n_late)
-      md_release_later(nb[1 + nn + lane], deps, queue, counters);
+      md_release_later(nb[1 + nn + lane], deps, queue, counters, mq);
+  }
+}
+
+// one THREAD per cell (the deep, sparse levels: tens of millions of cells holding a handful of points each; a warp
+// per cell leaves 30 lanes idle and is bound by the per-cell latency of queue, descriptor and neighbour loads, so
+// 32 times as many cells in flight win).  The accepted points of the cell go straight into acc_xyz at a range
+// reserved for the cell's point count (acc_xyz holds one slot per point of the level), which doubles as the list
+// the cell's later points are tested against.
+__global__ void __launch_bounds__(256)
+md_wave_thread_kernel(const double* __restrict__ P, const u32* __restrict__ cell_start, const u32* __restrict__ nbr,
+                      unsigned char* __restrict__ state, u64* desc, double* acc_xyz, u32* deps, u32* queue,
+                      u32* counters, double threshold, MdQueues mq)
+{
+  const u32 lane = threadIdx.x & 31;
+  u32 home = (blockIdx.x * 8u + (threadIdx.x >> 5)) % mq.n, visited = 0;
+  while (visited < mq.n) {
+    // one ticket atomic per 32 cells: tens of millions of same-address atomics serialise in one L2 slice
+    __syncwarp();
+    u32* qc = md_queue_counters(counters, home);
+    u32 t0 = 0;
+    if (lane == 0)
+      t0 = atomicAdd(qc + MDQ_POP, 32u);
+    t0 = __shfl_sync(0xffffffffu, t0, 0);
+    const u32 analysed = __ldcg(qc + MDQ_ANALYSED);
+    if (t0 >= analysed) { // this queue is handed out: help with the next one
+      home = (home + 1) % mq.n;
+      ++visited;
+      continue;
+    }
+    const u32 t = t0 + lane;
+    if (t >= analysed)
+      continue;
+    u32 c;
+    const u32* slot = queue + (size_t)home * mq.cap + t;
+    while ((c = ld_acquire_u32(slot)) == MD_QUEUE_EMPTY)
+      __nanosleep(100);
+    const u32 b = cell_start[c], e = cell_start[c + 1];
+    const u32* nb = nbr + (size_t)c * MD_NBR_SLOTS;
+    const u32 hdr = nb[0];
+    const u32 nn = hdr & 0xffu, n_late = hdr >> 8;
+    const u32 off = b; // the cell's own range of acc_xyz (one slot per point of the level): no allocation atomic
+    double* own = acc_xyz + 3 * (size_t)off;
+    u32 n_own = 0;
+    for (u32 i = b; i < e; ++i) {
+      if (state[i] != MD_UNDECIDED)
+        continue;
+      const double px = P[3 * (size_t)i], py = P[3 * (size_t)i + 1], pz = P[3 * (size_t)i + 2];
+      bool cand = true;
+      for (u32 k = 0; k < n_own && cand; ++k)
+        cand = !md_in_range(px, py, pz, __ldcg(own + 3 * k), __ldcg(own + 3 * k + 1), __ldcg(own + 3 * k + 2), threshold);
+      for (u32 j = 0; j < nn && cand; ++j) {
+        const u64 d = __ldcg(desc + nb[1 + j]);
+        const u32 cnt = (u32)(d >> 32) & 0xffu;
+        const double* src = acc_xyz + 3 * (size_t)(u32)d;
+        for (u32 k = 0; k < cnt && cand; ++k)
+          cand = !md_in_range(px, py, pz, __ldcg(src + 3 * k), __ldcg(src + 3 * k + 1), __ldcg(src + 3 * k + 2), threshold);
+      }
+      if (cand) {
+        if (n_own < MD_OWN_CAP) {
+          __stcg(own + 3 * n_own, px);
+          __stcg(own + 3 * n_own + 1, py);
+          __stcg(own + 3 * n_own + 2, pz);
+          ++n_own;
+        } else {
+          atomicExch(counters + 2, 1u); // cannot happen for cells of side < 2 spacings; reported, never silent
+        }
+      }
+      state[i] = cand ? MD_ACCEPTED : MD_REJECTED;
+    }
+    __threadfence();
+    __stcg(desc + c, MD_DESC_DONE | ((u64)n_own << 32) | off);
+    __threadfence();
+    for (u32 l = 0; l < n_late; ++l)
+      md_release_later(nb[1 + nn + l], deps, queue, counters, mq);
   }
 }
 
@@ -1603,7 +1751,7 @@ template<int T>
 __global__ void __launch_bounds__(T)
 md_wave_cta_kernel(const double* __restrict__ P, const u32* __restrict__ cell_start, const u32* __restrict__ nbr,
                    unsigned char* __restrict__ state, u64* desc, double* acc_xyz, u32* deps, u32* queue,
-                   u32* counters, double threshold)
+                   u32* counters, double threshold, MdQueues mq)
 {
   constexpr int WARPS = T / 32;
   extern __shared__ __align__(16) unsigned char md_smem[];
@@ -1617,7 +1765,7 @@ md_wave_cta_kernel(const double* __restrict__ P, const u32* __restrict__ cell_st
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   while (true) {
     if (tid == 0)
-      s_c = md_pop_cell(queue, counters);
+      s_c = md_pop_cell(queue, counters, 0u, mq);
     __syncthreads();
     const u32 c = s_c;
     if (c == MD_QUEUE_EMPTY)
@@ -1709,9 +1857,9 @@ md_wave_cta_kernel(const double* __restrict__ P, const u32* __restrict__ cell_st
         state[i] = s_flag[tid] ? MD_ACCEPTED : MD_REJECTED;
     }
     const u32 n_own = s_nown;
-    if (n_own) {
+    if (n_own) { // the cell's own range of acc_xyz (one slot per point of the level)
       if (tid == 0)
-        s_off = atomicAdd(&counters[1], n_own);
+        s_off = b;
       __syncthreads();
       if (tid < n_own) {
         double* dst = acc_xyz + 3 * (size_t)(s_off + tid);
@@ -1726,7 +1874,7 @@ md_wave_cta_kernel(const double* __restrict__ P, const u32* __restrict__ cell_st
     __threadfence();
     __syncthreads();
     if (tid < n_late)
-      md_release_later(nb[1 + nn + tid], deps, queue, counters);
+      md_release_later(nb[1 + nn + tid], deps, queue, counters, mq);
   }
 }
 
@@ -1747,7 +1895,7 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
   MD_TRY(grow(sc.cell_tile_rank0, tiles * 4));
   MD_TRY(grow(sc.state, n));
   MD_TRY(grow(sc.acc_xyz, n * 24));
-  MD_TRY(grow(sc.counters, 64));
+  MD_TRY(grow(sc.counters, (MDQ_BASE + MD_MAX_QUEUES * MDQ_STRIDE) * 4));
   if (a.in_idx)
     MD_TRY(grow(sc.lpos, n * 24));
 
@@ -1758,7 +1906,7 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
   const int cell_shift = shift_for_levels(cell_levels);
 
   u32* counters = static_cast<u32*>(sc.counters.p);
-  MD_TRY(cudaMemsetAsync(counters, 0, 64, stream));
+  MD_TRY(cudaMemsetAsync(counters, 0, (MDQ_BASE + MD_MAX_QUEUES * MDQ_STRIDE) * 4, stream));
   launch_node_rle(a.in_key, n, cell_shift, static_cast<u32*>(sc.cell_start.p), static_cast<u32*>(sc.cell_tile_rank0.p),
                   counters + 4, sc.status, sc.ticket, stream);
   md_setup_kernel<<<(u32)tiles, SWP_THREADS, 0, stream>>>(a, static_cast<unsigned char*>(sc.state.p),
@@ -1782,10 +1930,40 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
   MD_TRY(grow(sc.nbr, (size_t)n_cells * MD_NBR_SLOTS * 4));
   MD_TRY(grow(sc.desc, (size_t)n_cells * 8));
   MD_TRY(grow(sc.deps, (size_t)n_cells * 4));
-  MD_TRY(grow(sc.queue, (size_t)n_cells * 4));
+  // group size by the average number of analysed points per cell: the time of one cell is on the critical path
+  // of the dependency graph, so dense levels get a whole CTA per cell, the sparse ones a warp or a thread
+  int mode = 0;
+  static int thread_below = -1; // average analysed points per cell below which a thread takes a cell
+  if (thread_below < 0) {
+    const char* env = getenv("SWGPU_MD_THREAD_BELOW");
+    thread_below = env ? atoi(env) : 6;
+  }
+  if (const char* env = getenv("SWGPU_MD_GROUP")) // tuning experiments: 1, 32, 256 or 1024
+    mode = atoi(env);
+  if (mode != 1 && mode != 32 && mode != 256 && mode != 1024)
+    mode = (u64)n_active >= 384ull * n_cells
+             ? 1024
+             : ((u64)n_active >= 48ull * n_cells ? 256 : ((u64)n_active < (u64)thread_below * n_cells ? 1 : 32));
+  // ready queues: one for the CTA kernels (few, heavy cells), up to MD_MAX_QUEUES for the warp / thread kernels
+  MdQueues mq;
+  mq.n = 1;
+  if (mode == 1 || mode == 32) {
+    static int max_queues = -1;
+    if (max_queues < 0) {
+      const char* env = getenv("SWGPU_MD_QUEUES");
+      max_queues = env ? atoi(env) : MD_MAX_QUEUES;
+      if (max_queues < 1 || max_queues > MD_MAX_QUEUES)
+        max_queues = MD_MAX_QUEUES;
+    }
+    mq.n = n_cells / 16384u;
+    mq.n = mq.n < 1u ? 1u : (mq.n > (u32)max_queues ? (u32)max_queues : mq.n);
+  }
+  mq.cap = ((n_cells + MD_QUEUE_CHUNK * mq.n - 1) / (MD_QUEUE_CHUNK * mq.n)) * MD_QUEUE_CHUNK;
+  const size_t queue_entries = (size_t)mq.n * mq.cap;
+  MD_TRY(grow(sc.queue, queue_entries * 4));
   MD_TRY(grow(sc.cell_active, (size_t)n_cells));
   MD_TRY(cudaMemsetAsync(sc.hkeys.p, 0, (size_t)cap * 8, stream));
-  MD_TRY(cudaMemsetAsync(sc.queue.p, 0xff, (size_t)n_cells * 4, stream));
+  MD_TRY(cudaMemsetAsync(sc.queue.p, 0xff, queue_entries * 4, stream));
   const double* P = a.in_idx ? static_cast<const double*>(sc.lpos.p) : a.pos_sorted;
   const u32* cell_start = static_cast<const u32*>(sc.cell_start.p);
   u32* nbr = static_cast<u32*>(sc.nbr.p);
@@ -1802,23 +1980,26 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
   md_neighbors_kernel<<<cgrid, 256, 0, stream>>>(a.in_key, cell_start, n_cells, cell_shift, cell_levels, a.node_levels,
                                                  cell_active, static_cast<const u64*>(sc.hkeys.p),
                                                  static_cast<const u32*>(sc.hvals.p), cap - 1, nbr, deps, queue,
-                                                 counters);
+                                                 counters, mq);
 
   // persistent dataflow kernel: every resident group pops ready cells until all analysed cells are done
   // co-resident group counts and the dynamic shared-memory opt-in are per device
-  static int warp_blocks_of[64] = {}, cta256_blocks_of[64] = {}, cta1024_blocks_of[64] = {};
+  static int warp_blocks_of[64] = {}, cta256_blocks_of[64] = {}, cta1024_blocks_of[64] = {}, thread_blocks_of[64] = {};
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
   const int slot = (cur_dev >= 0 && cur_dev < 64) ? cur_dev : 0;
   int& warp_blocks = warp_blocks_of[slot];
   int& cta256_blocks = cta256_blocks_of[slot];
   int& cta1024_blocks = cta1024_blocks_of[slot];
+  int& thread_blocks = thread_blocks_of[slot];
   if (!warp_blocks) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, md_wave_warp_kernel, 256, 0);
     warp_blocks = sms * (per_sm > 0 ? per_sm : 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, md_wave_thread_kernel, 256, 0);
+    thread_blocks = sms * (per_sm > 0 ? per_sm : 1);
     cudaFuncSetAttribute(md_wave_cta_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDW_CTA_SMEM(256));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, md_wave_cta_kernel<256>, 256, MDW_CTA_SMEM(256));
     cta256_blocks = sms * (per_sm > 0 ? per_sm : 1);
@@ -1826,26 +2007,24 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, md_wave_cta_kernel<1024>, 1024, MDW_CTA_SMEM(1024));
     cta1024_blocks = sms * (per_sm > 0 ? per_sm : 1);
   }
-  // group size by the average number of analysed points per cell: the time of one cell is on the
-  // critical path of the dependency graph, so dense levels get a whole CTA per cell
-  int mode = 0;
-  if (const char* env = getenv("SWGPU_MD_GROUP")) // tuning experiments: 32, 256 or 1024
-    mode = atoi(env);
-  if (mode != 32 && mode != 256 && mode != 1024)
-    mode = (u64)n_active >= 384ull * n_cells ? 1024 : ((u64)n_active >= 48ull * n_cells ? 256 : 32);
   if (mode == 1024) {
     const u32 blocks = n_cells < (u32)cta1024_blocks ? n_cells : (u32)cta1024_blocks;
     md_wave_cta_kernel<1024><<<blocks, 1024, MDW_CTA_SMEM(1024), stream>>>(P, cell_start, nbr, state, desc, acc_xyz,
-                                                                          deps, queue, counters, a.threshold);
+                                                                          deps, queue, counters, a.threshold, mq);
   } else if (mode == 256) {
     const u32 blocks = n_cells < (u32)cta256_blocks ? n_cells : (u32)cta256_blocks;
     md_wave_cta_kernel<256><<<blocks, 256, MDW_CTA_SMEM(256), stream>>>(P, cell_start, nbr, state, desc, acc_xyz, deps,
-                                                                        queue, counters, a.threshold);
+                                                                        queue, counters, a.threshold, mq);
+  } else if (mode == 1) {
+    const u32 want = (n_cells + 255) / 256;
+    const u32 blocks = want < (u32)thread_blocks ? want : (u32)thread_blocks;
+    md_wave_thread_kernel<<<blocks, 256, 0, stream>>>(P, cell_start, nbr, state, desc, acc_xyz, deps, queue, counters,
+                                                      a.threshold, mq);
   } else {
     const u32 want = (n_cells + 7) / 8;
     const u32 blocks = want < (u32)warp_blocks ? want : (u32)warp_blocks;
     md_wave_warp_kernel<<<blocks, 256, 0, stream>>>(P, cell_start, nbr, state, desc, acc_xyz, deps, queue, counters,
-                                                    a.threshold);
+                                                    a.threshold, mq);
   }
   MD_TRY(cudaMemcpyAsync(sc.h_pinned, counters + 2, 4, cudaMemcpyDeviceToHost, stream));
   MD_TRY(cudaStreamSynchronize(stream));
