@@ -1293,6 +1293,10 @@ md_setup_kernel(SwMinDistArgs a, unsigned char* __restrict__ state, double* __re
     atomicAdd(n_active, my_active);
 }
 
+// Uniform hash on purpose.  A locality-preserving variant (hash the 4 x 4 x 4 block, keep the cell's place inside
+// a 64-slot group) halves md_hash_insert_kernel but makes md_neighbors_kernel slower (109 vs 91 ms over the levels
+// of 125 M terrain points): two thirds of the 26 neighbour probes look for cells that do not exist and have to
+// walk the clustered groups to the next empty slot.
 __device__ __forceinline__ u32
 md_hash(u64 code, u32 mask)
 {
