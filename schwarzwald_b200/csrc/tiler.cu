@@ -180,6 +180,9 @@ struct swgpu_tiler
   DevBuf list_key[4], list_idx[4]; // (key, gid) lists of the sweep: input, fetched, merged, remainder
   DevBuf st_slot, st_cnt, st_boff, st_scan, st_gcount, st_lo, st_found, st_cumf;
   DevBuf st_nidx, st_ncnt, st_nflags, st_nsrc, st_nfirst, st_nids;
+  // RANDOM_GRID never reads positions: its sweep lists carry the ORIGINAL point index (the sort's permutation)
+  // instead of the sorted position, so the output ids need no composition with the permutation afterwards
+  bool out_idx_original = false;
   const double* sample_pos = nullptr; // positions the selection kernels read, indexed by the lists' ids
   const u32* gcount_override = nullptr;
 
@@ -840,7 +843,8 @@ run_batch(swgpu_tiler* h)
 
   // level-synchronous sweep
   const u64* in_key = h->keys[0].as<u64>();
-  const u32* in_idx = nullptr;
+  h->out_idx_original = !needs_positions(h->prm.sampling);
+  const u32* in_idx = h->out_idx_original ? h->vals[0].as<u32>() : nullptr;
   u64 count = n;
   u64* rem_key[2] = { h->keys[1].as<u64>(), h->wkey2.as<u64>() };
   u32* rem_idx[2] = { h->vals[1].as<u32>(), h->widx2.as<u32>() };
@@ -1591,6 +1595,13 @@ swgpu_result_size(swgpu_handle h, uint64_t* n_nodes, uint64_t* n_point_ids)
 static void
 compose_output_ids(swgpu_tiler* h, u32* out_device)
 {
+  if (h->out_idx_original) { // the lists carried original indices all along
+    if (h->global_ids)
+      launch_compose_ids(h->global_ids, h->out_idx.as<u32>(), h->out_count, out_device, h->stream);
+    else
+      cudaMemcpyAsync(out_device, h->out_idx.p, h->out_count * 4, cudaMemcpyDeviceToDevice, h->stream);
+    return;
+  }
   if (h->global_ids)
     launch_compose_ids_mapped(h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->global_ids, h->out_count, out_device,
                               h->stream);
@@ -1709,7 +1720,7 @@ payload_source(const swgpu_tiler* h, const double** xyz, const u32** perm)
     *perm = nullptr;
   } else {
     *xyz = h->d_xyz;
-    *perm = h->vals[0].as<u32>();
+    *perm = h->out_idx_original ? nullptr : h->vals[0].as<u32>(); // the lists may hold original indices already
   }
 }
 
@@ -1718,7 +1729,7 @@ payload_checks(swgpu_tiler* h)
 {
   if (!h->batch_done)
     return fail(h, SW_ERR_STATE, "no batch has been indexed");
-  if (!h->d_xyz && h->n)
+  if (!h->multi_batch && !h->d_xyz && h->n)
     return fail(h, SW_ERR_STATE, "the positions of the batch are gone");
   return SW_OK;
 }
@@ -1732,6 +1743,16 @@ swgpu_get_payload_pnts_device(swgpu_handle h, float* xyz_f32_device)
   if (rc)
     return rc;
   cudaSetDevice(h->device);
+  if (h->multi_batch) { // node-major global ids of the store, positions of all batches
+    const u64 n_ids = store_id_total(h);
+    CK(h->ids_tmp.ensure(std::max<u64>(n_ids, 1) * 4));
+    const int rc2 = store_get_nodes(h, nullptr, h->ids_tmp.as<u32>(), true);
+    if (rc2)
+      return rc2;
+    launch_payload_pnts(h->store_xyz.as<double>(), nullptr, h->ids_tmp.as<u32>(), n_ids, xyz_f32_device, h->stream);
+    CK(cudaGetLastError());
+    return SW_OK;
+  }
   const double* src = nullptr;
   const u32* perm = nullptr;
   payload_source(h, &src, &perm);
@@ -1746,11 +1767,12 @@ swgpu_get_payload_pnts(swgpu_handle h, float* xyz_f32_host)
   if (!h || !xyz_f32_host)
     return SW_ERR_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
-  CK(h->payload_tmp.ensure(std::max<u64>(h->out_count, 1) * 12));
+  const u64 n_out = h->multi_batch ? store_id_total(h) : h->out_count;
+  CK(h->payload_tmp.ensure(std::max<u64>(n_out, 1) * 12));
   const int rc = swgpu_get_payload_pnts_device(h, h->payload_tmp.as<float>());
   if (rc)
     return rc;
-  CK(cudaMemcpyAsync(xyz_f32_host, h->payload_tmp.p, h->out_count * 12, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(xyz_f32_host, h->payload_tmp.p, n_out * 12, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return SW_OK;
 }
@@ -1764,6 +1786,46 @@ swgpu_get_payload_las_device(swgpu_handle h, int32_t* xyz_i32_device, sw_las_nod
   if (rc)
     return rc;
   cudaSetDevice(h->device);
+  if (h->multi_batch) {
+    const u64 n_nodes = store_node_total(h), n_ids = store_id_total(h);
+    if (!n_nodes)
+      return SW_OK;
+    std::vector<sw_node> nodes(n_nodes);
+    CK(h->ids_tmp.ensure(std::max<u64>(n_ids, 1) * 4));
+    rc = store_get_nodes(h, nodes.data(), h->ids_tmp.as<u32>(), true);
+    if (rc)
+      return rc;
+    std::vector<double> hdr(n_nodes * 4);
+    std::vector<u64> first(n_nodes);
+    for (u64 row = 0; row < n_nodes; ++row) {
+      double mn[3], mx[3];
+      node_bounds_of(h, nodes[row].index, nodes[row].levels, mn, mx);
+      const double scale = las_scale_from_bounds(mn, mx);
+      hdr[4 * row + 0] = mn[0];
+      hdr[4 * row + 1] = mn[1];
+      hdr[4 * row + 2] = mn[2];
+      hdr[4 * row + 3] = scale;
+      first[row] = nodes[row].first;
+      if (headers_host) {
+        sw_las_node_header& o = headers_host[row];
+        for (int a = 0; a < 3; ++a) {
+          o.offset[a] = mn[a];
+          o.max[a] = mx[a];
+        }
+        o.scale = scale;
+        o.reserved = 0;
+      }
+    }
+    CK(h->node_hdr.ensure(n_nodes * 32));
+    CK(h->st_nfirst.ensure((n_nodes + 1) * 8));
+    CK(cudaMemcpyAsync(h->node_hdr.p, hdr.data(), n_nodes * 32, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->st_nfirst.p, first.data(), n_nodes * 8, cudaMemcpyHostToDevice, h->stream));
+    launch_payload_las(h->store_xyz.as<double>(), nullptr, h->ids_tmp.as<u32>(), n_ids, h->st_nfirst.as<u64>(),
+                       (u32)n_nodes, h->node_hdr.as<double>(), xyz_i32_device, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return SW_OK;
+  }
   if (!h->node_count)
     return SW_OK;
   // per-node header values on the host (a few thousand nodes), then one kernel over all points
@@ -1810,11 +1872,12 @@ swgpu_get_payload_las(swgpu_handle h, int32_t* xyz_i32_host, sw_las_node_header*
   if (!h || !xyz_i32_host)
     return SW_ERR_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
-  CK(h->payload_tmp.ensure(std::max<u64>(h->out_count, 1) * 12));
+  const u64 n_out = h->multi_batch ? store_id_total(h) : h->out_count;
+  CK(h->payload_tmp.ensure(std::max<u64>(n_out, 1) * 12));
   const int rc = swgpu_get_payload_las_device(h, h->payload_tmp.as<int32_t>(), headers_host);
   if (rc)
     return rc;
-  CK(cudaMemcpyAsync(xyz_i32_host, h->payload_tmp.p, h->out_count * 12, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(xyz_i32_host, h->payload_tmp.p, n_out * 12, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return SW_OK;
 }
@@ -1861,13 +1924,19 @@ swgpu_gather_attribute_device(swgpu_handle h, const void* src_device, uint32_t w
   if (!h->batch_done)
     return fail(h, SW_ERR_STATE, "no batch has been indexed");
   cudaSetDevice(h->device);
-  CK(h->ids_tmp.ensure(std::max<u64>(h->out_count, 1) * 4));
-  launch_compose_ids(h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, h->ids_tmp.as<u32>(), h->stream);
+  const u32* ids = h->out_idx.as<u32>(); // original indices (RANDOM_GRID), else sorted positions to compose
+  if (h->multi_batch)
+    return fail(h, SW_ERR_STATE, "multi-batch mode: gather by the global ids of swgpu_get_nodes_device_ids instead");
+  if (!h->out_idx_original) {
+    CK(h->ids_tmp.ensure(std::max<u64>(h->out_count, 1) * 4));
+    launch_compose_ids(h->vals[0].as<u32>(), h->out_idx.as<u32>(), h->out_count, h->ids_tmp.as<u32>(), h->stream);
+    ids = h->ids_tmp.as<u32>();
+  }
   if (width == 24)
-    launch_gather_positions(static_cast<const double*>(src_device), h->ids_tmp.as<u32>(), h->out_count,
+    launch_gather_positions(static_cast<const double*>(src_device), ids, h->out_count,
                             static_cast<double*>(dst_device), h->stream);
   else if (width == 1 || width == 2 || width == 3 || width == 4 || width == 8 || width == 12 || width == 16)
-    launch_gather_bytes(src_device, h->ids_tmp.as<u32>(), h->out_count, width, dst_device, h->stream);
+    launch_gather_bytes(src_device, ids, h->out_count, width, dst_device, h->stream);
   else
     return fail(h, SW_ERR_INVALID_ARGUMENT, "unsupported attribute width");
   CK(cudaGetLastError());

@@ -164,3 +164,30 @@ def test_multi_batch_mode_resets_and_refuses_sharding():
         t.set_multi_batch(False)
         r = t.tile(xyz[:20_000].copy())
         assert int(r.nodes["count"].sum()) == 20_000
+
+
+@pytest.mark.parametrize("sampling,tiling", [("RANDOM_GRID", "FAST"), ("JITTERED", "ACCURATE")])
+def test_multi_batch_writer_payloads(port_oracle, sampling, tiling):
+    """PNTS / LAS position payloads of the final node store (PNTSWriter.cpp:326-342, LASPersistence.h:119-131,160-163)
+    over the positions of ALL batches, against the oracle's payload functions on the same nodes."""
+    _torch_cuda()
+    import schwarzwald_b200 as sw
+    mgb = _golden_mod()
+    xyz, bmin, bmax, spacing = mgb.case_input()
+    sizes = mgb.SPLITS[tiling]
+    host = np.array(xyz, dtype=np.float64, order="C", copy=True)
+    with sw.GpuTiler(sampling, tiling, bmin, bmax, spacing, max_points_per_node=800, concurrency=2) as t:
+        t.set_multi_batch(True)
+        lo = 0
+        for n in sizes:
+            t.build_execution_graph(host[lo:lo + n])
+            lo += n
+        t.finalize()
+        res = t.result()
+        pnts = t.payload_pnts()
+        las, headers = t.payload_las()
+    assert np.array_equal(pnts, port_oracle.payload_pnts(host, res.ids))
+    w_las, w_headers = port_oracle.payload_las(host, res.ids, res.nodes, (bmin, bmax))
+    assert np.array_equal(las, w_las)
+    for f in ("offset", "scale", "max"):
+        assert np.array_equal(headers[f], w_headers[f])
