@@ -323,6 +323,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle check of the result")
+    ap.add_argument("--no-payload", action="store_true", help="skip the attribute / writer-payload leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -435,6 +436,65 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = n_total / (ms_per_step * 1e-3)
+
+    # ---- payload leg: the same step with the attribute permutation north_star names ----------------------------
+    # A 16-byte attribute record per point (LAS point format 2: 14 B, PointBuffer.h:291-304) travels with the point
+    # (N > 1: through the exchange, 44 instead of 28 B per point), and every GPU produces the node-major writer
+    # payloads of its nodes: the attribute records (swgpu_gather_attribute_device) and the float32 positions of
+    # PNTSWriter (swgpu_get_payload_pnts_device).  Reported next to `value`, not inside it: the reference arm's
+    # timed region hands over point ids only, and `value` keeps the same work as that arm.
+    payload = None
+    if not args.no_payload:
+        try:
+            nn0, ni0 = tiler.result_size()
+            attr = torch.empty((max(n_local, 1), 16), dtype=torch.uint8, device=dev)
+            attr.view(torch.int32).random_(0, 2 ** 31 - 1)
+            cap = int(ni0 * 1.05) + 1024
+            out_attr = torch.empty((cap, 16), dtype=torch.uint8, device=dev)
+            out_pnts = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+
+            def step_payload():
+                if world > 1:
+                    tiler.build_execution_graph(xyz, attributes=attr[:n_local])
+                else:
+                    tiler.build_execution_graph(xyz)
+                tiler.finalize()
+                tiler.result_device_ids(ids_dev.data_ptr())
+                if world > 1:
+                    tiler.gather_attributes(out_attr)
+                    tiler.tiler.payload_pnts_device(out_pnts.data_ptr())
+                else:
+                    tiler.gather_attribute_device(attr.data_ptr(), 16, out_attr.data_ptr())
+                    tiler.payload_pnts_device(out_pnts.data_ptr())
+
+            step_payload()
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p_steps = max(1, min(args.steps, 3))
+            p0.record(stream)
+            for _ in range(p_steps):
+                step_payload()
+            p1.record(stream)
+            barrier()
+            p_ms = p0.elapsed_time(p1) / p_steps
+            if world > 1:
+                t = torch.tensor([p_ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                p_ms = float(t.item())
+            payload = {"ms_per_step": p_ms, "value": n_total / (p_ms * 1e-3), "unit": UNIT, "steps": p_steps,
+                       "extra_ms_over_value_step": p_ms - ms_per_step,
+                       "what": "the step of `value` plus: a 16-byte attribute record per point " +
+                               ("through the exchange (44 instead of 28 B per point) and " if world > 1 else "") +
+                               "gathered into node-major order, and the node-major float32 position payload "
+                               "(PNTSWriter) of every node"}
+            del attr, out_attr, out_pnts
+        except Exception as ex:  # the headline numbers above stand on their own
+            import traceback
+            traceback.print_exc()
+            payload = {"error": repr(ex)}
+        torch.cuda.empty_cache()
+        step()  # the parity and e2e legs below look at a result without attributes
+        barrier()
 
     # ---- parity (untimed): this rank's result against the CPU oracle ----------------------------------------
     parity = None
@@ -664,6 +724,8 @@ def main():
                                          "(another cloud and strategy), so value(N) / value(1) is NOT a scaling efficiency",
                                  "same_config_n1": same_config_n1(cfg_name)}),
     }
+    if payload is not None:
+        line["payload"] = payload
     if e2e is not None:
         line["e2e"] = e2e
     if cpu_line is None and not args.no_cpu_baseline and world == 1:

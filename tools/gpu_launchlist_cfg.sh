@@ -6,6 +6,6 @@ mkdir -p gpurun_out
 REGEX='regex:^(morton|onesweep|gather|level|select|argmin|node_|tile_rank|start_nodes|parent|md_|compose|las_|payload|partition|prefix|store_|scan_|merge_|concat_|face_|bin_|root_node|make_gids|key_hist|sort_)'
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name "$REGEX" -c 3000 --csv \
   --log-file gpurun_out/${TAG}_launches.csv python bench.py --config $CFG --points $PTS --steps 1 --warmup 1 \
-  --no-e2e --no-parity --no-cpu-baseline > gpurun_out/${TAG}_launches.log 2>&1
+  --no-e2e --no-parity --no-cpu-baseline --no-payload > gpurun_out/${TAG}_launches.log 2>&1
 echo "ncu rc=$?"; tail -2 gpurun_out/${TAG}_launches.log | cut -c1-600
 python profiles/summarize_launches.py gpurun_out/${TAG}_launches.csv
