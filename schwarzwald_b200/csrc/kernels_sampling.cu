@@ -1603,7 +1603,7 @@ md_wave_warp_kernel(const double* __restrict__ P, const u32* __restrict__ cell_s
     u64 d = 0;
     if (lane < nn)
       d = __ldcg(desc + nb[1 + lane]);
-    const u32 ncnt = (u32)(d >> 32) & 0xffu;
+    const u32 ncnt = (u32)(d >> 32) & 0xffffu;
     const u32 noff = (u32)d;
     u32 incl = ncnt;
 #pragma unroll
@@ -1722,13 +1722,13 @@ md_wave_thread_kernel(const double* __restrict__ P, const u32* __restrict__ cell
         cand = !md_in_range(px, py, pz, __ldcg(own + 3 * k), __ldcg(own + 3 * k + 1), __ldcg(own + 3 * k + 2), threshold);
       for (u32 j = 0; j < nn && cand; ++j) {
         const u64 d = __ldcg(desc + nb[1 + j]);
-        const u32 cnt = (u32)(d >> 32) & 0xffu;
+        const u32 cnt = (u32)(d >> 32) & 0xffffu;
         const double* src = acc_xyz + 3 * (size_t)(u32)d;
         for (u32 k = 0; k < cnt && cand; ++k)
           cand = !md_in_range(px, py, pz, __ldcg(src + 3 * k), __ldcg(src + 3 * k + 1), __ldcg(src + 3 * k + 2), threshold);
       }
       if (cand) {
-        if (n_own < MD_OWN_CAP) {
+        if (n_own < 0xffffu) { // the list lives in the cell's own range of acc_xyz: only the descriptor's 16 bits bound it
           __stcg(own + 3 * n_own, px);
           __stcg(own + 3 * n_own + 1, py);
           __stcg(own + 3 * n_own + 2, pz);
@@ -1781,7 +1781,7 @@ md_wave_cta_kernel(const double* __restrict__ P, const u32* __restrict__ cell_st
       u64 d = 0;
       if (lane < nn)
         d = __ldcg(desc + nb[1 + lane]);
-      const u32 ncnt = (u32)(d >> 32) & 0xffu;
+      const u32 ncnt = (u32)(d >> 32) & 0xffffu;
       u32 incl = ncnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -1920,6 +1920,9 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
   MD_TRY(cudaStreamSynchronize(stream));
   const u32 n_active = sc.h_pinned[0];
   const u32 n_cells = sc.h_pinned[1];
+  // (Coarser cells on the sparse levels - any cell level with side >= spacing gives the same selection - were tried
+  // to cut the per-cell work of the graph: one level coarser costs 240 -> 260 ms at 125 M terrain points, two levels
+  // 820 ms: a cell's points are decided one after the other, so larger cells lengthen every chain.)
   *rounds = 0;
   *launches = 2;
   *bytes = n * (8 + 8 + 1 + (a.in_idx ? 52 : 0));

@@ -104,3 +104,40 @@ def test_min_spacing_check(port_oracle):
     res = port_oracle.tile(params, xyz)
     rep = parity.min_spacing_check(lambda ids: xyz[ids], res.nodes, res.ids, spacing)
     assert not rep["ok"]
+
+
+def test_min_spacing_helpers_use_the_reference_threshold():
+    """too_close_pairs / merged_min_spacing_check (bench.py's MIN_DISTANCE legs): squared distance strictly below
+    (float)(spacing_f * spacing_f) of the node's level, SparseGrid.cpp:11-14 / GridCell.cpp:41-58."""
+    from oracle import parity
+    s = np.float32(0.5)
+    thr = float(np.float32(s * s))
+    d_equal = np.sqrt(thr)  # exactly at the threshold: not a conflict (strict <)
+    pts = np.array([[0, 0, 0], [d_equal, 0, 0], [10, 0, 0], [10, d_equal * 0.999, 0]], np.float64)
+    dx = pts[1] - pts[0]
+    expect = int((dx @ dx) < thr) + 1
+    assert parity.too_close_pairs(pts, 0, s) == expect
+    assert parity.too_close_pairs(pts, 1, s) == 0  # one level deeper: half the spacing
+    assert parity.too_close_pairs(pts[:1], 0, s) == 0
+    # a node split over two ranks: the conflict only shows on the merged node
+    parts = [{(0, 0): pts[[2]]}, {(0, 0): pts[[3]], (1, 3): pts[[0]]}]
+    rep = parity.merged_min_spacing_check(parts, s)
+    assert rep["checked"] and not rep["ok"] and rep["too_close_pairs"] == 1 and rep["n_nodes"] == 2
+    assert parity.merged_min_spacing_check([{}, {}], s)["checked"] is False
+
+
+def test_workload_configs_match_baseline_json():
+    """schwarzwald_b200/workloads.py names the five BASELINE.json configs with their sizes and strategies."""
+    import json
+    import os
+    from schwarzwald_b200 import workloads
+    base = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "BASELINE.json")))
+    sizes = {"c1": 10_000_000, "c2": 100_000_000, "c3": 500_000_000, "c4": 1_000_000_000, "c5": 2_000_000_000}
+    words = {"c1": ("GRID_CENTER", "FAST"), "c2": ("RANDOM_GRID", "FAST"), "c3": ("JITTERED", "FAST"),
+             "c4": ("MIN_DISTANCE", "ACCURATE"), "c5": ("GRID_CENTER",)}
+    for k, (name, text) in enumerate(zip(sorted(sizes), base["configs"])):
+        cfg = workloads.CONFIGS[name]
+        assert cfg["points"] == sizes[name]
+        for w in words[name]:
+            assert w in text and w in (cfg["sampling"], cfg["tiling"])
+    assert workloads.default_config(1) == "c2" and workloads.default_config(8) == "c3"
