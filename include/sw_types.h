@@ -43,6 +43,9 @@ typedef enum sw_tiling {
 #define SW_NODE_TAKE_ALL 1u      /* all points of the visit were taken (count <= max_points_per_node) */
 #define SW_NODE_TERMINAL 2u      /* tile_terminal_node: level >= max_level, stored unsampled */
 #define SW_NODE_RECONSTRUCTED 4u /* FAST finalize: re-sampled copy of the children's points */
+#define SW_NODE_DEEP 8u          /* swgpu_set_deep_node_policy(h, 1): the node sits where the reference would re-index its
+                                  * points with the node as the new root (TilingAlgorithms.cpp:444-483); it holds all
+                                  * remaining points unsampled (set together with SW_NODE_TERMINAL) */
 
 typedef struct sw_params {
   int32_t sampling;             /* sw_sampling */

@@ -72,6 +72,19 @@ int swgpu_finalize(swgpu_handle h);
  * Not combinable with swgpu_set_shard. */
 int swgpu_set_multi_batch(swgpu_handle h, int enable);
 
+/* Nodes below the capacity of a MortonIndex64.  A node at level >= 14 (grid strategies, JITTERED; level 20 for
+ * MIN_DISTANCE never gets there) whose sampling grid would need more than 21 key levels is re-indexed by the
+ * reference with the node as the new root (TilingAlgorithms.cpp:444-483).  That happens when more than
+ * max_points_per_node points share a cell of 1 / 2^15 of the extent, or - in multi-batch runs, where a revisited
+ * node is always sampled (:272-275) - as soon as two points of different batches cannot be told apart above that
+ * level (duplicates, millimetre-quantised LiDAR).  The library does not reproduce the re-root:
+ *   policy 0 (default)  the batch fails with SW_ERR_DEEP_REROOT, like the oracle;
+ *   policy 1            such a node stores all its remaining points unsampled and is flagged
+ *                       SW_NODE_TERMINAL | SW_NODE_DEEP - the same content the reference's re-rooted sampling
+ *                       produces whenever it can separate the points (each in its own cell of the finer grid),
+ *                       a stated deviation otherwise. */
+int swgpu_set_deep_node_policy(swgpu_handle h, int policy);
+
 /* The hand-off that replaces the per-node persist_points() calls (io/PointsPersistence.h:23-31):
  * a node table plus one node-major array of ORIGINAL point indices, Morton-ordered inside each
  * node.  The adapter turns row i into persist_points(refs[first..first+count), bounds, name). */

@@ -16,6 +16,7 @@
 #include "../../include/swgpu.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +25,18 @@
 #include <vector>
 
 namespace {
+
+// SWGPU_TRACE_ALLOC=1: every (re)allocation of a device buffer is reported on stderr with its duration
+static bool
+trace_alloc()
+{
+  static int on = -1;
+  if (on < 0) {
+    const char* e = std::getenv("SWGPU_TRACE_ALLOC");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
 
 struct DevBuf
 {
@@ -35,6 +48,18 @@ struct DevBuf
   {
     if (bytes <= cap)
       return cudaSuccess;
+    const auto t0 = std::chrono::steady_clock::now();
+    struct Report
+    {
+      std::chrono::steady_clock::time_point t0;
+      size_t from, to, keep;
+      ~Report()
+      {
+        if (trace_alloc())
+          std::fprintf(stderr, "[swgpu alloc] %zu -> %zu bytes (keep %zu): %.3f ms\n", from, to, keep,
+                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+      }
+    } report{ t0, cap, bytes, keep_bytes };
     size_t want = bytes;
     if (keep_bytes) // amortise growth of append-only buffers
       want = std::max(bytes, cap + cap / 2);
@@ -100,9 +125,22 @@ struct LevelStore
   DevBuf first; // u64 n_nodes + 1 (exclusive scan of the counts)
   DevBuf flags; // u32 n_nodes
   DevBuf ids;   // u32 n_ids
+  // the rebuild of store_update writes into the level's own spare set and swaps: the sizes of a level only
+  // grow, so after a few batches no allocation happens any more (a set shared by all levels would be
+  // re-allocated on nearly every swap)
+  DevBuf spare_index, spare_first, spare_flags, spare_ids;
   u64 n_nodes = 0;
   u64 n_ids = 0;
 };
+
+// grow with head room (append-only tables): at least `bytes`, twice the old capacity when it has to grow
+cudaError_t
+ensure_amortised(DevBuf& b, size_t bytes)
+{
+  if (bytes <= b.cap)
+    return cudaSuccess;
+  return b.ensure(std::max(bytes, 2 * b.cap));
+}
 
 enum LevelKind
 {
@@ -171,6 +209,7 @@ struct swgpu_tiler
   DevBuf face_flags, face_offs, face_scan, face_rec, face_src;
   u64 face_points_sent = 0, face_points_rejected_upper_bound = 0;
 
+  int deep_policy = 0; // swgpu_set_deep_node_policy
   // multi-batch mode (swgpu_set_multi_batch): the node store that persists between batches
   bool multi_batch = false;
   DevBuf store_xyz;       // positions of every batch, clamped; global point id = row
@@ -869,9 +908,10 @@ run_batch(swgpu_tiler* h)
   for (int levels = first_levels; count > 0 || spans_shards(h, levels); ++levels) {
     const int node_level = levels - 1;
     const LevelKind kind = level_kind(h, node_level);
-    if (kind == KIND_REROOT || levels > 21)
+    const bool deep = kind == KIND_REROOT && h->deep_policy == 1 && levels <= 21;
+    if ((kind == KIND_REROOT && !deep) || levels > 21)
       return fail(h, SW_ERR_DEEP_REROOT, "deep re-root path (TilingAlgorithms.cpp:444-483) is not supported");
-    const bool terminal = (kind == KIND_TERMINAL);
+    const bool terminal = (kind == KIND_TERMINAL) || deep;
     if (!terminal && levels >= 21)
       return fail(h, SW_ERR_DEEP_REROOT, "child level exceeds MortonIndex64 capacity");
     if (count == 0) { // nothing left on this GPU, but the other shards still need our (zero) counts
@@ -890,7 +930,8 @@ run_batch(swgpu_tiler* h)
     u64 n_sel = 0;
     u32 n_nodes_next = 0;
     rc = sweep_level(h, in_key, in_idx, count, levels, /*allow_take_all=*/true, terminal, rem_key[flip],
-                     rem_idx[flip], 0u, &n_sel, false, 0, nodes_known, n_nodes_known, &n_nodes_next);
+                     rem_idx[flip], deep ? SW_NODE_DEEP : 0u, &n_sel, false, 0, nodes_known, n_nodes_known,
+                     &n_nodes_next);
     if (rc)
       return rc;
     h->stats.n_levels += 1;
@@ -971,35 +1012,35 @@ store_update(swgpu_tiler* h, int levels, const Chunk& c)
   CK(h->st_found.ensure((size_t)nv * 4));
   CK(h->st_cumf.ensure(((size_t)nv + 1) * 8));
   CK(h->st_scan.ensure(scan_scratch_words(nn_max) * 8));
-  CK(h->st_nidx.ensure(nn_max * 8));
+  CK(ensure_amortised(L.spare_index, nn_max * 8));
   CK(h->st_ncnt.ensure(nn_max * 4));
-  CK(h->st_nflags.ensure(nn_max * 4));
+  CK(ensure_amortised(L.spare_flags, nn_max * 4));
   CK(h->st_nsrc.ensure(nn_max * 8));
-  CK(h->st_nfirst.ensure((nn_max + 1) * 8));
+  CK(ensure_amortised(L.spare_first, (nn_max + 1) * 8));
   launch_store_match(vidx, nv, L.index.as<u64>(), no, h->st_lo.as<u32>(), h->st_found.as<u32>(), s);
   launch_exclusive_scan_u32(h->st_found.as<u32>(), nv, h->st_cumf.as<u64>(), h->st_scan.as<u64>(), s);
   CK(cudaMemsetAsync(h->st_ncnt.p, 0, nn_max * 4, s)); // rows past the real table count nothing
   launch_store_rows(vidx, vfirst, nv, c.out_offset + c.count, c.flags, h->st_lo.as<u32>(), h->st_cumf.as<u64>(),
-                    L.index.as<u64>(), L.first.as<u64>(), L.flags.as<u32>(), no, h->st_nidx.as<u64>(),
-                    h->st_ncnt.as<u32>(), h->st_nflags.as<u32>(), h->st_nsrc.as<u64>(), s);
-  launch_exclusive_scan_u32(h->st_ncnt.as<u32>(), nn_max, h->st_nfirst.as<u64>(), h->st_scan.as<u64>(), s);
+                    L.index.as<u64>(), L.first.as<u64>(), L.flags.as<u32>(), no, L.spare_index.as<u64>(),
+                    h->st_ncnt.as<u32>(), L.spare_flags.as<u32>(), h->st_nsrc.as<u64>(), s);
+  launch_exclusive_scan_u32(h->st_ncnt.as<u32>(), nn_max, L.spare_first.as<u64>(), h->st_scan.as<u64>(), s);
   h->stats.kernel_launches += 8;
   CK(cudaGetLastError());
-  int rc = read_store_vals(h, h->st_cumf.as<u64>() + nv, h->st_nfirst.as<u64>() + nn_max);
+  int rc = read_store_vals(h, h->st_cumf.as<u64>() + nv, L.spare_first.as<u64>() + nn_max);
   if (rc)
     return rc;
   const u64 n_found = h->h_scalars->store_vals[0], total = h->h_scalars->store_vals[1];
   const u64 nn = nn_max - n_found;
-  CK(h->st_nids.ensure(std::max<u64>(total, 1) * 4));
-  launch_store_copy(total, h->st_nfirst.as<u64>(), (u32)nn, h->st_nsrc.as<u64>(), L.ids.as<u32>(),
-                    h->out_idx.as<u32>(), h->st_nids.as<u32>(), s);
+  CK(ensure_amortised(L.spare_ids, std::max<u64>(total, 1) * 4));
+  launch_store_copy(total, L.spare_first.as<u64>(), (u32)nn, h->st_nsrc.as<u64>(), L.ids.as<u32>(),
+                    h->out_idx.as<u32>(), L.spare_ids.as<u32>(), s);
   h->stats.kernel_launches += 1;
   h->stats.bytes_traffic += 8 * total;
   CK(cudaGetLastError());
-  std::swap(L.index, h->st_nidx);
-  std::swap(L.first, h->st_nfirst);
-  std::swap(L.flags, h->st_nflags);
-  std::swap(L.ids, h->st_nids);
+  std::swap(L.index, L.spare_index);
+  std::swap(L.first, L.spare_first);
+  std::swap(L.flags, L.spare_flags);
+  std::swap(L.ids, L.spare_ids);
   L.n_nodes = nn;
   L.n_ids = total;
   return SW_OK;
@@ -1008,7 +1049,8 @@ store_update(swgpu_tiler* h, int levels, const Chunk& c)
 // One sweep level of a batch against the store.  cur: slot of list_key / list_idx that holds the input list
 // (Morton ordered, node boundaries in h->node_start); on return the slot of the remainder list.
 int
-store_level(swgpu_tiler* h, int* cur, u64* count_io, int levels, bool terminal, u32 n_nodes, u32* n_nodes_next)
+store_level(swgpu_tiler* h, int* cur, u64* count_io, int levels, bool terminal, u32 level_flags, u32 n_nodes,
+            u32* n_nodes_next)
 {
   cudaStream_t s = h->stream;
   LevelStore& L = h->store[levels];
@@ -1079,7 +1121,7 @@ store_level(swgpu_tiler* h, int* cur, u64* count_io, int levels, bool terminal, 
 
   u64 n_sel = 0;
   int rc = sweep_level(h, in_key, in_idx, count, levels, /*allow_take_all=*/true, terminal, h->list_key[sr].as<u64>(),
-                       h->list_idx[sr].as<u32>(), 0u, &n_sel, false, 0, true, n_nodes, n_nodes_next);
+                       h->list_idx[sr].as<u32>(), level_flags, &n_sel, false, 0, true, n_nodes, n_nodes_next);
   h->gcount_override = nullptr;
   if (rc)
     return rc;
@@ -1194,13 +1236,14 @@ run_batch_store(swgpu_tiler* h)
   }
   for (int levels = first_levels; count > 0; ++levels) {
     const LevelKind kind = level_kind(h, levels - 1);
-    if (kind == KIND_REROOT || levels > 21)
+    const bool deep = kind == KIND_REROOT && h->deep_policy == 1 && levels <= 21;
+    if ((kind == KIND_REROOT && !deep) || levels > 21)
       return fail(h, SW_ERR_DEEP_REROOT, "deep re-root path (TilingAlgorithms.cpp:444-483) is not supported");
-    const bool terminal = (kind == KIND_TERMINAL);
+    const bool terminal = (kind == KIND_TERMINAL) || deep;
     if (!terminal && levels >= 21)
       return fail(h, SW_ERR_DEEP_REROOT, "child level exceeds MortonIndex64 capacity");
     u32 n_nodes_next = 0;
-    rc = store_level(h, &cur, &count, levels, terminal, n_nodes, &n_nodes_next);
+    rc = store_level(h, &cur, &count, levels, terminal, deep ? SW_NODE_DEEP : 0u, n_nodes, &n_nodes_next);
     if (rc)
       return rc;
     h->stats.n_levels += 1;
@@ -1337,6 +1380,10 @@ release_store(swgpu_tiler* h)
     L.first.release();
     L.flags.release();
     L.ids.release();
+    L.spare_index.release();
+    L.spare_first.release();
+    L.spare_flags.release();
+    L.spare_ids.release();
     L.n_nodes = 0;
     L.n_ids = 0;
   }
@@ -1443,6 +1490,15 @@ swgpu_set_stream(swgpu_handle h, void* cuda_stream)
   if (!h)
     return SW_ERR_INVALID_ARGUMENT;
   h->stream = static_cast<cudaStream_t>(cuda_stream);
+  return SW_OK;
+}
+
+int
+swgpu_set_deep_node_policy(swgpu_handle h, int policy)
+{
+  if (!h || policy < 0 || policy > 1)
+    return SW_ERR_INVALID_ARGUMENT;
+  h->deep_policy = policy;
   return SW_OK;
 }
 

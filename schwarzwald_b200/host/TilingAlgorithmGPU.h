@@ -117,6 +117,9 @@ struct TilingAlgorithmGPU : TilingAlgorithmBase
                                                 bmax,
                                                 num_indexing_threads,
                                                 _cuda_device);
+        // nodes where the reference would re-root (TilingAlgorithms.cpp:444-483) are stored whole instead of failing
+        // the run; hand_off() reports them
+        _tiler->set_deep_node_policy(true);
         // a full batch may be followed by more (Tiler::run fills internal_cache_size points per batch)
         _multi_batch = n >= _meta_parameters.internal_cache_size;
         if (_multi_batch)
@@ -197,7 +200,12 @@ private:
     const double rmin[3] = { _root_bounds.min.x, _root_bounds.min.y, _root_bounds.min.z };
     const double rmax[3] = { _root_bounds.max.x, _root_bounds.max.y, _root_bounds.max.z };
     std::vector<PointBuffer::PointReference> refs;
+    size_t deep_nodes = 0, deep_points = 0;
     for (const sw_node& node : result.nodes) {
+      if (node.flags & SW_NODE_DEEP) {
+        ++deep_nodes;
+        deep_points += node.count;
+      }
       refs.clear();
       refs.reserve(node.count);
       for (uint64_t k = 0; k < node.count; ++k)
@@ -211,6 +219,11 @@ private:
       if (count_progress && _progress_reporter && !(node.flags & SW_NODE_RECONSTRUCTED))
         _progress_reporter->increment_progress<size_t>(progress::INDEXING, node.count);
     }
+    if (deep_nodes)
+      std::fprintf(stderr,
+                   "note: %zu nodes at the depth where the reference re-indexes with a new root hold their %zu "
+                   "remaining points unsampled (duplicate or extremely dense points)\n",
+                   deep_nodes, deep_points);
   }
 
   int _cuda_device;

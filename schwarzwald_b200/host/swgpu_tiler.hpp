@@ -132,6 +132,9 @@ public:
   // stored (tile_node with cached points, core/tiling/TilingAlgorithms.cpp:351-492); result() then returns the
   // final content of every node with GLOBAL point ids (points of earlier batches + index in the batch).
   void set_multi_batch(bool on) { check(swgpu_set_multi_batch(_handle, on ? 1 : 0)); }
+  // Nodes where the reference would re-root (TilingAlgorithms.cpp:444-483): fail (default) or store them whole,
+  // flagged SW_NODE_TERMINAL | SW_NODE_DEEP
+  void set_deep_node_policy(bool store_whole) { check(swgpu_set_deep_node_policy(_handle, store_whole ? 1 : 0)); }
 
   struct Result
   {

@@ -87,6 +87,7 @@ SYMBOLS = [
     ("swgpu_get_payload_las_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swgpu_finalize", C.c_int, [C.c_void_p]),
     ("swgpu_set_multi_batch", C.c_int, [C.c_void_p, C.c_int]),
+    ("swgpu_set_deep_node_policy", C.c_int, [C.c_void_p, C.c_int]),
     ("swgpu_result_size", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("swgpu_get_nodes", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swgpu_get_nodes_device_ids", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -27,6 +27,7 @@ _TILING = {ACCURATE: 0, FAST: 1}
 
 NODE_TERMINAL = 2
 NODE_RECONSTRUCTED = 4
+NODE_DEEP = 8
 
 NODE_DTYPE = np.dtype(
     [("index", "<u8"), ("levels", "<u4"), ("flags", "<u4"), ("first", "<u8"), ("count", "<u8")])
@@ -182,6 +183,11 @@ class GpuTiler:
 
     def enable_timing(self, on=True):
         self._check(self._lib.swgpu_enable_timing(self._h, 1 if on else 0))
+
+    def set_deep_node_policy(self, store_whole=True):
+        """Nodes where the reference would re-root (TilingAlgorithms.cpp:444-483): fail with error 6 (default) or
+        store all remaining points unsampled, flagged NODE_TERMINAL | NODE_DEEP."""
+        self._check(self._lib.swgpu_set_deep_node_policy(self._h, 1 if store_whole else 0))
 
     # -- the two calls of TilingAlgorithmBase --------------------------------------------------------
     def build_execution_graph(self, points):

@@ -191,3 +191,42 @@ def test_multi_batch_writer_payloads(port_oracle, sampling, tiling):
     assert np.array_equal(las, w_las)
     for f in ("offset", "scale", "max"):
         assert np.array_equal(headers[f], w_headers[f])
+
+
+def test_multi_batch_duplicates_reach_the_re_root_depth():
+    """The same points arriving batch after batch can never be separated by a sampling grid: a revisited leaf is
+    always sampled (TilingAlgorithms.cpp:272-275), keeps one copy and hands the others to a new child, which takes
+    them whole - one level deeper per batch, until the depth where the reference re-roots (:444-483).  Default
+    policy: SW_ERR_DEEP_REROOT, like the oracle.  swgpu_set_deep_node_policy(1): those nodes store their points
+    whole, flagged TERMINAL | DEEP, every point exactly once."""
+    _torch_cuda()
+    import schwarzwald_b200 as sw
+    from schwarzwald_b200 import tiler as swt
+    mgb = _golden_mod()
+    xyz, bmin, bmax, spacing = mgb.case_input()
+    xyz = xyz[5:30_005].copy()
+    copies = np.concatenate([xyz[:200]] * 3)
+    sizes = [30_000] + [600] * 16
+    cloud = np.concatenate([xyz] + [copies] * 16)
+    for sampling in ("RANDOM_GRID", "JITTERED"):
+        with sw.GpuTiler(sampling, "ACCURATE", bmin, bmax, spacing, max_points_per_node=800, concurrency=2) as t:
+            t.set_multi_batch(True)
+            with pytest.raises(sw.SwgpuError) as e:
+                lo = 0
+                for n in sizes:
+                    t.build_execution_graph(cloud[lo:lo + n].copy())
+                    lo += n
+            assert e.value.code == 6
+        with sw.GpuTiler(sampling, "ACCURATE", bmin, bmax, spacing, max_points_per_node=800, concurrency=2) as t:
+            t.set_multi_batch(True)
+            t.set_deep_node_policy(True)
+            lo = 0
+            for n in sizes:
+                t.build_execution_graph(cloud[lo:lo + n].copy())
+                lo += n
+            t.finalize()
+            res = t.result()
+        assert (np.bincount(res.ids.astype(np.int64), minlength=len(cloud)) == 1).all()
+        deep = res.nodes[(res.nodes["flags"] & swt.NODE_DEEP) != 0]
+        assert len(deep) > 0 and (deep["flags"] & swt.NODE_TERMINAL).all() and (deep["levels"] == 15).all()
+        assert int(deep["count"].sum()) < 49 * 200
