@@ -1223,7 +1223,7 @@ grow(SwGrowBuf& b, size_t bytes)
 void
 free_min_distance_scratch(SwMinDistScratch& sc)
 {
-  SwGrowBuf* all[] = { &sc.cell_start, &sc.cell_tile_rank0, &sc.state, &sc.lpos, &sc.desc,  &sc.acc_xyz,    &sc.hkeys,
+  SwGrowBuf* all[] = { &sc.hmask, &sc.cell_start, &sc.cell_tile_rank0, &sc.state, &sc.lpos, &sc.desc,  &sc.acc_xyz,    &sc.hkeys,
                        &sc.hvals,      &sc.nbr,             &sc.deps,  &sc.queue, &sc.cell_active, &sc.counters };
   for (SwGrowBuf* b : all) {
     if (b->p)
@@ -1306,12 +1306,17 @@ md_hash(u64 code, u32 mask)
   return (u32)code & mask;
 }
 
-// One thread per cell: is there anything to analyse in the cell (cells of take-all nodes are not), and
-// where is the cell in the hash table of occupied cells.
+// The occupied cells are found through a hash table over 4 x 4 x 4 BLOCKS of cells (block = cell code >> 6): one
+// entry holds the block's first cell (cells are in Morton order, so a block's cells are consecutive) and a 64-bit
+// occupancy mask; cell = first + popc(mask below the cell's bit).  A cell's 26 neighbours lie in at most 8 blocks,
+// neighbours that do not exist are answered by the mask instead of a probe sequence, and the table has a fraction
+// of the entries of a per-cell table (round 2: 26 random probes per cell were 45 ms of a 237 ms step).
+// One thread per cell: is there anything to analyse in the cell (cells of take-all nodes are not); the first cell
+// of every block inserts the block.
 __global__ void __launch_bounds__(256)
 md_hash_insert_kernel(const u64* __restrict__ in_key, const u32* __restrict__ cell_start, u32 n_cells, int cell_shift,
                       const unsigned char* __restrict__ state, unsigned char* __restrict__ cell_active,
-                      u64* __restrict__ hkeys, u32* __restrict__ hvals, u32 mask)
+                      u64* __restrict__ hkeys, u32* __restrict__ hvals, u64* __restrict__ hmask, u32 mask)
 {
   const u32 c = blockIdx.x * 256 + threadIdx.x;
   if (c >= n_cells)
@@ -1322,11 +1327,22 @@ md_hash_insert_kernel(const u64* __restrict__ in_key, const u32* __restrict__ ce
     active = state[i] == MD_UNDECIDED;
   cell_active[c] = active ? 1 : 0;
   const u64 code = (in_key[b] & SW_KEY_MASK) >> cell_shift;
-  u32 slot = md_hash(code, mask);
+  const u64 block = code >> 6;
+  if (c > 0 && (((in_key[cell_start[c - 1]] & SW_KEY_MASK) >> cell_shift) >> 6) == block)
+    return; // not the first cell of its block
+  u64 occupied = 1ull << (code & 63ull);
+  for (u32 k = c + 1; k < n_cells; ++k) {
+    const u64 other = (in_key[cell_start[k]] & SW_KEY_MASK) >> cell_shift;
+    if ((other >> 6) != block)
+      break;
+    occupied |= 1ull << (other & 63ull);
+  }
+  u32 slot = md_hash(block, mask);
   while (true) {
-    const u64 prev = atomicCAS(&hkeys[slot], 0ull, code + 1);
-    if (prev == 0ull || prev == code + 1) {
+    const u64 prev = atomicCAS(&hkeys[slot], 0ull, block + 1);
+    if (prev == 0ull) {
       hvals[slot] = c;
+      hmask[slot] = occupied;
       return;
     }
     slot = (slot + 1) & mask;
@@ -1373,8 +1389,8 @@ md_queue_counters(u32* counters, u32 q)
 __device__ __forceinline__ u32
 md_neighbors_of(u32 c, const u64* __restrict__ in_key, const u32* __restrict__ cell_start, int cell_shift,
                 int cell_levels, int node_levels, const unsigned char* __restrict__ cell_active,
-                const u64* __restrict__ hkeys, const u32* __restrict__ hvals, u32 mask, u32* __restrict__ nbr,
-                u32* __restrict__ deps)
+                const u64* __restrict__ hkeys, const u32* __restrict__ hvals, const u64* __restrict__ hmask, u32 mask,
+                u32* __restrict__ nbr, u32* __restrict__ deps)
 {
   u32* out = nbr + (size_t)c * MD_NBR_SLOTS;
   u32 later[26];
@@ -1387,6 +1403,11 @@ md_neighbors_of(u32 c, const u64* __restrict__ in_key, const u32* __restrict__ c
     const long long y = (long long)contract_bits_by_3(code >> 1);
     const long long z = (long long)contract_bits_by_3(code);
     const u64 node_prefix = code >> (3 * below);
+    // the (at most 8) blocks the neighbourhood touches, looked up once each: slot = which side of the own block
+    // per axis (0 = own block's coordinate, 1 = the adjacent one)
+    u64 blk_mask[8];
+    u32 blk_first[8];
+    u32 blk_known = 0;
     for (int dx = -1; dx <= 1; ++dx)
       for (int dy = -1; dy <= 1; ++dy)
         for (int dz = -1; dz <= 1; ++dz) {
@@ -1398,22 +1419,38 @@ md_neighbors_of(u32 c, const u64* __restrict__ in_key, const u32* __restrict__ c
           const u64 nc = expand_bits_by_3((u64)Z) | (expand_bits_by_3((u64)Y) << 1) | (expand_bits_by_3((u64)X) << 2);
           if ((nc >> (3 * below)) != node_prefix)
             continue;
-          u32 slot = md_hash(nc, mask);
-          while (true) {
-            const u64 k = hkeys[slot];
-            if (k == 0ull)
-              break;
-            if (k == nc + 1) {
-              const u32 other = hvals[slot];
-              if (cell_active[other]) {
-                if (nc < code)
-                  out[1 + n_early++] = other;
-                else
-                  later[n_late++] = other;
+          const u32 bi = (((X >> 2) != (x >> 2)) ? 4u : 0u) | (((Y >> 2) != (y >> 2)) ? 2u : 0u) |
+                         (((Z >> 2) != (z >> 2)) ? 1u : 0u);
+          if (!((blk_known >> bi) & 1u)) {
+            const u64 block = nc >> 6;
+            u64 m = 0ull;
+            u32 f = 0u;
+            u32 slot = md_hash(block, mask);
+            while (true) {
+              const u64 k = hkeys[slot];
+              if (k == 0ull)
+                break;
+              if (k == block + 1) {
+                f = hvals[slot];
+                m = hmask[slot];
+                break;
               }
-              break;
+              slot = (slot + 1) & mask;
             }
-            slot = (slot + 1) & mask;
+            blk_mask[bi] = m;
+            blk_first[bi] = f;
+            blk_known |= 1u << bi;
+          }
+          const u32 bit = (u32)(nc & 63ull);
+          const u64 m = blk_mask[bi];
+          if (!((m >> bit) & 1ull))
+            continue; // no such cell
+          const u32 other = blk_first[bi] + (u32)__popcll(m & ((1ull << bit) - 1ull));
+          if (cell_active[other]) {
+            if (nc < code)
+              out[1 + n_early++] = other;
+            else
+              later[n_late++] = other;
           }
         }
   }
@@ -1427,15 +1464,16 @@ md_neighbors_of(u32 c, const u64* __restrict__ in_key, const u32* __restrict__ c
 __global__ void __launch_bounds__(256)
 md_neighbors_kernel(const u64* __restrict__ in_key, const u32* __restrict__ cell_start, u32 n_cells, int cell_shift,
                     int cell_levels, int node_levels, const unsigned char* __restrict__ cell_active,
-                    const u64* __restrict__ hkeys, const u32* __restrict__ hvals, u32 mask, u32* __restrict__ nbr,
-                    u32* __restrict__ deps, u32* __restrict__ queue, u32* __restrict__ counters, MdQueues mq)
+                    const u64* __restrict__ hkeys, const u32* __restrict__ hvals, const u64* __restrict__ hmask, u32 mask,
+                    u32* __restrict__ nbr, u32* __restrict__ deps, u32* __restrict__ queue, u32* __restrict__ counters,
+                    MdQueues mq)
 {
   const u32 c = blockIdx.x * 256 + threadIdx.x;
   const bool act = c < n_cells && cell_active[c];
   u32 n_early_out = 1;
   if (act)
     n_early_out = md_neighbors_of(c, in_key, cell_start, cell_shift, cell_levels, node_levels, cell_active, hkeys, hvals,
-                                  mask, nbr, deps);
+                                  hmask, mask, nbr, deps);
   // the 32 cells of a warp belong to one queue (MD_QUEUE_CHUNK = 64 consecutive cells): one atomic per warp for
   // the analysed-cell count and one for the cells that are ready at once
   const u32 lane = threadIdx.x & 31;
@@ -1929,11 +1967,13 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
   if (n_active == 0) // every node of the level is stored whole
     return cudaGetLastError();
 
+  // table over 4 x 4 x 4 blocks of cells: a block holds at least one cell, typically 10 - 20
   u32 cap = 64;
-  while (cap < 2 * n_cells)
+  while ((u64)cap < (u64)n_cells + n_cells / 2 + 64) // at most 2/3 full even if every block held one cell only
     cap <<= 1;
   MD_TRY(grow(sc.hkeys, (size_t)cap * 8));
   MD_TRY(grow(sc.hvals, (size_t)cap * 4));
+  MD_TRY(grow(sc.hmask, (size_t)cap * 8));
   MD_TRY(grow(sc.nbr, (size_t)n_cells * MD_NBR_SLOTS * 4));
   MD_TRY(grow(sc.desc, (size_t)n_cells * 8));
   MD_TRY(grow(sc.deps, (size_t)n_cells * 4));
@@ -1983,10 +2023,11 @@ run_min_distance(const SwMinDistArgs& a, SwMinDistScratch& sc, cudaStream_t stre
   const u32 cgrid = (n_cells + 255) / 256;
   md_hash_insert_kernel<<<cgrid, 256, 0, stream>>>(a.in_key, cell_start, n_cells, cell_shift, state, cell_active,
                                                    static_cast<u64*>(sc.hkeys.p), static_cast<u32*>(sc.hvals.p),
-                                                   cap - 1);
+                                                   static_cast<u64*>(sc.hmask.p), cap - 1);
   md_neighbors_kernel<<<cgrid, 256, 0, stream>>>(a.in_key, cell_start, n_cells, cell_shift, cell_levels, a.node_levels,
                                                  cell_active, static_cast<const u64*>(sc.hkeys.p),
-                                                 static_cast<const u32*>(sc.hvals.p), cap - 1, nbr, deps, queue,
+                                                 static_cast<const u32*>(sc.hvals.p),
+                                                 static_cast<const u64*>(sc.hmask.p), cap - 1, nbr, deps, queue,
                                                  counters, mq);
 
   // persistent dataflow kernel: every resident group pops ready cells until all analysed cells are done

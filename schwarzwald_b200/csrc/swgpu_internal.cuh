@@ -174,7 +174,8 @@ struct SwMinDistArgs
 
 struct SwMinDistScratch
 {
-  SwGrowBuf cell_start, cell_tile_rank0, state, lpos, desc, acc_xyz, hkeys, hvals, nbr, deps, queue, cell_active, counters;
+  SwGrowBuf cell_start, cell_tile_rank0, state, lpos, desc, acc_xyz, hkeys, hvals, hmask, nbr, deps, queue, cell_active,
+    counters;
   u64* status; // look-back descriptors (>= sweep_tiles u64)
   u32* ticket;
   u32* h_pinned; // pinned host scratch, >= 8 u32
