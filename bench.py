@@ -320,6 +320,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default=None, choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--points", type=int, default=None, help="total points (default: the config's size)")
+    ap.add_argument("--sort-mode", type=int, default=-1,
+                    help="swgpu_set_sort_mode: -1 automatic (default), 0 eight LSD passes, 2 / 3 explicit top-digit sort")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle check of the result")
@@ -380,6 +382,7 @@ def main():
                             device=local_rank)
     tiler.set_stream(stream.cuda_stream)
     tiler.enable_timing(True)
+    (tiler.tiler if world > 1 else tiler).set_sort_mode(args.sort_mode)
 
     ids_dev = None
     nodes_host = None
@@ -406,7 +409,7 @@ def main():
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sort_ms, launches = 0.0, 0
+    sort_ms, finish_ms, launches = 0.0, 0.0, 0
     stats = None
     barrier()
     t_begin = time.perf_counter()
@@ -415,6 +418,7 @@ def main():
         step()
         stats = tiler.stats()
         sort_ms += stats["ms_sort"]
+        finish_ms += stats["ms_sort_finish"]
         launches += stats["kernel_launches"]
     ev1.record(stream)
     barrier()
@@ -679,8 +683,15 @@ def main():
     # dominant kernel: one onesweep radix pass: 12 B read + 12 B written per point of THIS GPU's shard.  The pass
     # count comes back through the library's byte accounting (8 + passes * 24 B per point).
     n_sorted = max(1, int(stats["n_points"]))
-    n_passes = int(round((stats["bytes_sort"] / n_sorted - 8) / 24.0))
-    pass_ms = sort_ms / args.steps / max(1, n_passes)
+    n_passes = max(1, int(stats["sort_passes"]))
+    pass_ms = (sort_ms - finish_ms) / args.steps / n_passes  # the segment finish kernel is not a pass
+    sort_info = {"onesweep_passes": n_passes, "first_bit": int(stats["sort_first_bit"]),
+                 "fallback": int(stats["sort_fallback"]), "ms_sort": sort_ms / args.steps,
+                 "ms_segment_finish": finish_ms / args.steps,
+                 "finish_scan_steps_per_point": stats["sort_scan_steps"] / n_sorted,
+                 "finish_moved_fraction": stats["sort_moved"] / n_sorted,
+                 "note": "passes over key bits >= first_bit, then runs of equal top bits are ordered in place by "
+                         "segment_finish_kernel (same order as eight LSD passes; swgpu_set_sort_mode)"}
     achieved = (24.0 * n_sorted) / (pass_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "onesweep_pass_kernel (%d launches per step)" % n_passes,
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
@@ -713,6 +724,7 @@ def main():
             "step": "index + sort + sampling sweep + FAST reconstruct + hand-off (node table to host, node-major "
                     "original ids composed on the device)"},
         "roofline": roofline,
+        "sort": sort_info,
         "stage_ms": {k: stats[k] for k in ("ms_index", "ms_sort", "ms_gather", "ms_sample", "ms_total")},
         "gpu_launches": int(launches),
         "shuffle_phase_ms": phase_ms,

@@ -85,6 +85,16 @@ int swgpu_set_multi_batch(swgpu_handle h, int enable);
  *                       a stated deviation otherwise. */
 int swgpu_set_deep_node_policy(swgpu_handle h, int policy);
 
+/* K2, the sort that replaces std::sort over IndexedPoint64 (TilingAlgorithms.cpp:600-604,1289-1292).  The result is
+ * the same in every mode (key order, ties by original point index); the modes differ in how often the pairs move:
+ *   -1 (default)  automatic: onesweep passes over the top 40 or 48 key bits only, then the runs of equal top bits
+ *                 are ordered in place by one kernel; the number of top bits follows the point density (estimated
+ *                 from the point count for the first batch of a handle, from the previous batch's run lengths
+ *                 afterwards)
+ *    0            eight LSD passes over all 63 bits
+ *    1, 2, 3      passes over the key bits from 8 * mode up, then the segment finish */
+int swgpu_set_sort_mode(swgpu_handle h, int mode);
+
 /* The hand-off that replaces the per-node persist_points() calls (io/PointsPersistence.h:23-31):
  * a node table plus one node-major array of ORIGINAL point indices, Morton-ordered inside each
  * node.  The adapter turns row i into persist_points(refs[first..first+count), bounds, name). */
@@ -303,6 +313,13 @@ typedef struct swgpu_stats {
   uint32_t kernel_launches;
   uint32_t min_distance_rounds;
   uint64_t bytes_traffic;
+  /* K2 of the last batch (swgpu_set_sort_mode) */
+  uint32_t sort_passes;     /* onesweep passes executed (8 = plain LSD; 5 or 6 + the segment finish otherwise) */
+  uint32_t sort_first_bit;  /* key bits below this one were ordered by the segment finish kernel (0 = none) */
+  uint32_t sort_fallback;   /* 1 = a long unsorted run of equal top bits made the eight LSD passes necessary */
+  float ms_sort_finish;     /* part of ms_sort spent in the segment finish kernel */
+  uint64_t sort_scan_steps; /* neighbour comparisons of the segment finish kernel */
+  uint64_t sort_moved;      /* elements the segment finish kernel moved */
 } swgpu_stats;
 int swgpu_enable_timing(swgpu_handle h, int enable);
 int swgpu_get_stats(swgpu_handle h, swgpu_stats* out);

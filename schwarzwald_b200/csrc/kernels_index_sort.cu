@@ -667,12 +667,12 @@ sort_status_words(u64 n)
   return (tiles ? tiles : 1) * RS_RADIX;
 }
 
-template<int PASS>
+template<int PASS, bool FIRST>
 static void
 launch_onesweep_pass(const u64* kin, const u32* vin, u64* kout, u32* vout, u32 n, const u32* digit_base, u32* status,
                      u32* ticket, u32 tiles, cudaStream_t stream)
 {
-  auto kernel = onesweep_pass_kernel<PASS, PASS == 0>;
+  auto kernel = onesweep_pass_kernel<PASS, FIRST>;
   // function attributes are per device: one flag per device ordinal (a process may drive several GPUs)
   static bool attr_set[64] = {};
   int dev = 0;
@@ -704,38 +704,57 @@ sort_input_buffer()
   return RS_PASSES & 1; // an odd number of ping-pongs ends in buffer 0 when it starts in buffer 1
 }
 
-void
-launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hist, u32* status, u32* ticket,
-                  cudaStream_t stream)
+int
+sort_input_buffer_top(int first_pass)
 {
-  if (n == 0)
-    return;
+  return (RS_PASSES - first_pass) & 1;
+}
+
+// passes first_pass .. RS_PASSES - 1, ping-ponging from (kin, vin); `implicit_ids`: the first of them generates
+// the ids 0..n-1 instead of reading vin
+static void
+run_passes(u64* kin, u32* vin, u64* kout, u32* vout, u32 n, int first_pass, bool implicit_ids, const u32* hist,
+           u32* status, u32* ticket, cudaStream_t stream)
+{
   const u32 tiles = (u32)((n + RS_TILE - 1) / RS_TILE);
-  digit_base_kernel<<<1, RS_PASSES * 32, 0, stream>>>(hist);
   cudaMemsetAsync(ticket, 0, 8 * sizeof(u32), stream);
-  const bool from1 = sort_input_buffer() == 1;
-  u64* kin = from1 ? keys1 : keys0;
-  u64* kout = from1 ? keys0 : keys1;
-  u32* vin = from1 ? vals1 : vals0;
-  u32* vout = from1 ? vals0 : vals1;
-  for (int pass = 0; pass < RS_PASSES; ++pass) {
+  for (int pass = first_pass; pass < RS_PASSES; ++pass) {
     cudaMemsetAsync(status, 0, (size_t)tiles * RS_RADIX * sizeof(u32), stream);
     const u32* base = hist + pass * RS_RADIX;
     u32* tk = ticket + pass;
+    const bool first = implicit_ids && pass == first_pass;
+#define RS_LAUNCH(P)                                                                                                   \
+  case P:                                                                                                              \
+    if (first)                                                                                                         \
+      launch_onesweep_pass<P, true>(kin, vin, kout, vout, n, base, status, tk, tiles, stream);                         \
+    else                                                                                                               \
+      launch_onesweep_pass<P, false>(kin, vin, kout, vout, n, base, status, tk, tiles, stream);                        \
+    break;
     switch (pass) {
-      case 0: launch_onesweep_pass<0>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
-      case 1: launch_onesweep_pass<1>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
-      case 2: launch_onesweep_pass<2>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
-      case 3: launch_onesweep_pass<3>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
-      case 4: launch_onesweep_pass<4>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
-      case 5: launch_onesweep_pass<5>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+      RS_LAUNCH(0)
+      RS_LAUNCH(1)
+      RS_LAUNCH(2)
+      RS_LAUNCH(3)
+      RS_LAUNCH(4)
+      RS_LAUNCH(5)
 #if RS_PASSES > 7
-      case 6: launch_onesweep_pass<6>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
-      default: launch_onesweep_pass<7>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+      RS_LAUNCH(6)
+      default:
+        if (first)
+          launch_onesweep_pass<7, true>(kin, vin, kout, vout, n, base, status, tk, tiles, stream);
+        else
+          launch_onesweep_pass<7, false>(kin, vin, kout, vout, n, base, status, tk, tiles, stream);
+        break;
 #else
-      default: launch_onesweep_pass<6>(kin, vin, kout, vout, (u32)n, base, status, tk, tiles, stream); break;
+      default:
+        if (first)
+          launch_onesweep_pass<6, true>(kin, vin, kout, vout, n, base, status, tk, tiles, stream);
+        else
+          launch_onesweep_pass<6, false>(kin, vin, kout, vout, n, base, status, tk, tiles, stream);
+        break;
 #endif
     }
+#undef RS_LAUNCH
     u64* tk2 = kin;
     kin = kout;
     kout = tk2;
@@ -743,6 +762,223 @@ launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hi
     vin = vout;
     vout = tv;
   }
+}
+
+void
+launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hist, u32* status, u32* ticket,
+                  cudaStream_t stream)
+{
+  if (n == 0)
+    return;
+  digit_base_kernel<<<1, RS_PASSES * 32, 0, stream>>>(hist);
+  const bool from1 = sort_input_buffer() == 1;
+  run_passes(from1 ? keys1 : keys0, from1 ? vals1 : vals0, from1 ? keys0 : keys1, from1 ? vals0 : vals1, (u32)n, 0,
+             true, hist, status, ticket, stream);
+}
+
+// ---- top-digit sort + segment finish ----------------------------------------------------------------------
+// An LSD sort has to move every pair once per digit, whatever the data.  A MortonIndex64 of a real cloud is
+// nearly unique long before its last bit: 100 M terrain points fall into 62 M cells of octree level 13, the
+// longest run of points sharing the top 39 key bits is 12.  So only the TOP digits are sorted by onesweep passes
+// (passes first_pass .. 7: stable, ids ascending inside every run of equal top bits), and one kernel finishes
+// the runs ("segments") in place: every element counts the elements of its segment that have to precede it
+// (smaller low bits, or equal low bits and an earlier position = smaller id) and moves there.  That is one read
+// of the keys and the ids and a write of the elements that move, instead of first_pass read+write passes.
+//
+// A segment is finished by the tile in which it STARTS; the tile keeps a window of FIN_LIMIT further keys in
+// shared memory for segments that reach into the next tile, so segments of up to FIN_LIMIT elements are
+// handled and tiles never write to the same elements (other tiles only compare the top bits of foreign
+// elements, which a permutation inside a segment does not change).  A longer segment is left as it is; if it is
+// not already in order (identical points are) an element that sees an inversion raises stats[0] and the caller
+// runs the eight LSD passes over the current arrangement (still stable: equal keys are in id order).
+#define FIN_THREADS 256
+#define FIN_TILE 4096
+#define FIN_LIMIT 256
+#define FIN_WINDOW (FIN_TILE + FIN_LIMIT)
+#define FIN_ITEMS (FIN_WINDOW / FIN_THREADS)
+#define FIN_HEAD 0x80000000u    /* the element starts a run of equal top bits */
+#define FIN_FOREIGN 0x40000000u /* left sentinel: the run continues from the previous tile */
+#define FIN_KEEP 0xffffu
+#define FIN_CHUNK 6 /* loads in flight per thread while the tags are built */
+
+// Shared memory holds one 32-bit tag per window element (the low key bits, at most 24, and the head flag: a step
+// of a scan is one LDS and three integer instructions) and, per window position, which element moves there.
+// Elements are pulled: the thread of position q reads the id of the element that belongs at q, and after a block
+// barrier rewrites the low bits of keys[q] (the top bits are those of its run) and ids[q].  So every thread writes
+// its own position only, and all reads of ids precede all writes.
+template<int LOW_BITS>
+__global__ void __launch_bounds__(FIN_THREADS, 6)
+segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32* __restrict__ stats)
+{
+  static_assert(LOW_BITS <= 24, "tags keep the low bits next to two flag bits");
+  __shared__ u32 s_tag[FIN_WINDOW + 2]; // [0] left sentinel, [1 + j] window element j, [1 + FIN_WINDOW] right sentinel
+  __shared__ unsigned short s_src[FIN_WINDOW];
+  constexpr u32 LOW_MASK = (1u << LOW_BITS) - 1;
+  const u32 tid = threadIdx.x;
+  const u32 base = blockIdx.x * FIN_TILE;
+  const u32 valid = (n - base) < FIN_WINDOW ? (n - base) : FIN_WINDOW; // window elements that exist
+
+  // ---- tags -------------------------------------------------------------------------------------------------
+  // (chunks of FIN_CHUNK elements per thread keep the loads in flight without spilling registers)
+  {
+    const bool interior = valid == FIN_WINDOW && base != 0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < FIN_ITEMS; k0 += FIN_CHUNK) {
+      u64 key[FIN_CHUNK], pk[FIN_CHUNK];
+#pragma unroll
+      for (int c = 0; c < FIN_CHUNK; ++c) {
+        const u32 j = tid + (k0 + c) * FIN_THREADS;
+        const u32 g = base + j;
+        if (interior) {
+          if (k0 + c < FIN_ITEMS) {
+            key[c] = keys[g];
+            pk[c] = keys[g - 1];
+          }
+        } else {
+          key[c] = (k0 + c < FIN_ITEMS && j < valid) ? keys[g] : ~0ull; // bit 63 set: top bits no MortonIndex64 has
+          pk[c] = (k0 + c < FIN_ITEMS && g > 0 && j <= valid) ? keys[g - 1] : ~0ull;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < FIN_CHUNK; ++c) {
+        if (k0 + c < FIN_ITEMS) {
+          const u32 j = tid + (k0 + c) * FIN_THREADS;
+          const bool head = ((key[c] ^ pk[c]) >> LOW_BITS) != 0 || (base + j) == 0;
+          s_tag[1 + j] = ((u32)key[c] & LOW_MASK) | (head ? FIN_HEAD : 0u);
+          s_src[j] = FIN_KEEP;
+          if (j == 0) // left sentinel: the low bits of the element before the tile (inversion test of element 0)
+            s_tag[0] = ((u32)pk[c] & LOW_MASK) | FIN_HEAD | FIN_FOREIGN;
+        }
+      }
+    }
+    if (tid == 0)
+      s_tag[1 + FIN_WINDOW] = FIN_HEAD;
+  }
+  __syncthreads();
+
+  // ---- where every element belongs --------------------------------------------------------------------------
+  u32 steps = 0, moved = 0;
+  bool unsorted_long = false;
+#pragma unroll 1
+  for (u32 j = tid; j < valid; j += FIN_THREADS) {
+    const u32 w = s_tag[1 + j];
+    if (w & s_tag[2 + j] & FIN_HEAD)
+      continue; // a run of one element
+    const u32 lo = w & LOW_MASK;
+    u32 budget = FIN_LIMIT - 1; // other elements a run may have
+    bool too_long = false;
+    // elements of the run in front of this one: those that do not have larger low bits stay in front
+    int l = (int)j;
+    u32 t = w, rank = 0;
+    while (!(t & FIN_HEAD)) {
+      if (budget == 0) {
+        too_long = true;
+        break;
+      }
+      --budget;
+      --l;
+      t = s_tag[1 + l];
+      rank += ((t & LOW_MASK) <= lo) ? 1u : 0u;
+    }
+    if (!too_long) {
+      // runs that start in an earlier tile are finished there (its window reaches this element), runs that start
+      // behind this tile by the next one
+      if ((t & FIN_FOREIGN) || l >= FIN_TILE) {
+        steps += FIN_LIMIT - 1 - budget;
+        continue;
+      }
+      // elements of the run behind this one: those with smaller low bits move in front
+      for (u32 r = j + 1;; ++r) {
+        const u32 t2 = s_tag[1 + r];
+        if (t2 & FIN_HEAD)
+          break;
+        if (budget == 0) {
+          too_long = true;
+          break;
+        }
+        --budget;
+        rank += ((t2 & LOW_MASK) < lo) ? 1u : 0u;
+      }
+    }
+    steps += FIN_LIMIT - 1 - budget;
+    if (too_long) { // the run stays as it is: fine if it is in order already (identical points are)
+      unsorted_long |= !(w & FIN_HEAD) && (s_tag[j] & LOW_MASK) > lo;
+      continue;
+    }
+    const u32 p = (u32)l + rank;
+    if (p != j) {
+      s_src[p] = (unsigned short)j;
+      ++moved;
+    }
+  }
+  __syncthreads();
+
+  // ---- pull ----------------------------------------------------------------------------------------------------
+  u32 id[FIN_ITEMS];
+#pragma unroll
+  for (int k = 0; k < FIN_ITEMS; ++k) {
+    const u32 src = s_src[tid + k * FIN_THREADS];
+    id[k] = src != FIN_KEEP ? ids[base + src] : 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < FIN_ITEMS; ++k) {
+    const u32 j = tid + k * FIN_THREADS;
+    const u32 src = s_src[j];
+    if (src != FIN_KEEP) {
+      const u32 g = base + j;
+      keys[g] = (keys[g] & ~(u64)LOW_MASK) | (u64)(s_tag[1 + src] & LOW_MASK);
+      ids[g] = id[k];
+    }
+  }
+  if (unsorted_long)
+    stats[0] = 1u;
+  // work counters (feedback for the choice of first_pass): scan steps and moved elements
+  steps = __reduce_add_sync(0xffffffffu, steps);
+  moved = __reduce_add_sync(0xffffffffu, moved);
+  if ((tid & 31) == 0) {
+    if (steps)
+      atomicAdd(reinterpret_cast<unsigned long long*>(stats + 2), (unsigned long long)steps);
+    if (moved)
+      atomicAdd(reinterpret_cast<unsigned long long*>(stats + 4), (unsigned long long)moved);
+  }
+}
+
+void
+launch_radix_sort_top(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, int first_pass, u32* hist, u32* status,
+                      u32* ticket, u32* stats, cudaStream_t stream, cudaEvent_t before_finish)
+{
+  if (n == 0)
+    return;
+  digit_base_kernel<<<1, RS_PASSES * 32, 0, stream>>>(hist);
+  const bool from1 = sort_input_buffer_top(first_pass) == 1;
+  run_passes(from1 ? keys1 : keys0, from1 ? vals1 : vals0, from1 ? keys0 : keys1, from1 ? vals0 : vals1, (u32)n,
+             first_pass, true, hist, status, ticket, stream);
+  if (before_finish)
+    cudaEventRecord(before_finish, stream);
+  if (first_pass == 0)
+    return;
+  const u32 tiles = (u32)((n + FIN_TILE - 1) / FIN_TILE);
+  switch (first_pass) {
+    case 1: segment_finish_kernel<8><<<tiles, FIN_THREADS, 0, stream>>>(keys0, vals0, (u32)n, stats); break;
+    case 2: segment_finish_kernel<16><<<tiles, FIN_THREADS, 0, stream>>>(keys0, vals0, (u32)n, stats); break;
+    default: segment_finish_kernel<24><<<tiles, FIN_THREADS, 0, stream>>>(keys0, vals0, (u32)n, stats); break;
+  }
+}
+
+void
+launch_radix_sort_again(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, const u32* scanned_hist, u32* status,
+                        u32* ticket, cudaStream_t stream)
+{
+  if (n == 0)
+    return;
+  const bool from1 = sort_input_buffer() == 1;
+  if (from1) { // odd pass count (9-bit digits): the passes must start in buffer 1
+    cudaMemcpyAsync(keys1, keys0, n * 8, cudaMemcpyDeviceToDevice, stream);
+    cudaMemcpyAsync(vals1, vals0, n * 4, cudaMemcpyDeviceToDevice, stream);
+  }
+  run_passes(from1 ? keys1 : keys0, from1 ? vals1 : vals0, from1 ? keys0 : keys1, from1 ? vals0 : vals1, (u32)n, 0,
+             false, scanned_hist, status, ticket, stream);
 }
 
 // =============================================================================================

@@ -32,6 +32,19 @@ size_t sort_status_words(u64 n);
 void launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hist, u32* status, u32* ticket,
                        cudaStream_t stream);
 
+// The same order with fewer passes over the data (see kernels_index_sort.cu): onesweep passes first_pass .. 7 sort by
+// the key bits from 8 * first_pass up (unsorted keys in keys<sort_input_buffer_top(first_pass)>), then the runs of
+// equal top bits are ordered in place by their low bits.  first_pass = 0 is launch_radix_sort.
+// `stats` (6 u32, 8-byte aligned, zeroed by the caller): [0] != 0: a run longer than the finish kernel handles was not
+// in order -> the caller must run launch_radix_sort_again (all eight passes over the current arrangement, `hist`
+// already scanned); [2..3] u64 scan steps, [4..5] u64 elements moved.  `before_finish`: optional event recorded
+// between the passes and the finish kernel.
+int sort_input_buffer_top(int first_pass);
+void launch_radix_sort_top(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, int first_pass, u32* hist,
+                           u32* status, u32* ticket, u32* stats, cudaStream_t stream, cudaEvent_t before_finish);
+void launch_radix_sort_again(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, const u32* scanned_hist,
+                             u32* status, u32* ticket, cudaStream_t stream);
+
 // positions gathered into Morton order: dst[i] = src[perm[i]] (24-byte records)
 void launch_gather_positions(const double* src, const u32* perm, u64 n, double* dst, cudaStream_t stream);
 // generic attribute gather for records of `width` bytes (1, 2, 3, 4, 8, 12)

@@ -115,6 +115,7 @@ struct HostScalars
   u64 n_selected;
   u32 scratch[16]; // pinned scratch for the min-distance driver (starts at u32 index 8... see below)
   u64 store_vals[4]; // read-backs of the multi-batch node store
+  u32 sort_stats[6]; // read-back of d_sort_stats(): flag, -, u64 scan steps, u64 moved
 };
 
 // One octree level of the multi-batch node store: node table sorted by node index and the
@@ -228,7 +229,12 @@ struct swgpu_tiler
   // stats
   swgpu_stats stats{};
   bool timing = false;
-  cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  cudaEvent_t ev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // [6]: before the sort's finish kernel
+
+  // K2 (swgpu_set_sort_mode): passes over the key bits from 8 * sort_first_pass up, then the segment finish
+  int sort_mode = -1;      // -1 = automatic
+  int sort_first_pass = 0; // of the current batch
+  int sort_next = -1;      // automatic mode: choice for the next batch from this batch's run lengths (-1 = none yet)
 
   // device scalar slots inside `scalars`
   u32* d_n_nodes() { return scalars.as<u32>() + 0; }
@@ -238,6 +244,7 @@ struct swgpu_tiler
   u64* d_n_selected() { return reinterpret_cast<u64*>(scalars.as<u32>() + 4); }
   u32* d_tickets() { return scalars.as<u32>() + 8; } // 16 u32
   u32* d_md_ncells() { return scalars.as<u32>() + 24; }
+  u32* d_sort_stats() { return scalars.as<u32>() + 26; } // 6 u32, 8-byte aligned
 };
 
 namespace {
@@ -344,6 +351,82 @@ sync_scalars(swgpu_tiler* h)
   CK(cudaMemcpyAsync(h->h_scalars, h->scalars.p, 24, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return SW_OK;
+}
+
+// ---- K2 ------------------------------------------------------------------------------------------------
+// Which onesweep pass the sort of this batch starts with (kernels_index_sort.cu: passes over the top digits, then
+// the segment finish).  Automatic mode: 3 (top 40 bits = 13 octree levels) when runs of equal top bits are short,
+// 2 (top 48 bits = 16 levels) for dense clouds.  The first batch of a handle takes 2: a wrong guess of 3 costs
+// eight extra passes (clustered LiDAR reaches thousands of points per level-13 cell at densities where a terrain
+// model has two), a cautious 2 costs one.  Afterwards the scan steps per point the finish kernel counted on the
+// previous batch decide.  The order produced is the same either way.
+int
+choose_sort_first_pass(const swgpu_tiler* h, u64 n)
+{
+  if (const char* e = std::getenv("SWGPU_SORT_FIRST_PASS")) { // experiments only
+    const int v = std::atoi(e);
+    if (v >= 0 && v <= 3)
+      return v;
+  }
+  if (h->sort_mode >= 0)
+    return h->sort_mode;
+  if (h->sort_next >= 0)
+    return h->sort_next;
+  (void)n;
+  return 2;
+}
+
+// the batch's keys are in keys[sort_input_buffer_top(h->sort_first_pass)]; sorted pairs end in keys[0] / vals[0]
+int
+sort_pairs(swgpu_tiler* h, u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, int fp)
+{
+  cudaStream_t s = h->stream;
+  launch_radix_sort_top(keys0, keys1, vals0, vals1, n, fp, h->hist.as<u32>(), h->sort_status.as<u32>(),
+                        h->d_tickets() + 8, h->d_sort_stats(), s, h->timing ? h->ev[6] : nullptr);
+  u32 passes = (u32)(sort_passes() - fp);
+  h->stats.kernel_launches += 1 + passes + (fp ? 1 : 0);
+  h->stats.sort_first_bit = 8u * (u32)fp;
+  h->stats.sort_fallback = 0;
+  h->stats.sort_scan_steps = 0;
+  h->stats.sort_moved = 0;
+  u64 moved = 0;
+  if (fp && n) {
+    CK(cudaMemcpyAsync(h->h_scalars->sort_stats, h->d_sort_stats(), 24, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const u32* st = h->h_scalars->sort_stats;
+    std::memcpy(&h->stats.sort_scan_steps, st + 2, 8);
+    std::memcpy(&moved, st + 4, 8);
+    h->stats.sort_moved = moved;
+    if (st[0]) { // a long run of equal top bits that is not in order: all eight passes over the current arrangement
+      launch_radix_sort_again(keys0, keys1, vals0, vals1, n, h->hist.as<u32>(), h->sort_status.as<u32>(),
+                              h->d_tickets() + 8, s);
+      h->stats.sort_fallback = 1;
+      h->stats.kernel_launches += (u32)sort_passes();
+      passes += (u32)sort_passes();
+      h->sort_next = fp >= 3 ? 2 : 0;
+    } else {
+      const double steps_per_point = (double)h->stats.sort_scan_steps / (double)n;
+      if (fp >= 3)
+        h->sort_next = steps_per_point > 32.0 ? 2 : 3;
+      else if (fp == 2)
+        h->sort_next = steps_per_point < 0.3 ? 3 : 2;
+      else
+        h->sort_next = fp;
+    }
+  }
+  h->stats.sort_passes = passes;
+  // histogram read + passes x 2 x 12 B (+ one read of the pairs by the finish kernel)
+  h->stats.bytes_sort = (8 + (u64)passes * 24 + (fp ? 12 : 0)) * n;
+  // traffic model: histograms come from K1, the first pass reads no ids, the finish writes what it moves
+  h->stats.bytes_traffic += ((u64)passes * 24 - 4 + (fp ? 12 : 0)) * n + 12 * moved;
+  return SW_OK;
+}
+
+int
+sort_batch(swgpu_tiler* h, u64 n)
+{
+  return sort_pairs(h, h->keys[0].as<u64>(), h->keys[1].as<u64>(), h->vals[0].as<u32>(), h->vals[1].as<u32>(), n,
+                    h->sort_first_pass);
 }
 
 int
@@ -832,7 +915,8 @@ run_batch(swgpu_tiler* h)
   // K1 (every launcher is a no-op for an empty shard)
   CK(cudaMemsetAsync(h->hist.p, 0, sort_hist_words() * 4, s));
   CK(cudaMemsetAsync(h->scalars.p, 0, 128, s));
-  u64* unsorted_keys = h->keys[sort_input_buffer()].as<u64>(); // the sort's last pass lands in keys[0]
+  h->sort_first_pass = choose_sort_first_pass(h, n);
+  u64* unsorted_keys = h->keys[sort_input_buffer_top(h->sort_first_pass)].as<u64>(); // the last pass lands in keys[0]
   if (h->d_las) { // K1-LAS: 12 B record in, 24 B position + 8 B key out
     launch_las_encode(h->d_las, n, h->las_t, h->bounds, h->d_xyz, unsorted_keys, h->hist.as<u32>(),
                       h->d_n_clamped(), s);
@@ -846,11 +930,9 @@ run_batch(swgpu_tiler* h)
   h->stats.kernel_launches += 1;
   record(h, 1);
   // K2
-  launch_radix_sort(h->keys[0].as<u64>(), h->keys[1].as<u64>(), h->vals[0].as<u32>(), h->vals[1].as<u32>(), n,
-                    h->hist.as<u32>(), h->sort_status.as<u32>(), h->d_tickets() + 8, s);
-  h->stats.kernel_launches += 1 + sort_passes();
-  h->stats.bytes_sort = (8 + (u64)sort_passes() * 24) * n; // histogram read + passes x 2 x 12 B
-  h->stats.bytes_traffic += ((u64)sort_passes() * 24 - 4) * n; // histograms come from K1, pass 0 reads no ids
+  rc = sort_batch(h, n);
+  if (rc)
+    return rc;
   record(h, 2);
   // K4
   if (needs_positions(h->prm.sampling)) {
@@ -1176,7 +1258,8 @@ run_batch_store(swgpu_tiler* h)
   record(h, 0);
   CK(cudaMemsetAsync(h->hist.p, 0, sort_hist_words() * 4, s));
   CK(cudaMemsetAsync(h->scalars.p, 0, 128, s));
-  u64* unsorted_keys = h->keys[sort_input_buffer()].as<u64>();
+  h->sort_first_pass = choose_sort_first_pass(h, n);
+  u64* unsorted_keys = h->keys[sort_input_buffer_top(h->sort_first_pass)].as<u64>();
   if (h->d_las) {
     launch_las_encode(h->d_las, n, h->las_t, h->bounds, h->d_xyz, unsorted_keys, h->hist.as<u32>(), h->d_n_clamped(),
                       s);
@@ -1186,10 +1269,10 @@ run_batch_store(swgpu_tiler* h)
     h->stats.bytes_index = 36 * n;
   }
   record(h, 1);
-  launch_radix_sort(h->keys[0].as<u64>(), h->keys[1].as<u64>(), h->vals[0].as<u32>(), h->vals[1].as<u32>(), n,
-                    h->hist.as<u32>(), h->sort_status.as<u32>(), h->d_tickets() + 8, s);
-  h->stats.kernel_launches += 2 + sort_passes();
-  h->stats.bytes_sort = (8 + (u64)sort_passes() * 24) * n;
+  rc = sort_batch(h, n);
+  if (rc)
+    return rc;
+  h->stats.kernel_launches += 1;
   record(h, 2);
   // the batch joins the point store (clamped positions, like the PointBuffer after index_point)
   const u64 base = h->store_points;
@@ -2035,10 +2118,16 @@ swgpu_sort_keys_device(swgpu_handle h, uint64_t* keys_device, uint64_t n, uint32
   CK(h->sort_status.ensure(sort_status_words(n) * 4));
   CK(cudaMemsetAsync(h->hist.p, 0, sort_hist_words() * 4, h->stream));
   launch_key_histogram(reinterpret_cast<const u64*>(keys_device), n, h->hist.as<u32>(), h->stream);
-  if (sort_input_buffer() == 1) // odd number of passes: start in the scratch buffer, finish in the caller's
+  // an explicit swgpu_set_sort_mode applies here too (keys with bit 63 clear); automatic mode sorts all digits,
+  // arbitrary keys carry no density hint
+  const int fp = h->sort_mode > 0 ? h->sort_mode : 0;
+  if (sort_input_buffer_top(fp) == 1) // odd number of passes: start in the scratch buffer, finish in the caller's
     CK(cudaMemcpyAsync(h->keys[1].p, keys_device, n * 8, cudaMemcpyDeviceToDevice, h->stream));
-  launch_radix_sort(reinterpret_cast<u64*>(keys_device), h->keys[1].as<u64>(), order_device, h->vals[1].as<u32>(), n, h->hist.as<u32>(),
-                    h->sort_status.as<u32>(), h->d_tickets() + 8, h->stream);
+  CK(cudaMemsetAsync(h->d_sort_stats(), 0, 24, h->stream));
+  const int rc = sort_pairs(h, reinterpret_cast<u64*>(keys_device), h->keys[1].as<u64>(), order_device,
+                            h->vals[1].as<u32>(), n, fp);
+  if (rc)
+    return rc;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   return SW_OK;
@@ -2270,6 +2359,16 @@ swgpu_set_shard_faces(swgpu_handle h, const uint32_t* first_prefix, uint32_t n_r
 }
 
 int
+swgpu_set_sort_mode(swgpu_handle h, int mode)
+{
+  if (!h || mode < -1 || mode > 3)
+    return SW_ERR_INVALID_ARGUMENT;
+  h->sort_mode = mode;
+  h->sort_next = -1;
+  return SW_OK;
+}
+
+int
 swgpu_enable_timing(swgpu_handle h, int enable)
 {
   if (!h)
@@ -2290,6 +2389,12 @@ swgpu_get_stats(swgpu_handle h, swgpu_stats* out)
     cudaStreamSynchronize(h->stream);
     cudaEventElapsedTime(&h->stats.ms_index, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->stats.ms_sort, h->ev[1], h->ev[2]);
+    h->stats.ms_sort_finish = 0.f;
+    if (h->stats.sort_first_bit && h->stats.n_points && !h->stats.sort_fallback) {
+      float before = 0.f;
+      cudaEventElapsedTime(&before, h->ev[1], h->ev[6]);
+      h->stats.ms_sort_finish = h->stats.ms_sort - before;
+    }
     cudaEventElapsedTime(&h->stats.ms_gather, h->ev[2], h->ev[3]);
     cudaEventElapsedTime(&h->stats.ms_sample, h->ev[3], h->ev[4]);
     const bool fin = h->finalized && h->prm.tiling == SW_FAST;

@@ -135,6 +135,8 @@ public:
   // Nodes where the reference would re-root (TilingAlgorithms.cpp:444-483): fail (default) or store them whole,
   // flagged SW_NODE_TERMINAL | SW_NODE_DEEP
   void set_deep_node_policy(bool store_whole) { check(swgpu_set_deep_node_policy(_handle, store_whole ? 1 : 0)); }
+  // K2: -1 automatic (top-digit passes + segment finish), 0 eight LSD passes, 1..3 explicit; same order in every mode
+  void set_sort_mode(int mode) { check(swgpu_set_sort_mode(_handle, mode)); }
 
   struct Result
   {

@@ -58,6 +58,12 @@ class SwgpuStats(C.Structure):
         ("kernel_launches", C.c_uint32),
         ("min_distance_rounds", C.c_uint32),
         ("bytes_traffic", C.c_uint64),
+        ("sort_passes", C.c_uint32),
+        ("sort_first_bit", C.c_uint32),
+        ("sort_fallback", C.c_uint32),
+        ("ms_sort_finish", C.c_float),
+        ("sort_scan_steps", C.c_uint64),
+        ("sort_moved", C.c_uint64),
     ]
 
 
@@ -88,6 +94,7 @@ SYMBOLS = [
     ("swgpu_finalize", C.c_int, [C.c_void_p]),
     ("swgpu_set_multi_batch", C.c_int, [C.c_void_p, C.c_int]),
     ("swgpu_set_deep_node_policy", C.c_int, [C.c_void_p, C.c_int]),
+    ("swgpu_set_sort_mode", C.c_int, [C.c_void_p, C.c_int]),
     ("swgpu_result_size", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("swgpu_get_nodes", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("swgpu_get_nodes_device_ids", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

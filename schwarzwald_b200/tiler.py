@@ -189,6 +189,11 @@ class GpuTiler:
         store all remaining points unsampled, flagged NODE_TERMINAL | NODE_DEEP."""
         self._check(self._lib.swgpu_set_deep_node_policy(self._h, 1 if store_whole else 0))
 
+    def set_sort_mode(self, mode=-1):
+        """K2: -1 automatic (top-digit passes + segment finish), 0 eight LSD passes, 1..3 passes over the key bits
+        from 8 * mode up + segment finish.  The sorted order is identical in every mode."""
+        self._check(self._lib.swgpu_set_sort_mode(self._h, int(mode)))
+
     # -- the two calls of TilingAlgorithmBase --------------------------------------------------------
     def build_execution_graph(self, points):
         """One batch.  `points`: host numpy (n,3) float64 (clamped in place like index_point does) or

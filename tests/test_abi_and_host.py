@@ -52,7 +52,7 @@ def test_struct_layouts_match_header():
     from schwarzwald_b200 import native, tiler
     assert ctypes.sizeof(native.SwParams) == ctypes.sizeof(sworacle.SwParams) == 80
     assert tiler.NODE_DTYPE.itemsize == sworacle.NODE_DTYPE.itemsize == 32
-    assert ctypes.sizeof(native.SwgpuStats) == 112
+    assert ctypes.sizeof(native.SwgpuStats) == 144
 
 
 def test_cubic_bounds_and_spacing_follow_reference():
