@@ -435,6 +435,7 @@ level_scan_kernel(u32* __restrict__ tile_sel, u32 n_tiles, u64* __restrict__ n_s
                   const u32* __restrict__ child_count, u32 n_slots, u32* __restrict__ next_node_start,
                   u32* __restrict__ n_nodes_next)
 {
+  // tile_sel == nullptr: only part (B) (the single-pass compaction has no tile counts to scan)
   __shared__ u32 s_wa[32], s_wb[32];
   __shared__ u32 s_carry_a, s_carry_b;
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -444,7 +445,7 @@ level_scan_kernel(u32* __restrict__ tile_sel, u32 n_tiles, u64* __restrict__ n_s
   }
   __syncthreads();
   // ---- (A) ---- (8 consecutive tiles per thread per iteration)
-  for (u32 t0 = 0; t0 < n_tiles; t0 += SCAN_THREADS * 8) {
+  for (u32 t0 = 0; tile_sel && t0 < n_tiles; t0 += SCAN_THREADS * 8) {
     const u32 t = t0 + threadIdx.x * 8;
     u32 v[8];
     u32 sum = 0;
@@ -479,7 +480,7 @@ level_scan_kernel(u32* __restrict__ tile_sel, u32 n_tiles, u64* __restrict__ n_s
       s_carry_a = carry + wofs + incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0 && tile_sel)
     *n_selected = s_carry_a;
   // ---- (B) ----
   if (!child_count)
@@ -611,6 +612,261 @@ level_scatter_kernel(SwLevelArgs a)
   }
 }
 
+// ---- single-pass variant (opt-in: SWGPU_COMPACT=1pass) -----------------------------------------------------
+// level_count + level_scatter in one kernel: the tile decides its selection, publishes the number of selected
+// points, and while the decoupled look-back over the tile descriptors resolves (warp 0) the other warps count the
+// children and stage the tile in output order.  One read of (key, id) and one write per point instead of a second
+// read of the keys, no selection bits, no tile scan.  Result identical to the two-pass kernels (the GPU parity
+// suite passes with it), but measured SLOWER on B200 in round 2: 0.88 ms instead of 0.82 ms per 100 M-point level
+// (C2 sweep 3.86 vs 3.61 ms, C3 shape at 100 M 13.70 vs 13.23 ms), and slower still with LB_WIDE = 8 descriptors
+// per lane and round trip (4.35 ms): the wait is not the walk over the descriptors but the block barrier behind the
+// look-back warp, a few memory round trips per tile that the 4 resident blocks per SM do not cover.  Kept for A/B
+// runs; the two-pass kernels stay the default.
+#ifndef LB_WIDE
+#define LB_WIDE 1
+#endif
+__device__ __forceinline__ u64
+lookback_resolve(u64* status, u32 tile, u64 aggregate) // all lanes of one warp; the aggregate is already published
+{
+  const u32 lane = threadIdx.x & 31;
+  if (tile == 0)
+    return 0;
+  u64 prefix = 0;
+  long long pos = (long long)tile - 1;
+  bool done = false;
+  while (!done) {
+    u64 s[LB_WIDE];
+#pragma unroll
+    for (int k = 0; k < LB_WIDE; ++k) {
+      const long long idx = pos - k * 32 - lane;
+      s[k] = (idx >= 0) ? ld_relaxed_u64(status + idx) : SW_LB_PFX; // tiles before 0: inclusive prefix 0
+    }
+#pragma unroll
+    for (int k = 0; k < LB_WIDE; ++k) {
+      if (!done) {
+        const long long idx = pos - k * 32 - lane;
+        u64 v = s[k];
+        while ((v >> 62) == 0)
+          v = ld_relaxed_u64(status + idx);
+        const u32 pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int first_p = pm ? (__ffs(pm) - 1) : 32;
+        u64 c = ((int)lane <= first_p) ? (v & SW_LB_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+          c += __shfl_xor_sync(0xffffffffu, c, o);
+        prefix += c;
+        done = pm != 0;
+      }
+    }
+    pos -= 32 * LB_WIDE;
+  }
+  if (lane == 0)
+    st_relaxed_u64(status + tile, SW_LB_PFX | ((prefix + aggregate) & SW_LB_MASK));
+  return prefix;
+}
+
+__global__ void __launch_bounds__(SWP_THREADS, 4)
+level_compact_fused_kernel(SwLevelArgs a, u64* __restrict__ n_selected)
+{
+  __shared__ u64 s_k[BLK_SLOTS];
+  __shared__ u32 s_i[BLK_SLOTS];
+  __shared__ u64 s_prev;
+  __shared__ u64 s_prefix;
+  __shared__ u32 s_w[SWP_WARPS];
+  __shared__ u32 s_w2[SWP_WARPS];
+  __shared__ u32 s_slot;
+  __shared__ u32 s_child[CHILD_WINDOW];
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 tile = take_ticket(a.ticket, &s_slot);
+  const u64 base = (u64)tile * SW_SWEEP_TILE;
+  const u64 e0 = base + 8ull * tid;
+  const u32 tile_valid = (a.count - base) < SW_SWEEP_TILE ? (u32)(a.count - base) : SW_SWEEP_TILE;
+  for (u32 i = tid; i < CHILD_WINDOW; i += SWP_THREADS)
+    s_child[i] = 0;
+
+  // ---- load: keys and ids, coalesced, transposed to the blocked layout ----------------------------------
+  if (a.in_idx) {
+#pragma unroll
+    for (int j = 0; j < BLK_ITEMS; ++j) {
+      const u32 p = j * SWP_THREADS + tid;
+      s_i[BLK_PAD(p)] = (p < tile_valid) ? a.in_idx[base + p] : 0u;
+    }
+  }
+  u64 k[BLK_ITEMS];
+  u64 prev;
+  load_keys_blocked(a.in_key, base, a.count, s_k, &s_prev, k, prev);
+  u32 idx[BLK_ITEMS];
+#pragma unroll
+  for (int j = 0; j < BLK_ITEMS; ++j)
+    idx[j] = a.in_idx ? s_i[9 * tid + j] : (u32)(e0 + j);
+  const u32 nvalid = e0 >= a.count ? 0u : (a.count - e0 < 8 ? (u32)(a.count - e0) : 8u);
+  const u32 valid = (1u << nvalid) - 1u;
+
+  // ---- node heads, cell heads, node rank -> take-all decision -> selection bits (as level_count_kernel) -----
+  u32 nh, ch;
+  head_bits2(k, prev, a.node_shift, a.cell_shift, e0 == 0, nh, ch);
+  nh &= valid;
+  ch &= valid;
+  u32 hexcl;
+  block_scan_packed(__popc(nh), s_w, hexcl); // (barrier: every thread holds its keys and ids in registers now)
+  const u32 rank0 = a.tile_rank0[tile];
+  const u32 rank_before = rank0 + hexcl - 1u; // node of the element before my first one (0xFFFFFFFF: none yet)
+  u32 rank = rank_before;
+  bool take = a.force_all != 0;
+  if (!take && a.allow_take_all && nvalid && !(nh & 1u))
+    take = (u64)node_point_count(a.node_start, a.node_gcount, rank) <= a.max_points_per_node;
+  u32 other = 0; // strategy flags of the 8 elements (one byte each in a.sel)
+  if (a.sampling != SW_RANDOM_GRID && !a.force_all && nvalid) {
+    if (nvalid == 8) {
+      const u64 bytes = *reinterpret_cast<const u64*>(a.sel + e0);
+#pragma unroll
+      for (int j = 0; j < BLK_ITEMS; ++j)
+        other |= (((bytes >> (8 * j)) & 0xFFu) == 1u ? 1u : 0u) << j;
+    } else {
+      for (u32 j = 0; j < nvalid; ++j)
+        other |= (a.sel[e0 + j] == 1 ? 1u : 0u) << j;
+    }
+  }
+  const u32 pick = (a.sampling == SW_RANDOM_GRID) ? ch : other; // Sampling.h:253-284: first point of each cell run
+  u32 sel = 0, takebits = 0;
+  u32 slot0 = 0;        // child slot of my first element
+  bool one_slot = true; // all my elements fall into the same child of the same node
+  const int child_shift = a.node_shift - 3;
+#pragma unroll
+  for (int j = 0; j < BLK_ITEMS; ++j) {
+    if ((nh >> j) & 1u) {
+      ++rank;
+      if (!a.force_all && a.allow_take_all)
+        take = (u64)node_point_count(a.node_start, a.node_gcount, rank) <= a.max_points_per_node;
+    }
+    sel |= ((take ? 1u : ((pick >> j) & 1u)) << j);
+    takebits |= (take ? 1u : 0u) << j;
+    if (a.child_count) {
+      const u32 slot = rank * 8u + (u32)((k[j] >> child_shift) & 7u);
+      if (j == 0)
+        slot0 = slot;
+      else if (((valid >> j) & 1u) && slot != slot0)
+        one_slot = false;
+    }
+  }
+  sel &= valid;
+
+  // ---- selected points of the tile: publish, then look back while the rest of the block goes on -------------
+  u32 sexcl;
+  const u32 tile_selected = block_scan_packed(__popc(sel), s_w2, sexcl);
+  if (tid == 0)
+    st_relaxed_u64(a.status + tile, (tile == 0 ? SW_LB_PFX : SW_LB_AGG) | (u64)tile_selected);
+
+  // ---- points that stay, counted per child node (as level_count_kernel) -------------------------------------
+  if (a.child_count) {
+    const u32 slot_base = (rank0 ? rank0 - 1u : 0u) * 8u; // slots of this tile start here or later
+    const u32 rem = valid & ~sel;
+    const u32 lead_slot = __shfl_sync(0xffffffffu, slot0, 0);
+    const bool uniform = __all_sync(0xffffffffu, nvalid == 0 || (one_slot && slot0 == lead_slot));
+    if (uniform) { // the whole warp (256 points) lies in one child: one atomic
+      u32 c = __popc(rem);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0 && c) {
+        if (lead_slot - slot_base < CHILD_WINDOW)
+          atomicAdd(&s_child[lead_slot - slot_base], c);
+        else
+          atomicAdd(&a.child_count[lead_slot], c);
+      }
+    } else { // runs of equal child inside the thread
+      u32 r2 = rank_before;
+      u32 cur = 0xFFFFFFFFu, cnt = 0;
+#pragma unroll
+      for (int j = 0; j < BLK_ITEMS; ++j) {
+        if ((nh >> j) & 1u)
+          ++r2;
+        if ((rem >> j) & 1u) {
+          const u32 slot = r2 * 8u + (u32)((k[j] >> child_shift) & 7u);
+          if (slot != cur) {
+            if (cnt) {
+              if (cur - slot_base < CHILD_WINDOW)
+                atomicAdd(&s_child[cur - slot_base], cnt);
+              else
+                atomicAdd(&a.child_count[cur], cnt);
+            }
+            cur = slot;
+            cnt = 0;
+          }
+          ++cnt;
+        }
+      }
+      if (cnt) {
+        if (cur - slot_base < CHILD_WINDOW)
+          atomicAdd(&s_child[cur - slot_base], cnt);
+        else
+          atomicAdd(&a.child_count[cur], cnt);
+      }
+    }
+  }
+
+  // ---- staging in output order: selected points first, then the points that stay, both in input order --------
+#pragma unroll
+  for (int j = 0; j < BLK_ITEMS; ++j) {
+    if ((valid >> j) & 1u) {
+      const u32 sbefore = sexcl + __popc(sel & ((1u << j) - 1u));
+      const u32 p = ((sel >> j) & 1u) ? sbefore : tile_selected + (8u * tid + j - sbefore);
+      s_k[BLK_PAD(p)] = k[j];
+      s_i[BLK_PAD(p)] = idx[j];
+    }
+  }
+  if (warp == 0) {
+    const u64 pfx = lookback_resolve(a.status, tile, (u64)tile_selected);
+    if (lane == 0)
+      s_prefix = pfx;
+  }
+  __syncthreads();
+  const u64 tile_off = s_prefix; // selected before this tile
+  if (a.child_count) {
+    const u32 slot_base = (rank0 ? rank0 - 1u : 0u) * 8u;
+    for (u32 i = tid; i < CHILD_WINDOW; i += SWP_THREADS) {
+      const u32 c = s_child[i];
+      if (c)
+        atomicAdd(&a.child_count[slot_base + i], c);
+    }
+  }
+  if (tid == 0 && base + SW_SWEEP_TILE >= a.count)
+    *n_selected = tile_off + tile_selected;
+
+  // ---- node table rows ---------------------------------------------------------------------------------------
+  if (nh) {
+    u32 r3 = rank_before;
+#pragma unroll
+    for (int j = 0; j < BLK_ITEMS; ++j) {
+      if ((nh >> j) & 1u) {
+        ++r3;
+        const u32 sbefore = sexcl + __popc(sel & ((1u << j) - 1u));
+        const bool tk = !a.force_all && a.allow_take_all && ((takebits >> j) & 1u);
+        a.node_index[a.node_base + r3] = k[j] >> a.node_shift;
+        // bit 63 = SW_NODE_TAKE_ALL (decoded by the host when it builds the node table)
+        a.node_first[a.node_base + r3] = (a.out_offset + tile_off + sbefore) | ((u64)(tk ? 1u : 0u) << 63);
+      }
+    }
+  }
+
+  // ---- coalesced copy-out: one contiguous range of the output chunk, one of the remainder list -------------
+  u64* const out_key = a.out_key + a.out_offset + tile_off;
+  u32* const out_idx = a.out_idx + a.out_offset + tile_off;
+  const u64 rem_base = base - tile_off;
+#pragma unroll
+  for (int m = 0; m < BLK_ITEMS; ++m) {
+    const u32 q = m * SWP_THREADS + tid;
+    if (q < tile_selected) {
+      out_key[q] = s_k[BLK_PAD(q)];
+      out_idx[q] = s_i[BLK_PAD(q)];
+    } else if (q < tile_valid && a.rem_key) {
+      const u32 r = q - tile_selected;
+      a.rem_key[rem_base + r] = s_k[BLK_PAD(q)];
+      a.rem_idx[rem_base + r] = s_i[BLK_PAD(q)];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // node tables that come from per-node data instead of a pass over the points
 // ---------------------------------------------------------------------------------------------
@@ -696,6 +952,15 @@ launch_level_compact(const SwLevelArgs& a, u64* n_selected, u32 n_child_slots, u
   const u32 tiles = (u32)sweep_tiles(a.count);
   if (a.child_count)
     cudaMemsetAsync(a.child_count, 0, (size_t)n_child_slots * sizeof(u32), stream);
+  if (a.status) { // single pass (a.status == nullptr selects the two-pass kernels: A/B measurements)
+    cudaMemsetAsync(a.status, 0, (size_t)tiles * sizeof(u64), stream);
+    cudaMemsetAsync(a.ticket, 0, sizeof(u32), stream);
+    level_compact_fused_kernel<<<tiles, SWP_THREADS, 0, stream>>>(a, n_selected);
+    if (a.child_count)
+      level_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(nullptr, 0, n_selected, a.child_count, n_child_slots,
+                                                        next_node_start, n_nodes_next);
+    return;
+  }
   level_count_kernel<<<tiles, SWP_THREADS, 0, stream>>>(a);
   level_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(a.tile_sel, tiles, n_selected, a.child_count, n_child_slots,
                                                     next_node_start, n_nodes_next);

@@ -86,6 +86,8 @@ struct SwLevelArgs
   // optional per-element selection flags (argmin / min-distance strategies)
   const unsigned char* sel;
   // scratch of the two-pass compaction
+  u64* status;      // single-pass compaction: sweep_tiles look-back descriptors (nullptr = two-pass kernels)
+  u32* ticket;      // single-pass compaction: tile ticket
   u32* selbits;     // one bit per element: sweep_tiles * SW_SWEEP_TILE / 32 words
   u32* tile_sel;    // per tile: selected points (count pass), then their exclusive scan
   u32* child_count; // 8 * n_nodes counters of the points that stay, per child node; nullptr = not needed

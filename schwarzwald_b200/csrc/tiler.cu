@@ -232,6 +232,7 @@ struct swgpu_tiler
   cudaEvent_t ev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // [6]: before the sort's finish kernel
 
   // K2 (swgpu_set_sort_mode): passes over the key bits from 8 * sort_first_pass up, then the segment finish
+  bool two_pass_compaction = true; // SWGPU_COMPACT=1pass selects level_compact_fused_kernel (A/B measurements)
   int sort_mode = -1;      // -1 = automatic
   int sort_first_pass = 0; // of the current batch
   int sort_next = -1;      // automatic mode: choice for the next batch from this batch's run lengths (-1 = none yet)
@@ -761,6 +762,8 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
   CK(h->tile_sel.ensure(sweep_tiles(count) * 4));
   a.selbits = h->selbits.as<u32>();
   a.tile_sel = h->tile_sel.as<u32>();
+  a.status = h->two_pass_compaction ? nullptr : h->scan_status.as<u64>(); // >= sweep_tiles(count) u64 (node_rle)
+  a.ticket = h->d_tickets() + 7;
   // the points that stay are counted per child node: that IS the node table of the next level
   const bool want_children = rem_key != nullptr && !force_all && levels < 21;
   const u32 n_child_slots = want_children ? 8u * n_nodes : 0u;
@@ -770,7 +773,7 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
     a.child_count = h->child_count.as<u32>();
   }
   launch_level_compact(a, h->d_n_selected(), n_child_slots, h->node_start_next.as<u32>(), h->d_n_nodes_next(), s);
-  h->stats.kernel_launches += 3;
+  h->stats.kernel_launches += a.status ? (a.child_count ? 2 : 1) : 3;
   rc = sync_scalars(h);
   if (rc)
     return rc;
@@ -784,8 +787,8 @@ sweep_level(swgpu_tiler* h, const u64* in_key, const u32* in_idx, u64 count, int
   // algorithmic bytes of the level by SURVEY 8(d): read key + id (+ position), write the compacted remainder,
   // write the selected ids
   h->stats.bytes_sample += (12 + (reads_positions ? 24 : 0)) * count + (rem_key ? 12 * (count - n_sel) : 0) + 4 * n_sel;
-  // what this design really moves: count pass reads the keys, scatter pass reads keys + ids, writes (key, id)
-  h->stats.bytes_traffic += (16 + (in_idx ? 4 : 0)) * count + 12 * n_sel + (rem_key ? 12 * (count - n_sel) : 0);
+  // what this design really moves: keys + ids read once (the two-pass kernels read the keys twice), (key, id) written
+  h->stats.bytes_traffic += ((a.status ? 8 : 16) + (in_idx ? 4 : 0)) * count + 12 * n_sel + (rem_key ? 12 * (count - n_sel) : 0);
   if (n_nodes_next_out)
     *n_nodes_next_out = want_children ? h->h_scalars->n_nodes_next : 0u;
   if (want_children) // the next level reads its node boundaries from node_start
@@ -1504,6 +1507,8 @@ swgpu_create(const sw_params* params, int device, swgpu_handle* out)
     return SW_ERR_INVALID_ARGUMENT;
 
   auto* h = new swgpu_tiler();
+  if (const char* e = std::getenv("SWGPU_COMPACT"))
+    h->two_pass_compaction = std::strcmp(e, "1pass") != 0;
   h->prm = *params;
   if (h->prm.concurrency == 0)
     h->prm.concurrency = 1;

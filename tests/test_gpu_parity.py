@@ -89,6 +89,17 @@ def test_urban_clustered(port_oracle, sampling):
     assert_same(*run_both(port_oracle, xyz, sampling, "FAST", bmin, bmax, spacing, 5000, 4))
 
 
+@pytest.mark.parametrize("tiling", TILINGS)
+@pytest.mark.parametrize("sampling", ["RANDOM_GRID", "JITTERED", "MIN_DISTANCE"])
+def test_single_pass_compaction_variant(port_oracle, sampling, tiling, monkeypatch):
+    """SWGPU_COMPACT=1pass (read at swgpu_create): level_compact_fused_kernel instead of count + scatter."""
+    _torch_cuda()
+    monkeypatch.setenv("SWGPU_COMPACT", "1pass")
+    xyz = make_cloud("terrain", 700_000, 12, side_m=1500.0)
+    bmin, bmax, spacing = setup_case(xyz)
+    assert_same(*run_both(port_oracle, xyz, sampling, tiling, bmin, bmax, spacing, 8000, 8))
+
+
 @pytest.mark.parametrize("sampling", SAMPLINGS)
 def test_skewed_density(port_oracle, sampling):
     """95 % of the points in 1 % of the volume: long cells, unbalanced nodes."""
