@@ -799,19 +799,93 @@ launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hi
 #define FIN_HEAD 0x80000000u    /* the element starts a run of equal top bits */
 #define FIN_FOREIGN 0x40000000u /* left sentinel: the run continues from the previous tile */
 #define FIN_KEEP 0xffffu
-#define FIN_CHUNK 6 /* loads in flight per thread while the tags are built */
+#define FIN_STRIDE 24 /* elements a warp advances per 32-lane window */
 
 // Shared memory holds one 32-bit tag per window element (the low key bits, at most 24, and the head flag: a step
 // of a scan is one LDS and three integer instructions) and, per window position, which element moves there.
 // Elements are pulled: the thread of position q reads the id of the element that belongs at q, and after a block
 // barrier rewrites the low bits of keys[q] (the top bits are those of its run) and ids[q].  So every thread writes
 // its own position only, and all reads of ids precede all writes.
+// One element of a run, ranked by scanning the tags to both ends of the run (at most FIN_LIMIT - 1 steps).
+template<int LOW_BITS>
+__device__ __forceinline__ void
+finish_scan_run(u32 j, u32 tag, const u32* s_tag, unsigned short* s_src, u32& steps, u32& moved, bool& unsorted_long)
+{
+  constexpr u32 LOW_MASK = (1u << LOW_BITS) - 1;
+  const u32 lo = tag & LOW_MASK;
+  u32 budget = FIN_LIMIT - 1; // other elements a run may have
+  bool too_long = false;
+  // elements of the run in front of this one: those that do not have larger low bits stay in front
+  int l = (int)j;
+  u32 t = tag, rk = 0;
+  while (!(t & FIN_HEAD)) {
+    if (budget == 0) {
+      too_long = true;
+      break;
+    }
+    --budget;
+    --l;
+    t = s_tag[1 + l];
+    rk += ((t & LOW_MASK) <= lo) ? 1u : 0u;
+  }
+  bool skip = false;
+  if (!too_long) {
+    // runs that start in an earlier tile are finished there (its window reaches this element), runs that start
+    // behind this tile by the next one
+    skip = (t & FIN_FOREIGN) || l >= FIN_TILE;
+    // elements of the run behind this one: those with smaller low bits move in front
+    for (u32 r = j + 1; !skip; ++r) {
+      const u32 t2 = s_tag[1 + r];
+      if (t2 & FIN_HEAD)
+        break;
+      if (budget == 0) {
+        too_long = true;
+        break;
+      }
+      --budget;
+      rk += ((t2 & LOW_MASK) < lo) ? 1u : 0u;
+    }
+  }
+  steps += FIN_LIMIT - 1 - budget;
+  if (too_long) { // the run stays as it is: fine if it is in order already (identical points are)
+    unsorted_long |= !(tag & FIN_HEAD) && (s_tag[j] & LOW_MASK) > lo;
+  } else if (!skip) {
+    const u32 p = (u32)l + rk;
+    if (p != j) {
+      s_src[p] = (unsigned short)j;
+      ++moved;
+    }
+  }
+}
+
+// tags of window elements tid + k * FIN_THREADS, k in [K0, K0 + CNT), of an interior tile
+template<int LOW_BITS, int K0, int CNT>
+__device__ __forceinline__ void
+finish_tags(const u64* __restrict__ kp, u32 tid, u32* s_tag)
+{
+  constexpr u32 LOW_MASK = (1u << LOW_BITS) - 1;
+  u64 key[CNT], pk[CNT];
+#pragma unroll
+  for (int c = 0; c < CNT; ++c) {
+    const u32 j = tid + (K0 + c) * FIN_THREADS;
+    key[c] = kp[j];
+    pk[c] = kp[(int)j - 1];
+  }
+#pragma unroll
+  for (int c = 0; c < CNT; ++c) {
+    const u32 j = tid + (K0 + c) * FIN_THREADS;
+    const bool head = ((key[c] ^ pk[c]) >> LOW_BITS) != 0;
+    s_tag[1 + j] = ((u32)key[c] & LOW_MASK) | (head ? FIN_HEAD : 0u);
+  }
+}
+
 template<int LOW_BITS>
 __global__ void __launch_bounds__(FIN_THREADS, 6)
 segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32* __restrict__ stats)
 {
   static_assert(LOW_BITS <= 24, "tags keep the low bits next to two flag bits");
-  __shared__ u32 s_tag[FIN_WINDOW + 2]; // [0] left sentinel, [1 + j] window element j, [1 + FIN_WINDOW] right sentinel
+  // [0] left sentinel, [1 + j] window element j, then sentinels up to the end of the last warp window
+  __shared__ u32 s_tag[1 + FIN_WINDOW + 32];
   __shared__ unsigned short s_src[FIN_WINDOW];
   constexpr u32 LOW_MASK = (1u << LOW_BITS) - 1;
   const u32 tid = threadIdx.x;
@@ -819,97 +893,92 @@ segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32*
   const u32 valid = (n - base) < FIN_WINDOW ? (n - base) : FIN_WINDOW; // window elements that exist
 
   // ---- tags -------------------------------------------------------------------------------------------------
-  // (chunks of FIN_CHUNK elements per thread keep the loads in flight without spilling registers)
-  {
-    const bool interior = valid == FIN_WINDOW && base != 0;
+  for (u32 i = tid; i < FIN_WINDOW / 2; i += FIN_THREADS)
+    reinterpret_cast<u32*>(s_src)[i] = 0xffffffffu; // FIN_KEEP everywhere
+  if (tid < 32)
+    s_tag[1 + FIN_WINDOW + tid] = FIN_HEAD;
+  if (valid == FIN_WINDOW && base != 0) {
+    // interior tile (all but the first and the last two): no bounds tests; three chunks keep 6 + 6 + 5 pairs of
+    // loads in flight per thread without spilling registers
+    const u64* kp = keys + base;
+    finish_tags<LOW_BITS, 0, 6>(kp, tid, s_tag);
+    finish_tags<LOW_BITS, 6, 6>(kp, tid, s_tag);
+    finish_tags<LOW_BITS, 12, FIN_ITEMS - 12>(kp, tid, s_tag);
+    if (tid == 0) // left sentinel: the low bits of the element before the tile (inversion test of element 0)
+      s_tag[0] = ((u32)kp[-1] & LOW_MASK) | FIN_HEAD | FIN_FOREIGN;
+  } else {
 #pragma unroll 1
-    for (int k0 = 0; k0 < FIN_ITEMS; k0 += FIN_CHUNK) {
-      u64 key[FIN_CHUNK], pk[FIN_CHUNK];
-#pragma unroll
-      for (int c = 0; c < FIN_CHUNK; ++c) {
-        const u32 j = tid + (k0 + c) * FIN_THREADS;
-        const u32 g = base + j;
-        if (interior) {
-          if (k0 + c < FIN_ITEMS) {
-            key[c] = keys[g];
-            pk[c] = keys[g - 1];
-          }
-        } else {
-          key[c] = (k0 + c < FIN_ITEMS && j < valid) ? keys[g] : ~0ull; // bit 63 set: top bits no MortonIndex64 has
-          pk[c] = (k0 + c < FIN_ITEMS && g > 0 && j <= valid) ? keys[g - 1] : ~0ull;
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < FIN_CHUNK; ++c) {
-        if (k0 + c < FIN_ITEMS) {
-          const u32 j = tid + (k0 + c) * FIN_THREADS;
-          const bool head = ((key[c] ^ pk[c]) >> LOW_BITS) != 0 || (base + j) == 0;
-          s_tag[1 + j] = ((u32)key[c] & LOW_MASK) | (head ? FIN_HEAD : 0u);
-          s_src[j] = FIN_KEEP;
-          if (j == 0) // left sentinel: the low bits of the element before the tile (inversion test of element 0)
-            s_tag[0] = ((u32)pk[c] & LOW_MASK) | FIN_HEAD | FIN_FOREIGN;
-        }
-      }
+    for (u32 j = tid; j < FIN_WINDOW; j += FIN_THREADS) {
+      const u32 g = base + j;
+      const u64 key = j < valid ? keys[g] : ~0ull; // bit 63 set: top bits no MortonIndex64 has
+      const u64 pk = (g > 0 && j <= valid) ? keys[g - 1] : ~0ull;
+      const bool head = ((key ^ pk) >> LOW_BITS) != 0 || g == 0 || j >= valid;
+      s_tag[1 + j] = ((u32)key & LOW_MASK) | (head ? FIN_HEAD : 0u);
+      if (j == 0)
+        s_tag[0] = ((u32)pk & LOW_MASK) | FIN_HEAD | FIN_FOREIGN;
     }
-    if (tid == 0)
-      s_tag[1 + FIN_WINDOW] = FIN_HEAD;
   }
   __syncthreads();
 
   // ---- where every element belongs --------------------------------------------------------------------------
+  // A warp looks at 32 consecutive elements at a time and advances by FIN_STRIDE = 24: a run that starts in the
+  // first 24 lanes and ends inside the 32 is ranked with shuffles, in as many uniform steps as the longest such
+  // run of the window has elements (no divergent scans; runs of real clouds have a handful of elements).  Runs
+  // that reach beyond the window take the scalar scan over the tags (finish_scan_run).  Every element is seen by
+  // one or two windows and handled by exactly one: lanes 0..7 of a window are lanes 24..31 of the one before.
   u32 steps = 0, moved = 0;
   bool unsorted_long = false;
+  const u32 lane = tid & 31, warp = tid >> 5;
+  const u32 le = 0xffffffffu >> (31 - lane); // lanes <= mine
+  if constexpr (LOW_BITS < 24) {
+    // dense clouds (48 top bits sorted by the passes): nearly every run has one element, which two tag reads show
 #pragma unroll 1
-  for (u32 j = tid; j < valid; j += FIN_THREADS) {
-    const u32 w = s_tag[1 + j];
-    if (w & s_tag[2 + j] & FIN_HEAD)
-      continue; // a run of one element
-    const u32 lo = w & LOW_MASK;
-    u32 budget = FIN_LIMIT - 1; // other elements a run may have
-    bool too_long = false;
-    // elements of the run in front of this one: those that do not have larger low bits stay in front
-    int l = (int)j;
-    u32 t = w, rank = 0;
-    while (!(t & FIN_HEAD)) {
-      if (budget == 0) {
-        too_long = true;
-        break;
+    for (u32 j = tid; j < valid; j += FIN_THREADS) {
+      const u32 tag = s_tag[1 + j];
+      if (!(tag & s_tag[2 + j] & FIN_HEAD))
+        finish_scan_run<LOW_BITS>(j, tag, s_tag, s_src, steps, moved, unsorted_long);
+    }
+  } else {
+#pragma unroll 1
+  for (u32 w0 = warp * FIN_STRIDE; w0 < valid; w0 += (FIN_THREADS / 32) * FIN_STRIDE) {
+    const u32 j = w0 + lane;
+    const u32 tag = s_tag[1 + j]; // elements behind the last valid one carry FIN_HEAD
+    const u32 lo = tag & LOW_MASK;
+    const u32 heads = __ballot_sync(0xffffffffu, (tag & FIN_HEAD) != 0);
+    const u32 hb = heads & le, ha = heads & ~le;
+    const bool live = j < valid;
+    const int l_lane = 31 - __clz(hb); // -1: the run starts before the window
+    const int r_lane = ha ? __ffs(ha) - 1 : 32;
+    // runs of this window that the shuffle path can rank
+    const bool mine = live && hb != 0 && l_lane < FIN_STRIDE;
+    const bool fast = mine && ha != 0;
+    // elements nobody else scans: runs that leave the window at its end, or entered it more than 8 lanes ago (the
+    // previous window could not see their end either); in the first window every run that comes from the left
+    const bool slow = live && ((mine && ha == 0) || (hb == 0 && (lane >= 32 - FIN_STRIDE || w0 == 0)));
+    const int len = fast ? r_lane - l_lane : 1;
+    const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    // (low bits, lane) as one number: an element precedes another iff its number is smaller (ties: earlier lane)
+    const u32 val = (lo << 5) | lane;
+    u32 rank = 0;
+    for (int d = 1; d < maxlen; ++d) {
+      int partner = (int)lane + d;
+      if (partner >= r_lane)
+        partner -= len;
+      const u32 v = __shfl_sync(0xffffffffu, val, d < len ? partner : (int)lane);
+      rank += v < val ? 1u : 0u;
+    }
+    if (fast) {
+      steps += (u32)len - 1u;
+      const u32 l = w0 + (u32)l_lane;
+      const u32 p = l + rank;
+      if (l < FIN_TILE && p != j) { // runs that start behind this tile belong to the next one
+        s_src[p] = (unsigned short)j;
+        ++moved;
       }
-      --budget;
-      --l;
-      t = s_tag[1 + l];
-      rank += ((t & LOW_MASK) <= lo) ? 1u : 0u;
     }
-    if (!too_long) {
-      // runs that start in an earlier tile are finished there (its window reaches this element), runs that start
-      // behind this tile by the next one
-      if ((t & FIN_FOREIGN) || l >= FIN_TILE) {
-        steps += FIN_LIMIT - 1 - budget;
-        continue;
-      }
-      // elements of the run behind this one: those with smaller low bits move in front
-      for (u32 r = j + 1;; ++r) {
-        const u32 t2 = s_tag[1 + r];
-        if (t2 & FIN_HEAD)
-          break;
-        if (budget == 0) {
-          too_long = true;
-          break;
-        }
-        --budget;
-        rank += ((t2 & LOW_MASK) < lo) ? 1u : 0u;
-      }
-    }
-    steps += FIN_LIMIT - 1 - budget;
-    if (too_long) { // the run stays as it is: fine if it is in order already (identical points are)
-      unsorted_long |= !(w & FIN_HEAD) && (s_tag[j] & LOW_MASK) > lo;
-      continue;
-    }
-    const u32 p = (u32)l + rank;
-    if (p != j) {
-      s_src[p] = (unsigned short)j;
-      ++moved;
-    }
+    if (slow)
+      finish_scan_run<LOW_BITS>(j, tag, s_tag, s_src, steps, moved, unsorted_long);
+  }
   }
   __syncthreads();
 
@@ -936,7 +1005,7 @@ segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32*
   // work counters (feedback for the choice of first_pass): scan steps and moved elements
   steps = __reduce_add_sync(0xffffffffu, steps);
   moved = __reduce_add_sync(0xffffffffu, moved);
-  if ((tid & 31) == 0) {
+  if (lane == 0) {
     if (steps)
       atomicAdd(reinterpret_cast<unsigned long long*>(stats + 2), (unsigned long long)steps);
     if (moved)
