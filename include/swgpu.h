@@ -87,10 +87,10 @@ int swgpu_set_deep_node_policy(swgpu_handle h, int policy);
 
 /* K2, the sort that replaces std::sort over IndexedPoint64 (TilingAlgorithms.cpp:600-604,1289-1292).  The result is
  * the same in every mode (key order, ties by original point index); the modes differ in how often the pairs move:
- *   -1 (default)  automatic: onesweep passes over the top 40 or 48 key bits only, then the runs of equal top bits
- *                 are ordered in place by one kernel; the number of top bits follows the point density (estimated
- *                 from the point count for the first batch of a handle, from the previous batch's run lengths
- *                 afterwards)
+ *   -1 (default)  automatic: the first batch of a handle is sorted by the eight LSD passes and its sorted keys are
+ *                 probed for the lengths of the runs of equal top 40 / 48 key bits; while those are short (terrain,
+ *                 uniform and volume-filling clouds) later batches run onesweep passes over the top 40 or 48 bits
+ *                 only and order the runs in place with one kernel; clustered clouds keep the eight passes
  *    0            eight LSD passes over all 63 bits
  *    1, 2, 3      passes over the key bits from 8 * mode up, then the segment finish */
 int swgpu_set_sort_mode(swgpu_handle h, int mode);
@@ -316,7 +316,9 @@ typedef struct swgpu_stats {
   /* K2 of the last batch (swgpu_set_sort_mode) */
   uint32_t sort_passes;     /* onesweep passes executed (8 = plain LSD; 5 or 6 + the segment finish otherwise) */
   uint32_t sort_first_bit;  /* key bits below this one were ordered by the segment finish kernel (0 = none) */
-  uint32_t sort_fallback;   /* 1 = a long unsorted run of equal top bits made the eight LSD passes necessary */
+  uint32_t sort_fallback;   /* runs of equal top bits longer than the finish kernel handles (256) that were not in
+                             * order: 2 = each sorted on its own (long_run_sort_kernel), 1 = they held more than 1/8 of
+                             * the batch, eight LSD passes were run instead; 0 = none */
   float ms_sort_finish;     /* part of ms_sort spent in the segment finish kernel */
   uint64_t sort_scan_steps; /* neighbour comparisons of the segment finish kernel */
   uint64_t sort_moved;      /* elements the segment finish kernel moved */

@@ -799,6 +799,7 @@ launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hi
 #define FIN_HEAD 0x80000000u    /* the element starts a run of equal top bits */
 #define FIN_FOREIGN 0x40000000u /* left sentinel: the run continues from the previous tile */
 #define FIN_KEEP 0xffffu
+#define FIN_UNSORTED 0x80000000u /* stats[0]: a run longer than FIN_LIMIT is not in order */
 #define FIN_STRIDE 24 /* elements a warp advances per 32-lane window */
 
 // Shared memory holds one 32-bit tag per window element (the low key bits, at most 24, and the head flag: a step
@@ -809,7 +810,8 @@ launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u32* hi
 // One element of a run, ranked by scanning the tags to both ends of the run (at most FIN_LIMIT - 1 steps).
 template<int LOW_BITS>
 __device__ __forceinline__ void
-finish_scan_run(u32 j, u32 tag, const u32* s_tag, unsigned short* s_src, u32& steps, u32& moved, bool& unsorted_long)
+finish_scan_run(u32 j, u32 tag, const u32* s_tag, unsigned short* s_src, u32& steps, u32& moved, bool& unsorted_long,
+                u32& long_elements, u32 base, u32* __restrict__ stats, u32* __restrict__ long_runs)
 {
   constexpr u32 LOW_MASK = (1u << LOW_BITS) - 1;
   const u32 lo = tag & LOW_MASK;
@@ -849,6 +851,9 @@ finish_scan_run(u32 j, u32 tag, const u32* s_tag, unsigned short* s_src, u32& st
   steps += FIN_LIMIT - 1 - budget;
   if (too_long) { // the run stays as it is: fine if it is in order already (identical points are)
     unsorted_long |= !(tag & FIN_HEAD) && (s_tag[j] & LOW_MASK) > lo;
+    long_elements += j < FIN_TILE ? 1u : 0u;
+    if (tag & FIN_HEAD) // its first element (seen by the tile that owns the run) puts the run on the list
+      long_runs[atomicAdd(stats + 1, 1u)] = base + j;
   } else if (!skip) {
     const u32 p = (u32)l + rk;
     if (p != j) {
@@ -881,7 +886,8 @@ finish_tags(const u64* __restrict__ kp, u32 tid, u32* s_tag)
 
 template<int LOW_BITS>
 __global__ void __launch_bounds__(FIN_THREADS, 6)
-segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32* __restrict__ stats)
+segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32* __restrict__ stats,
+                      u32* __restrict__ long_runs)
 {
   static_assert(LOW_BITS <= 24, "tags keep the low bits next to two flag bits");
   // [0] left sentinel, [1 + j] window element j, then sentinels up to the end of the last warp window
@@ -926,7 +932,7 @@ segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32*
   // run of the window has elements (no divergent scans; runs of real clouds have a handful of elements).  Runs
   // that reach beyond the window take the scalar scan over the tags (finish_scan_run).  Every element is seen by
   // one or two windows and handled by exactly one: lanes 0..7 of a window are lanes 24..31 of the one before.
-  u32 steps = 0, moved = 0;
+  u32 steps = 0, moved = 0, long_elements = 0;
   bool unsorted_long = false;
   const u32 lane = tid & 31, warp = tid >> 5;
   const u32 le = 0xffffffffu >> (31 - lane); // lanes <= mine
@@ -936,7 +942,7 @@ segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32*
     for (u32 j = tid; j < valid; j += FIN_THREADS) {
       const u32 tag = s_tag[1 + j];
       if (!(tag & s_tag[2 + j] & FIN_HEAD))
-        finish_scan_run<LOW_BITS>(j, tag, s_tag, s_src, steps, moved, unsorted_long);
+        finish_scan_run<LOW_BITS>(j, tag, s_tag, s_src, steps, moved, unsorted_long, long_elements, base, stats, long_runs);
     }
   } else {
 #pragma unroll 1
@@ -977,7 +983,7 @@ segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32*
       }
     }
     if (slow)
-      finish_scan_run<LOW_BITS>(j, tag, s_tag, s_src, steps, moved, unsorted_long);
+      finish_scan_run<LOW_BITS>(j, tag, s_tag, s_src, steps, moved, unsorted_long, long_elements, base, stats, long_runs);
   }
   }
   __syncthreads();
@@ -1001,7 +1007,12 @@ segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32*
     }
   }
   if (unsorted_long)
-    stats[0] = 1u;
+    atomicOr(stats, FIN_UNSORTED);
+  if (__any_sync(0xffffffffu, long_elements != 0)) {
+    long_elements = __reduce_add_sync(0xffffffffu, long_elements);
+    if (lane == 0)
+      atomicAdd(stats, long_elements);
+  }
   // work counters (feedback for the choice of first_pass): scan steps and moved elements
   steps = __reduce_add_sync(0xffffffffu, steps);
   moved = __reduce_add_sync(0xffffffffu, moved);
@@ -1011,6 +1022,173 @@ segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32*
     if (moved)
       atomicAdd(reinterpret_cast<unsigned long long*>(stats + 4), (unsigned long long)moved);
   }
+}
+
+// Runs of more than FIN_LIMIT elements (thousands of returns from one pole, points piled up on the bounds by the
+// clamp of index_point): one block per run on the list the finish kernel wrote.  The block finds the end of the run,
+// returns if the run is in order already, and otherwise sorts it by its low bits with a stable LSD counting sort of
+// its own: histogram by all threads, ranks by one warp walking the run in order (match_any groups equal digits),
+// ping-pong with the same index range of the sort's second buffer pair.  Slow per element, but such runs hold a
+// fraction of a per cent of a cloud; the caller takes the eight LSD passes instead when they hold more than 1/8.
+template<int LOW_BITS>
+__global__ void __launch_bounds__(256)
+long_run_sort_kernel(u64* __restrict__ k0, u32* __restrict__ v0, u64* __restrict__ k1, u32* __restrict__ v1, u32 n,
+                     const u32* __restrict__ long_runs)
+{
+  __shared__ u32 s_end;
+  __shared__ u32 s_bin[256];
+  const u32 tid = threadIdx.x, lane = tid & 31;
+  const u32 start = long_runs[blockIdx.x];
+  const u64 hi0 = k0[start] >> LOW_BITS;
+  constexpr u32 LOW_MASK = (1u << LOW_BITS) - 1;
+  if (tid == 0)
+    s_end = n;
+  __syncthreads();
+  for (u32 i0 = start; i0 < n; i0 += 256) {
+    const u32 i = i0 + tid;
+    const bool diff = i < n && (k0[i] >> LOW_BITS) != hi0;
+    if (diff)
+      atomicMin(&s_end, i);
+    if (__syncthreads_or(diff))
+      break;
+  }
+  __syncthreads();
+  const u32 end = s_end, len = end - start;
+  bool descent = false;
+  for (u32 i = start + 1 + tid; i < end; i += 256)
+    descent |= ((u32)k0[i - 1] & LOW_MASK) > ((u32)k0[i] & LOW_MASK);
+  if (!__syncthreads_or(descent))
+    return;
+  u64* ks = k0 + start;
+  u32* vs = v0 + start;
+  u64* kd = k1 + start;
+  u32* vd = v1 + start;
+  for (int shift = 0; shift < LOW_BITS; shift += 8) {
+    s_bin[tid] = 0;
+    __syncthreads();
+    for (u32 i = tid; i < len; i += 256)
+      atomicAdd(&s_bin[(u32)(ks[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    if (tid < 32) {
+      // exclusive scan of the 256 bins: 8 per lane
+      u32 c[8], sum = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        c[q] = s_bin[lane * 8 + q];
+        sum += c[q];
+      }
+      u32 incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (u32)o)
+          incl += up;
+      }
+      u32 run = incl - sum;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        s_bin[lane * 8 + q] = run;
+        run += c[q];
+      }
+      __syncwarp();
+      // stable scatter, 32 elements at a time in run order
+      const u32 lt = lanemask_lt();
+      for (u32 g0 = 0; g0 < len; g0 += 32) {
+        const u32 i = g0 + lane;
+        const bool valid = i < len;
+        const u64 key = valid ? ks[i] : 0ull;
+        const u32 val = valid ? vs[i] : 0u;
+        const u32 d = valid ? ((u32)(key >> shift) & 255u) : (256u + lane);
+        const u32 peers = __match_any_sync(0xffffffffu, d);
+        const u32 before = __popc(peers & lt);
+        u32 pos = 0;
+        if (valid)
+          pos = s_bin[d] + before;
+        __syncwarp();
+        if (valid && before == 0)
+          s_bin[d] += __popc(peers);
+        __syncwarp();
+        if (valid) {
+          kd[pos] = key;
+          vd[pos] = val;
+        }
+      }
+    }
+    __syncthreads();
+    u64* tk = ks;
+    ks = kd;
+    kd = tk;
+    u32* tv = vs;
+    vs = vd;
+    vd = tv;
+  }
+  if (ks != k0 + start) // an odd number of passes ended in the second buffer pair
+    for (u32 i = tid; i < len; i += 256) {
+      k0[start + i] = ks[i];
+      v0[start + i] = vs[i];
+    }
+}
+
+// after the finish kernel flagged long unsorted runs: `n_runs` entries of `long_runs`
+void
+launch_long_run_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, int first_pass, const u32* long_runs,
+                     u32 n_runs, cudaStream_t stream)
+{
+  if (n_runs == 0)
+    return;
+  switch (first_pass) {
+    case 1: long_run_sort_kernel<8><<<n_runs, 256, 0, stream>>>(keys0, vals0, keys1, vals1, (u32)n, long_runs); break;
+    case 2: long_run_sort_kernel<16><<<n_runs, 256, 0, stream>>>(keys0, vals0, keys1, vals1, (u32)n, long_runs); break;
+    default: long_run_sort_kernel<24><<<n_runs, 256, 0, stream>>>(keys0, vals0, keys1, vals1, (u32)n, long_runs); break;
+  }
+}
+
+// Run lengths of the SORTED keys, for the choice of the sort mode of the next batch (tiler.cu): counter
+// [g * 8 + q] = number of elements i whose key equals key[i - 2^q] above bit 24 (g = 0) or bit 16 (g = 1), i.e. the
+// elements that have at least 2^q predecessors in their run.  sum_q 2^max(q-1,0) * counter[q] bounds the comparisons
+// the finish kernel would need; counter[7] says how many points sit in runs it would leave to long_run_sort_kernel.
+__global__ void __launch_bounds__(256)
+run_stats_kernel(const u64* __restrict__ keys, u32 n, unsigned long long* __restrict__ out)
+{
+  __shared__ u32 s_cnt[16];
+  if (threadIdx.x < 16)
+    s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  u32 c[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q)
+    c[q] = 0;
+  for (u32 i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const u64 k = keys[i];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const u32 d = 1u << q;
+      if (i >= d) {
+        const u64 x = k ^ keys[i - d];
+        c[q] += (x >> 24) == 0 ? 1u : 0u;
+        c[8 + q] += (x >> 16) == 0 ? 1u : 0u;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const u32 v = __reduce_add_sync(0xffffffffu, c[q]);
+    if ((threadIdx.x & 31) == 0 && v)
+      atomicAdd(&s_cnt[q], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 16 && s_cnt[threadIdx.x])
+    atomicAdd(&out[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+void
+launch_run_stats(const u64* sorted_keys, u64 n, unsigned long long* out16, cudaStream_t stream)
+{
+  cudaMemsetAsync(out16, 0, 16 * sizeof(unsigned long long), stream);
+  if (n == 0)
+    return;
+  const int grid = persistent_grid(n, 256, 8);
+  run_stats_kernel<<<grid, 256, 0, stream>>>(sorted_keys, (u32)n, out16);
 }
 
 void
@@ -1029,9 +1207,9 @@ launch_radix_sort_top(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, int
     return;
   const u32 tiles = (u32)((n + FIN_TILE - 1) / FIN_TILE);
   switch (first_pass) {
-    case 1: segment_finish_kernel<8><<<tiles, FIN_THREADS, 0, stream>>>(keys0, vals0, (u32)n, stats); break;
-    case 2: segment_finish_kernel<16><<<tiles, FIN_THREADS, 0, stream>>>(keys0, vals0, (u32)n, stats); break;
-    default: segment_finish_kernel<24><<<tiles, FIN_THREADS, 0, stream>>>(keys0, vals0, (u32)n, stats); break;
+    case 1: segment_finish_kernel<8><<<tiles, FIN_THREADS, 0, stream>>>(keys0, vals0, (u32)n, stats, status); break;
+    case 2: segment_finish_kernel<16><<<tiles, FIN_THREADS, 0, stream>>>(keys0, vals0, (u32)n, stats, status); break;
+    default: segment_finish_kernel<24><<<tiles, FIN_THREADS, 0, stream>>>(keys0, vals0, (u32)n, stats, status); break;
   }
 }
 

@@ -35,13 +35,19 @@ void launch_radix_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, u3
 // The same order with fewer passes over the data (see kernels_index_sort.cu): onesweep passes first_pass .. 7 sort by
 // the key bits from 8 * first_pass up (unsorted keys in keys<sort_input_buffer_top(first_pass)>), then the runs of
 // equal top bits are ordered in place by their low bits.  first_pass = 0 is launch_radix_sort.
-// `stats` (6 u32, 8-byte aligned, zeroed by the caller): [0] != 0: a run longer than the finish kernel handles was not
-// in order -> the caller must run launch_radix_sort_again (all eight passes over the current arrangement, `hist`
-// already scanned); [2..3] u64 scan steps, [4..5] u64 elements moved.  `before_finish`: optional event recorded
-// between the passes and the finish kernel.
+// `stats` (6 u32, 8-byte aligned, zeroed by the caller): [0] bit 31: a run longer than the finish kernel handles was
+// not in order, bits 0..30: elements in such long runs; [1] number of long runs, whose first positions the finish
+// kernel left in `status` (free after the passes) -> the caller runs launch_long_run_sort(status, stats[1]) or, when
+// long runs hold a large part of the points, launch_radix_sort_again (all eight passes over the current arrangement,
+// `hist` already scanned); [2..3] u64 scan steps, [4..5] u64 elements moved.  `before_finish`: optional event
+// recorded between the passes and the finish kernel.
 int sort_input_buffer_top(int first_pass);
 void launch_radix_sort_top(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, int first_pass, u32* hist,
                            u32* status, u32* ticket, u32* stats, cudaStream_t stream, cudaEvent_t before_finish);
+void launch_long_run_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, int first_pass, const u32* long_runs,
+                          u32 n_runs, cudaStream_t stream);
+// run-length counters of sorted keys (16 u64, see run_stats_kernel): input of the sort-mode choice
+void launch_run_stats(const u64* sorted_keys, u64 n, unsigned long long* out16, cudaStream_t stream);
 void launch_radix_sort_again(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, const u32* scanned_hist,
                              u32* status, u32* ticket, cudaStream_t stream);
 

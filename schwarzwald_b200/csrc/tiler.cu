@@ -115,7 +115,8 @@ struct HostScalars
   u64 n_selected;
   u32 scratch[16]; // pinned scratch for the min-distance driver (starts at u32 index 8... see below)
   u64 store_vals[4]; // read-backs of the multi-batch node store
-  u32 sort_stats[6]; // read-back of d_sort_stats(): flag, -, u64 scan steps, u64 moved
+  u32 sort_stats[6]; // read-back of d_sort_stats(): flag + long elements, long runs, u64 scan steps, u64 moved
+  u64 run_stats[16]; // read-back of run_stats_kernel
 };
 
 // One octree level of the multi-batch node store: node table sorted by node index and the
@@ -235,7 +236,8 @@ struct swgpu_tiler
   bool two_pass_compaction = true; // SWGPU_COMPACT=1pass selects level_compact_fused_kernel (A/B measurements)
   int sort_mode = -1;      // -1 = automatic
   int sort_first_pass = 0; // of the current batch
-  int sort_next = -1;      // automatic mode: choice for the next batch from this batch's run lengths (-1 = none yet)
+  int sort_next = 0;       // automatic mode: first pass of the next batch (0 until a probe found short runs)
+  int sort_probe_wait = 0; // automatic mode, eight passes: batches until the sorted keys are probed again
 
   // device scalar slots inside `scalars`
   u32* d_n_nodes() { return scalars.as<u32>() + 0; }
@@ -356,13 +358,15 @@ sync_scalars(swgpu_tiler* h)
 
 // ---- K2 ------------------------------------------------------------------------------------------------
 // Which onesweep pass the sort of this batch starts with (kernels_index_sort.cu: passes over the top digits, then
-// the segment finish).  Automatic mode: 3 (top 40 bits = 13 octree levels) when runs of equal top bits are short,
-// 2 (top 48 bits = 16 levels) for dense clouds.  The first batch of a handle takes 2: a wrong guess of 3 costs
-// eight extra passes (clustered LiDAR reaches thousands of points per level-13 cell at densities where a terrain
-// model has two), a cautious 2 costs one.  Afterwards the scan steps per point the finish kernel counted on the
-// previous batch decide.  The order produced is the same either way.
+// the segment finish).  0 = all eight passes.  Automatic mode never guesses: the first batch of a handle is sorted
+// by the eight passes and its sorted keys are probed (run_stats_kernel, one read of the keys) for the lengths of
+// the runs of equal top 40 / 48 bits; later batches start at pass 3 (top 40 bits = 13 octree levels) when those
+// runs are short (a terrain model: 1.6 points per run), at pass 2 (48 bits) when only those are, and stay with the
+// eight passes for clustered clouds (urban LiDAR: a fifth of the points in runs of more than eight at 6 cm), where
+// ordering the runs costs more than the passes it saves.  A batch that turns out denser than the probed one sends
+// the handle back to the eight passes and a new probe.  The order produced is the same in every mode.
 int
-choose_sort_first_pass(const swgpu_tiler* h, u64 n)
+choose_sort_first_pass(const swgpu_tiler* h)
 {
   if (const char* e = std::getenv("SWGPU_SORT_FIRST_PASS")) { // experiments only
     const int v = std::atoi(e);
@@ -371,15 +375,29 @@ choose_sort_first_pass(const swgpu_tiler* h, u64 n)
   }
   if (h->sort_mode >= 0)
     return h->sort_mode;
-  if (h->sort_next >= 0)
-    return h->sort_next;
-  (void)n;
-  return 2;
+  return h->sort_next > 0 ? h->sort_next : 0;
 }
 
-// the batch's keys are in keys[sort_input_buffer_top(h->sort_first_pass)]; sorted pairs end in keys[0] / vals[0]
+// bound on the comparisons per point the finish kernel needs for runs of equal key bits >= 24 (g = 0) or 16 (g = 1)
+// and the share of points with 128 or more predecessors in their run, from the run_stats_kernel counters
+void
+run_stats_summary(const u64* c, int g, u64 n, double* steps_per_point, double* long_share)
+{
+  double sum = 0;
+  for (int q = 0; q < 8; ++q)
+    sum += (double)(1u << q) * (double)c[g * 8 + q];
+  *steps_per_point = 2.0 * sum / (double)n;
+  *long_share = (double)c[g * 8 + 7] / (double)n;
+}
+
+#define SORT_STEPS_MAX_40 3.0 /* finish kernel at 1.15 steps per point: 0.66 ms per 100 M points, three passes: 2.0 ms */
+#define SORT_STEPS_MAX_48 1.0
+#define SORT_LONG_SHARE_MAX 1e-3
+
+// sorted pairs end in keys0 / vals0; the unsorted keys are in keys<sort_input_buffer_top(fp)>.  `adapt`: a batch of
+// the tiler (automatic mode learns from it), not the stand-alone primitive.
 int
-sort_pairs(swgpu_tiler* h, u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, int fp)
+sort_pairs(swgpu_tiler* h, u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, int fp, bool adapt)
 {
   cudaStream_t s = h->stream;
   launch_radix_sort_top(keys0, keys1, vals0, vals1, n, fp, h->hist.as<u32>(), h->sort_status.as<u32>(),
@@ -391,6 +409,7 @@ sort_pairs(swgpu_tiler* h, u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n
   h->stats.sort_scan_steps = 0;
   h->stats.sort_moved = 0;
   u64 moved = 0;
+  adapt = adapt && h->sort_mode < 0 && n > 0;
   if (fp && n) {
     CK(cudaMemcpyAsync(h->h_scalars->sort_stats, h->d_sort_stats(), 24, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -398,21 +417,49 @@ sort_pairs(swgpu_tiler* h, u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n
     std::memcpy(&h->stats.sort_scan_steps, st + 2, 8);
     std::memcpy(&moved, st + 4, 8);
     h->stats.sort_moved = moved;
-    if (st[0]) { // a long run of equal top bits that is not in order: all eight passes over the current arrangement
+    const bool unsorted_long = (st[0] >> 31) != 0;
+    const u64 long_elements = st[0] & 0x7fffffffu;
+    if (unsorted_long && long_elements * 8 > n) {
+      // long runs of equal top bits hold much of the batch: all eight passes over the current arrangement
       launch_radix_sort_again(keys0, keys1, vals0, vals1, n, h->hist.as<u32>(), h->sort_status.as<u32>(),
                               h->d_tickets() + 8, s);
       h->stats.sort_fallback = 1;
       h->stats.kernel_launches += (u32)sort_passes();
       passes += (u32)sort_passes();
-      h->sort_next = fp >= 3 ? 2 : 0;
-    } else {
+    } else if (unsorted_long) { // a few long runs (dense spots): each is sorted on its own
+      launch_long_run_sort(keys0, keys1, vals0, vals1, n, fp, h->sort_status.as<u32>(), st[1], s);
+      h->stats.kernel_launches += 1;
+      h->stats.sort_fallback = 2;
+    }
+    if (adapt) { // denser than the batch that was probed: back to the eight passes, probe again
       const double steps_per_point = (double)h->stats.sort_scan_steps / (double)n;
-      if (fp >= 3)
-        h->sort_next = steps_per_point > 32.0 ? 2 : 3;
-      else if (fp == 2)
-        h->sort_next = steps_per_point < 0.3 ? 3 : 2;
-      else
-        h->sort_next = fp;
+      const double limit = fp >= 3 ? SORT_STEPS_MAX_40 : SORT_STEPS_MAX_48;
+      if (h->stats.sort_fallback == 1 || steps_per_point > 1.5 * limit ||
+          (double)long_elements > 2 * SORT_LONG_SHARE_MAX * (double)n) {
+        h->sort_next = 0;
+        h->sort_probe_wait = 0;
+      }
+    }
+  } else if (adapt) {
+    if (h->sort_probe_wait > 0) {
+      --h->sort_probe_wait;
+    } else {
+      // the histogram rows are free after the passes: 16 u64 counters
+      unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(h->hist.p);
+      launch_run_stats(keys0, n, d_counts, s);
+      h->stats.kernel_launches += 1;
+      CK(cudaMemcpyAsync(h->h_scalars->run_stats, d_counts, 16 * 8, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      double steps = 0, long_share = 0;
+      run_stats_summary(h->h_scalars->run_stats, 0, n, &steps, &long_share);
+      if (steps <= SORT_STEPS_MAX_40 && long_share <= SORT_LONG_SHARE_MAX) {
+        h->sort_next = 3;
+      } else {
+        run_stats_summary(h->h_scalars->run_stats, 1, n, &steps, &long_share);
+        h->sort_next = (steps <= SORT_STEPS_MAX_48 && long_share <= SORT_LONG_SHARE_MAX) ? 2 : 0;
+      }
+      if (h->sort_next == 0)
+        h->sort_probe_wait = 15; // clustered cloud: look again after 15 more batches
     }
   }
   h->stats.sort_passes = passes;
@@ -427,7 +474,7 @@ int
 sort_batch(swgpu_tiler* h, u64 n)
 {
   return sort_pairs(h, h->keys[0].as<u64>(), h->keys[1].as<u64>(), h->vals[0].as<u32>(), h->vals[1].as<u32>(), n,
-                    h->sort_first_pass);
+                    h->sort_first_pass, true);
 }
 
 int
@@ -918,7 +965,7 @@ run_batch(swgpu_tiler* h)
   // K1 (every launcher is a no-op for an empty shard)
   CK(cudaMemsetAsync(h->hist.p, 0, sort_hist_words() * 4, s));
   CK(cudaMemsetAsync(h->scalars.p, 0, 128, s));
-  h->sort_first_pass = choose_sort_first_pass(h, n);
+  h->sort_first_pass = choose_sort_first_pass(h);
   u64* unsorted_keys = h->keys[sort_input_buffer_top(h->sort_first_pass)].as<u64>(); // the last pass lands in keys[0]
   if (h->d_las) { // K1-LAS: 12 B record in, 24 B position + 8 B key out
     launch_las_encode(h->d_las, n, h->las_t, h->bounds, h->d_xyz, unsorted_keys, h->hist.as<u32>(),
@@ -1261,7 +1308,7 @@ run_batch_store(swgpu_tiler* h)
   record(h, 0);
   CK(cudaMemsetAsync(h->hist.p, 0, sort_hist_words() * 4, s));
   CK(cudaMemsetAsync(h->scalars.p, 0, 128, s));
-  h->sort_first_pass = choose_sort_first_pass(h, n);
+  h->sort_first_pass = choose_sort_first_pass(h);
   u64* unsorted_keys = h->keys[sort_input_buffer_top(h->sort_first_pass)].as<u64>();
   if (h->d_las) {
     launch_las_encode(h->d_las, n, h->las_t, h->bounds, h->d_xyz, unsorted_keys, h->hist.as<u32>(), h->d_n_clamped(),
@@ -2130,7 +2177,7 @@ swgpu_sort_keys_device(swgpu_handle h, uint64_t* keys_device, uint64_t n, uint32
     CK(cudaMemcpyAsync(h->keys[1].p, keys_device, n * 8, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemsetAsync(h->d_sort_stats(), 0, 24, h->stream));
   const int rc = sort_pairs(h, reinterpret_cast<u64*>(keys_device), h->keys[1].as<u64>(), order_device,
-                            h->vals[1].as<u32>(), n, fp);
+                            h->vals[1].as<u32>(), n, fp, false);
   if (rc)
     return rc;
   CK(cudaGetLastError());
@@ -2369,7 +2416,8 @@ swgpu_set_sort_mode(swgpu_handle h, int mode)
   if (!h || mode < -1 || mode > 3)
     return SW_ERR_INVALID_ARGUMENT;
   h->sort_mode = mode;
-  h->sort_next = -1;
+  h->sort_next = 0;
+  h->sort_probe_wait = 0;
   return SW_OK;
 }
 
@@ -2395,7 +2443,7 @@ swgpu_get_stats(swgpu_handle h, swgpu_stats* out)
     cudaEventElapsedTime(&h->stats.ms_index, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->stats.ms_sort, h->ev[1], h->ev[2]);
     h->stats.ms_sort_finish = 0.f;
-    if (h->stats.sort_first_bit && h->stats.n_points && !h->stats.sort_fallback) {
+    if (h->stats.sort_first_bit && h->stats.n_points && h->stats.sort_fallback != 1) {
       float before = 0.f;
       cudaEventElapsedTime(&before, h->ev[1], h->ev[6]);
       h->stats.ms_sort_finish = h->stats.ms_sort - before;

@@ -40,9 +40,9 @@ def _check(keys, mode, fallback=None):
     assert np.array_equal(got_order, perm.astype(np.uint32)), "permutation differs (mode %d)" % mode
     if mode:
         assert stats["sort_first_bit"] == 8 * mode
-        if fallback is not None:
+        if fallback is not None:  # 0 none, 1 eight more LSD passes, 2 long runs sorted one by one
             assert stats["sort_fallback"] == int(fallback), stats
-            assert stats["sort_passes"] == (8 - mode) + (8 if fallback else 0), stats
+            assert stats["sort_passes"] == (8 - mode) + (8 if int(fallback) == 1 else 0), stats
     else:
         assert stats["sort_passes"] == 8 and stats["sort_first_bit"] == 0, stats
     return stats
@@ -93,7 +93,39 @@ def test_long_unsorted_runs_fall_back_to_the_full_sort(mode, seg_len):
     n = 6 * FIN_TILE + 5
     for offset in (0, 17):
         keys = _segments(n, seg_len, 8 * mode, rng, offset=offset)
-        _check(keys, mode, fallback=True)
+        _check(keys, mode, fallback=1)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_a_few_long_runs_are_sorted_one_by_one(mode):
+    """Dense spots: runs of 257 .. 10 000 elements (several tiles) between short runs hold less than 1/8 of the keys."""
+    rng = np.random.default_rng(40 + mode)
+    low = 8 * mode
+    parts, hi = [], 1
+
+    def run(length, lo_range=None, ordered=False):
+        nonlocal hi
+        lo = rng.integers(0, lo_range or (1 << low), length, dtype=np.uint64)
+        if ordered:
+            lo.sort()
+        parts.append((np.uint64(hi) << np.uint64(low)) | lo)
+        hi += 3
+
+    run(300)                      # a long run at the very start
+    for length in (257, 1000, 5000, 10_000, 700):
+        for _ in range(40_000 // 7):
+            run(7)
+        run(length)
+    run(4000, ordered=True)       # long, but in order already
+    run(600, lo_range=3)          # long with many ties
+    for _ in range(3000):
+        run(1)
+    run(258)                      # a long run at the very end
+    keys = np.concatenate(parts)
+    # the input order: runs stay together only after the top-digit passes, so shuffle everything
+    keys = keys[rng.permutation(len(keys))]
+    st = _check(keys, mode, fallback=2)
+    assert st["sort_passes"] == 8 - mode
 
 
 @pytest.mark.parametrize("mode", [1, 2, 3])
@@ -108,7 +140,7 @@ def test_one_inversion_deep_inside_a_long_run(mode):
         keys[a] = (np.uint64(42) << np.uint64(8 * mode)) | (lo[b] + np.uint64(1))  # the only descent: a -> b
         d = np.diff(keys.astype(np.int64))
         assert (d < 0).sum() == 1 and d[a] < 0
-        _check(keys, mode, fallback=True)
+        _check(keys, mode, fallback=1)
 
 
 @pytest.mark.parametrize("mode", [1, 2, 3])
@@ -160,5 +192,5 @@ def test_tiling_result_is_the_same_in_every_sort_mode(port_oracle, kind):
                 assert np.array_equal(wt[:, :3], gt[:, :3]) and np.array_equal(wi, gi), (kind, mode)
             st = t.stats()
             if mode > 0:  # clustered clouds hold runs the finish kernel leaves to the eight-pass fallback
-                assert st["sort_passes"] == 8 - mode + 8 * st["sort_fallback"]
+                assert st["sort_passes"] == 8 - mode + (8 if st["sort_fallback"] == 1 else 0)
                 assert st["sort_fallback"] == 0 or kind == "urban"
