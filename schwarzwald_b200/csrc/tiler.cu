@@ -463,8 +463,9 @@ sort_pairs(swgpu_tiler* h, u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n
     }
   }
   h->stats.sort_passes = passes;
-  // histogram read + passes x 2 x 12 B (+ one read of the pairs by the finish kernel)
-  h->stats.bytes_sort = (8 + (u64)passes * 24 + (fp ? 12 : 0)) * n;
+  // SURVEY 8(d) K2, the accounting model of the roofline: histogram read + 8 passes x 2 x 12 B per point, whatever
+  // this implementation moves (sort_passes and bytes_traffic say what it did move)
+  h->stats.bytes_sort = (8 + (u64)sort_passes() * 24) * n;
   // traffic model: histograms come from K1, the first pass reads no ids, the finish writes what it moves
   h->stats.bytes_traffic += ((u64)passes * 24 - 4 + (fp ? 12 : 0)) * n + 12 * moved;
   return SW_OK;
