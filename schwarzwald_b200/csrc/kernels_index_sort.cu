@@ -556,10 +556,17 @@ onesweep_pass_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ va
       const u32 peers = __match_any_sync(0xffffffffu, d);
 #endif
       const u32 lower = __popc(peers & lt);
+#if RS_SPLIT_TABLE
+      const u32 base = my_cnt[d];
+      __syncwarp();
+      if ((peers >> lane) <= 1u)
+        my_cnt[d] = base + lower + 1u;
+#else
       const u32 base = my_tab[d].y;
       __syncwarp();
       if ((peers >> lane) <= 1u)
         my_tab[d].y = base + lower + 1u;
+#endif
       __syncwarp();
       rank[j] = (unsigned short)(base + lower);
     }
