@@ -489,11 +489,28 @@ level_scan_kernel(u32* __restrict__ tile_sel, u32 n_tiles, u64* __restrict__ n_s
   if (threadIdx.x == 0)
     s_carry_a = 0;
   __syncthreads();
-  for (u32 t0 = 0; t0 < n_slots; t0 += SCAN_THREADS) {
-    const u32 t = t0 + threadIdx.x;
-    const u32 v = (t < n_slots) ? child_count[t] : 0u;
-    const u32 f = v ? 1u : 0u;
-    u32 ia = v, ib = f;
+  // 8 consecutive child slots per thread per iteration (the slots of one node): two scans in one, points and
+  // non-empty children
+  for (u32 t0 = 0; t0 < n_slots; t0 += SCAN_THREADS * 8) {
+    const u32 t = t0 + threadIdx.x * 8;
+    u32 v[8];
+    u32 sa = 0, sb = 0;
+    if (t + 8 <= n_slots) { // n_slots is a multiple of 8 and child_count is 16-byte aligned
+      const uint4 lo4 = *reinterpret_cast<const uint4*>(child_count + t);
+      const uint4 hi4 = *reinterpret_cast<const uint4*>(child_count + t + 4);
+      v[0] = lo4.x; v[1] = lo4.y; v[2] = lo4.z; v[3] = lo4.w;
+      v[4] = hi4.x; v[5] = hi4.y; v[6] = hi4.z; v[7] = hi4.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        v[q] = (t + q < n_slots) ? child_count[t + q] : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      sa += v[q];
+      sb += v[q] ? 1u : 0u;
+    }
+    u32 ia = sa, ib = sb;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const u32 ua = __shfl_up_sync(0xffffffffu, ia, o);
@@ -514,8 +531,15 @@ level_scan_kernel(u32* __restrict__ tile_sel, u32 n_tiles, u64* __restrict__ n_s
       ob += s_wb[w];
     }
     const u32 ca = s_carry_a, cb = s_carry_b;
-    if (f)
-      next_node_start[cb + ob + ib - 1] = ca + oa + ia - v;
+    u32 run_a = ca + oa + ia - sa, run_b = cb + ob + ib - sb;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (v[q]) {
+        next_node_start[run_b] = run_a;
+        ++run_b;
+      }
+      run_a += v[q];
+    }
     __syncthreads();
     if (threadIdx.x == SCAN_THREADS - 1) {
       s_carry_a = ca + oa + ia;
