@@ -294,7 +294,10 @@ block_scan_packed(u32 v, u32* s_w, u32& excl)
 }
 
 #define CHILD_WINDOW 256
-__global__ void __launch_bounds__(SWP_THREADS)
+#ifndef COUNT_MIN_CTAS
+#define COUNT_MIN_CTAS 6 /* 40 registers, no spills; 5 / 8: within 1 % */
+#endif
+__global__ void __launch_bounds__(SWP_THREADS, COUNT_MIN_CTAS)
 level_count_kernel(SwLevelArgs a)
 {
   __shared__ u64 s_k[BLK_SLOTS];
@@ -553,7 +556,10 @@ level_scan_kernel(u32* __restrict__ tile_sel, u32 n_tiles, u64* __restrict__ n_s
   }
 }
 
-__global__ void __launch_bounds__(SWP_THREADS, 4)
+#ifndef SCATTER_MIN_CTAS
+#define SCATTER_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(SWP_THREADS, SCATTER_MIN_CTAS)
 level_scatter_kernel(SwLevelArgs a)
 {
   __shared__ u64 s_k[BLK_SLOTS];
@@ -1163,7 +1169,10 @@ struct ArgminDesc
 // layout (element j * 256 + t: coalesced id / position loads) and handed over through shared memory; the
 // segmented min-scan then runs thread-locally over 8 elements, across the 32 thread aggregates of a warp with
 // 5 shuffle steps, across the warps through shared memory and across tiles by the decoupled look-back.
-__global__ void __launch_bounds__(SWP_THREADS, 4)
+#ifndef ARGMIN_MIN_CTAS
+#define ARGMIN_MIN_CTAS 5 /* 48 registers: 12.48 instead of 13.11 ms per C3-shaped sweep of 100 M points (6: the same) */
+#endif
+__global__ void __launch_bounds__(SWP_THREADS, ARGMIN_MIN_CTAS)
 select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__ ticket)
 {
   __shared__ u64 s_k[BLK_SLOTS]; // keys, then the distances (double bits) of the same elements
