@@ -1240,7 +1240,9 @@ launch_radix_sort_again(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, c
 // =============================================================================================
 // Random 24-byte records: ncu shows 145 B of DRAM reads per record (one 128-byte line per access, 1/8 of the
 // records straddle two).  Neither cudaLimitMaxL2FetchGranularity = 32 nor ld.global.nc.L2::64B changes that on
-// B200 (measured, round 2: 4.15 ms per 100 M records either way), so the loads stay plain.
+// B200 (measured, round 2: 4.15 ms per 100 M records either way), so the loads stay plain.  More records in flight per
+// thread do not help either (2 / 4 / 8 records per iteration: 4.21 / 5.00 / 4.57 ms instead of 4.10): with 17 GB of
+// DRAM traffic in 4.1 ms the kernel sits at the rate the memory delivers random lines, not at a latency limit.
 __global__ void __launch_bounds__(256)
 gather_positions_kernel(const double* __restrict__ src, const u32* __restrict__ perm, u64 n, double* __restrict__ dst)
 {
