@@ -46,8 +46,9 @@ void launch_radix_sort_top(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n
                            u32* status, u32* ticket, u32* stats, cudaStream_t stream, cudaEvent_t before_finish);
 void launch_long_run_sort(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, int first_pass, const u32* long_runs,
                           u32 n_runs, cudaStream_t stream);
-// run-length counters of sorted keys (16 u64, see run_stats_kernel): input of the sort-mode choice
-void launch_run_stats(const u64* sorted_keys, u64 n, unsigned long long* out16, cudaStream_t stream);
+// run-length counters of sorted keys (16 u64 + the number of keys sampled, see run_stats_kernel): input of the
+// sort-mode choice
+void launch_run_stats(const u64* sorted_keys, u64 n, unsigned long long* out17, cudaStream_t stream);
 void launch_radix_sort_again(u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n, const u32* scanned_hist,
                              u32* status, u32* ticket, cudaStream_t stream);
 

@@ -116,7 +116,7 @@ struct HostScalars
   u32 scratch[16]; // pinned scratch for the min-distance driver (starts at u32 index 8... see below)
   u64 store_vals[4]; // read-backs of the multi-batch node store
   u32 sort_stats[6]; // read-back of d_sort_stats(): flag + long elements, long runs, u64 scan steps, u64 moved
-  u64 run_stats[16]; // read-back of run_stats_kernel
+  u64 run_stats[17]; // read-back of run_stats_kernel
 };
 
 // One octree level of the multi-batch node store: node table sorted by node index and the
@@ -359,7 +359,7 @@ sync_scalars(swgpu_tiler* h)
 // ---- K2 ------------------------------------------------------------------------------------------------
 // Which onesweep pass the sort of this batch starts with (kernels_index_sort.cu: passes over the top digits, then
 // the segment finish).  0 = all eight passes.  Automatic mode never guesses: the first batch of a handle is sorted
-// by the eight passes and its sorted keys are probed (run_stats_kernel, one read of the keys) for the lengths of
+// by the eight passes and its sorted keys are probed (run_stats_kernel, a read of every 8th chunk of the keys) for the lengths of
 // the runs of equal top 40 / 48 bits; later batches start at pass 3 (top 40 bits = 13 octree levels) when those
 // runs are short (a terrain model: 1.6 points per run), at pass 2 (48 bits) when only those are, and stay with the
 // eight passes for clustered clouds (urban LiDAR: a fifth of the points in runs of more than eight at 6 cm), where
@@ -444,18 +444,19 @@ sort_pairs(swgpu_tiler* h, u64* keys0, u64* keys1, u32* vals0, u32* vals1, u64 n
     if (h->sort_probe_wait > 0) {
       --h->sort_probe_wait;
     } else {
-      // the histogram rows are free after the passes: 16 u64 counters
+      // the histogram rows are free after the passes: 17 u64 counters
       unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(h->hist.p);
       launch_run_stats(keys0, n, d_counts, s);
       h->stats.kernel_launches += 1;
-      CK(cudaMemcpyAsync(h->h_scalars->run_stats, d_counts, 16 * 8, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(h->h_scalars->run_stats, d_counts, 17 * 8, cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
       double steps = 0, long_share = 0;
-      run_stats_summary(h->h_scalars->run_stats, 0, n, &steps, &long_share);
+      const u64 sampled = std::max<u64>(h->h_scalars->run_stats[16], 1);
+      run_stats_summary(h->h_scalars->run_stats, 0, sampled, &steps, &long_share);
       if (steps <= SORT_STEPS_MAX_40 && long_share <= SORT_LONG_SHARE_MAX) {
         h->sort_next = 3;
       } else {
-        run_stats_summary(h->h_scalars->run_stats, 1, n, &steps, &long_share);
+        run_stats_summary(h->h_scalars->run_stats, 1, sampled, &steps, &long_share);
         h->sort_next = (steps <= SORT_STEPS_MAX_48 && long_share <= SORT_LONG_SHARE_MAX) ? 2 : 0;
       }
       if (h->sort_next == 0)
