@@ -1005,8 +1005,12 @@ launch_level_compact(const SwLevelArgs& a, u64* n_selected, u32 n_child_slots, u
 // Cells are runs of equal (key >> cell_shift) inside a node.  Per cell the reference selects
 // std::min_element of squaredDistanceTo(target) = the FIRST minimum in Morton order.  Here every
 // point evaluates its distance, a segmented inclusive min-scan (ties keep the earlier point) runs
-// over the list in one pass (decoupled look-back carries the open cell across tiles), and the last
-// point of each cell marks the winner in sel[].
+// over the list in one pass, and the last point of each cell marks the winner in sel[].  Tiles are
+// independent: a cell that begins in an earlier tile leaves its partial minimum in a descriptor and
+// argmin_carry_kernel (one thread per tile) combines it with the end-of-tile minima of the tiles
+// before.  (Until the second half of round 2 a single-thread look-back inside the kernel did this;
+// ncu showed a quarter of all stall samples at the block barrier behind it, 33 polls per tile on
+// average: 12.47 -> 11.27 ms per C3-shaped sweep of 100 M points with the wait taken out.)
 #include "jitter_tables.cuh"
 
 struct ArgminVal
@@ -1168,7 +1172,7 @@ struct ArgminDesc
 // [8t, 8t + 8) of the tile: runs are thread-local bit operations); the distances are evaluated in the STRIPED
 // layout (element j * 256 + t: coalesced id / position loads) and handed over through shared memory; the
 // segmented min-scan then runs thread-locally over 8 elements, across the 32 thread aggregates of a warp with
-// 5 shuffle steps, across the warps through shared memory and across tiles by the decoupled look-back.
+// 5 shuffle steps, across the warps through shared memory and across tiles by argmin_carry_kernel.
 #ifndef ARGMIN_MIN_CTAS
 #define ARGMIN_MIN_CTAS 5 /* 48 registers: 12.48 instead of 13.11 ms per C3-shaped sweep of 100 M points (6: the same) */
 #endif
@@ -1178,21 +1182,18 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
   __shared__ u64 s_k[BLK_SLOTS]; // keys, then the distances (double bits) of the same elements
   __shared__ u32 s_r[BLK_SLOTS]; // node rank of every element, bit 31 = its node is not sampled
   __shared__ u64 s_prev, s_next;
-  __shared__ u32 s_slot;
   __shared__ u32 s_w[SWP_WARPS];
   __shared__ ArgminDesc s_wagg[SWP_WARPS];
-  __shared__ ArgminDesc s_tile_carry;
   __shared__ u32 s_perm[JIT_TABLE_WORDS];
   const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (a.sampling == SW_JITTERED)
     jitter_stage_tables(a.node_level, s_perm); // visible after the barriers of phase 0
-  const u32 tile = take_ticket(ticket, &s_slot);
+  const u32 tile = blockIdx.x; // tiles are independent: what crosses a tile boundary is settled by argmin_carry_kernel
   const u64 base = (u64)tile * SW_SWEEP_TILE;
   const u64 e0 = base + 8ull * tid;
   const size_t n_tiles = (size_t)((a.count + SW_SWEEP_TILE - 1) / SW_SWEEP_TILE);
-  u32* flags = reinterpret_cast<u32*>(status);                            // n_tiles u32 (padded to u64)
-  ArgminDesc* agg = reinterpret_cast<ArgminDesc*>(status + n_tiles);      // n_tiles x 16 B
-  ArgminDesc* pfx = reinterpret_cast<ArgminDesc*>(status + 3 * n_tiles);  // n_tiles x 16 B
+  ArgminDesc* first = reinterpret_cast<ArgminDesc*>(status);              // n_tiles x 16 B, zeroed by the launcher
+  ArgminDesc* agg = reinterpret_cast<ArgminDesc*>(status + 2 * n_tiles);  // n_tiles x 16 B
 
   // ---- phase 0 (blocked): node ranks, which nodes are sampled, cell heads and tails --------------------------
   u32 hbits = 0, tbits = 0, abits = 0; // per element: starts a cell, ends a cell, its node is sampled
@@ -1338,7 +1339,7 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
   }
   __syncthreads();
 
-  // ---- tile aggregate, look-back for the run that is open at the tile start ----------------------
+  // ---- tile aggregate: the run that is open at the end of the tile, for the tiles behind this one --------------
   if (threadIdx.x == 0) {
     ArgminVal tv;
     tv.d = s_wagg[0].d;
@@ -1360,67 +1361,16 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
     mine.d = tv.d;
     mine.pos = tv.pos;
     mine.has_head = th ? 1u : 0u;
-    ArgminDesc carry_in;
-    carry_in.d = 0.0;
-    carry_in.pos = 0;
-    carry_in.has_head = 0; // has_head == 0 here means "no carry" (tile 0 or cut by a head)
-    bool have_carry = false;
-    if (tile == 0) {
-      pfx[0] = mine;
-      __threadfence();
-      st_relaxed_u32(flags, 2u);
-    } else {
-      agg[tile] = mine;
-      __threadfence();
-      st_relaxed_u32(flags + tile, 1u);
-      ArgminVal acc;
-      acc.d = 0.0;
-      acc.pos = 0;
-      long long t = (long long)tile - 1;
-      while (t >= 0) {
-        u32 f;
-        do {
-          f = ld_relaxed_u32(flags + t);
-        } while (f == 0);
-        __threadfence();
-        const volatile ArgminDesc* src = (f == 2u) ? (pfx + t) : (agg + t);
-        ArgminVal e;
-        e.d = src->d;
-        e.pos = src->pos;
-        const u32 hh = src->has_head;
-        acc = have_carry ? argmin_op(e, acc) : e;
-        have_carry = true;
-        if (f == 2u || hh)
-          break;
-        --t;
-      }
-      ArgminDesc incl = mine;
-      if (!th && have_carry) {
-        ArgminVal m;
-        m.d = mine.d;
-        m.pos = mine.pos;
-        const ArgminVal r = argmin_op(acc, m);
-        incl.d = r.d;
-        incl.pos = r.pos;
-      }
-      // the inclusive prefix always describes a run that may continue: keep has_head as "valid"
-      incl.has_head = 1u;
-      pfx[tile] = incl;
-      __threadfence();
-      st_relaxed_u32(flags + tile, 2u);
-      carry_in.d = acc.d;
-      carry_in.pos = acc.pos;
-    }
-    carry_in.has_head = have_carry ? 1u : 0u;
-    s_tile_carry = carry_in;
+    agg[tile] = mine; // the run that is open at the end of the tile (the whole tile when it has no head)
   }
-  __syncthreads();
 
   // ---- carry into my first element = (tile carry, previous warps, previous lanes), then the winners ------------
+  // (no barrier needed here: s_wagg was complete at the barrier above, thread 0 only read it)
   ArgminVal cin;
-  cin.d = s_tile_carry.d;
-  cin.pos = s_tile_carry.pos;
-  bool cin_valid = s_tile_carry.has_head != 0;
+  cin.d = 0.0;
+  cin.pos = 0;
+  bool cin_valid = false;
+  bool from_tile_start = true; // no cell head between the start of the tile and my first element
   for (u32 w = 0; w < warp; ++w) {
     ArgminVal wv;
     wv.d = s_wagg[w].d;
@@ -1430,6 +1380,7 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
     else
       cin = argmin_op(cin, wv);
     cin_valid = true;
+    from_tile_start = from_tile_start && !s_wagg[w].has_head;
   }
   if (lane > 0) {
     if (lane_in_cut || !cin_valid)
@@ -1437,6 +1388,7 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
     else
       cin = argmin_op(cin, lane_in);
     cin_valid = true;
+    from_tile_start = from_tile_start && !lane_in_cut;
   }
   const u32 nvalid = e0 >= a.count ? 0u : (a.count - e0 < 8 ? (u32)(a.count - e0) : 8u);
   bool open = cin_valid; // `cur` continues a run that started before my first element
@@ -1446,24 +1398,66 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
     ArgminVal v;
     v.d = d[j];
     v.pos = (u32)(e0 + j);
+    if ((hbits >> j) & 1u)
+      from_tile_start = false;
     if (((hbits >> j) & 1u) || !open)
       cur = v;
     else
       cur = argmin_op(cur, v);
     open = true;
-    if ((u32)j < nvalid && ((tbits >> j) & 1u) && ((abits >> j) & 1u))
-      a.sel[cur.pos] = 1;
+    if ((u32)j < nvalid && ((tbits >> j) & 1u) && ((abits >> j) & 1u)) {
+      if (from_tile_start && tile != 0) {
+        // the cell may have begun in an earlier tile: its winner is decided by argmin_carry_kernel
+        ArgminDesc f;
+        f.d = cur.d;
+        f.pos = cur.pos;
+        f.has_head = 1u; // "valid"
+        first[tile] = f;
+      } else {
+        a.sel[cur.pos] = 1;
+      }
+    }
   }
+}
+
+// One thread per tile whose first cell ends in the tile: the minimum of the part of the cell that lies in earlier
+// tiles (their end-of-tile aggregates, back to the first tile that holds a cell head) against the part in this tile;
+// ties keep the earlier point.
+__global__ void __launch_bounds__(256)
+argmin_carry_kernel(const u64* __restrict__ status, u32 n_tiles, unsigned char* __restrict__ sel)
+{
+  const u32 tile = blockIdx.x * 256 + threadIdx.x;
+  if (tile >= n_tiles)
+    return;
+  const ArgminDesc* first = reinterpret_cast<const ArgminDesc*>(status);
+  const ArgminDesc* agg = reinterpret_cast<const ArgminDesc*>(status + 2 * (size_t)n_tiles);
+  const ArgminDesc f = first[tile];
+  if (!f.has_head)
+    return;
+  ArgminVal best;
+  best.d = f.d;
+  best.pos = f.pos;
+  for (long long t = (long long)tile - 1; t >= 0; --t) {
+    const ArgminDesc e = agg[t];
+    ArgminVal ev;
+    ev.d = e.d;
+    ev.pos = e.pos;
+    best = argmin_op(ev, best); // the earlier tile's points come first
+    if (e.has_head)
+      break;
+  }
+  sel[best.pos] = 1;
 }
 
 void
 launch_select_argmin(const SwArgminArgs& a, u64* status, u32* ticket, cudaStream_t stream)
 {
   const size_t tiles = sweep_tiles(a.count);
-  cudaMemsetAsync(status, 0, tiles * sizeof(u64), stream); // flag words
-  cudaMemsetAsync(ticket, 0, sizeof(u32), stream);
+  (void)ticket;
+  cudaMemsetAsync(status, 0, tiles * sizeof(ArgminDesc), stream); // the "first cell of the tile" descriptors
   argmin_nodes_kernel<<<(a.n_nodes + 255) / 256, 256, 0, stream>>>(a);
   select_argmin_kernel<<<(u32)tiles, SWP_THREADS, 0, stream>>>(a, status, ticket);
+  argmin_carry_kernel<<<(u32)((tiles + 255) / 256), 256, 0, stream>>>(status, (u32)tiles, a.sel);
 }
 
 // =============================================================================================
