@@ -1108,9 +1108,17 @@ jitter_target(u64 key, const JitterNode& jn, const u32* __restrict__ s_perm, dou
   const u64 grid_mask = (1ull << (3 * jn.levels)) - 1ull;
   const u64 idx = rel & grid_mask;
   const u32 lmask = (1u << jn.levels) - 1u;
-  const u32 gz = (u32)contract_bits_by_3(idx) & lmask; // OctreeNodeIndex::to_grid_index, OctreeNodeIndex.h:357-363
-  const u32 gy = (u32)contract_bits_by_3(idx >> 1) & lmask;
-  const u32 gx = (u32)contract_bits_by_3(idx >> 2) & lmask;
+  u32 gx, gy, gz; // OctreeNodeIndex::to_grid_index, OctreeNodeIndex.h:357-363
+  if (jn.levels <= 10) { // the usual grids (128 cells per axis: 21 bits): 32-bit arithmetic
+    const u32 i32 = (u32)idx;
+    gz = contract_bits_by_3_u32(i32) & lmask;
+    gy = contract_bits_by_3_u32(i32 >> 1) & lmask;
+    gx = contract_bits_by_3_u32(i32 >> 2) & lmask;
+  } else {
+    gz = (u32)contract_bits_by_3(idx) & lmask;
+    gy = (u32)contract_bits_by_3(idx >> 1) & lmask;
+    gx = (u32)contract_bits_by_3(idx >> 2) & lmask;
+  }
   // len = min(cells, 64) is a power of two (cells = get_prev_power_of_two): x % len == x & (len - 1)
   const u32 len = jn.cells < 64u ? jn.cells : 64u;
   const u32 ix = (gy + gz) & (len - 1u), iy = (gx + gz) & (len - 1u), iz = (gx + gy) & (len - 1u);
@@ -1173,6 +1181,9 @@ struct ArgminDesc
 // layout (element j * 256 + t: coalesced id / position loads) and handed over through shared memory; the
 // segmented min-scan then runs thread-locally over 8 elements, across the 32 thread aggregates of a warp with
 // 5 shuffle steps, across the warps through shared memory and across tiles by argmin_carry_kernel.
+#ifndef ARGMIN_P1_UNROLL
+#define ARGMIN_P1_UNROLL 4 /* elements of the distance phase whose loads are in flight together; fully unrolled (8) the kernel has 7 400 SASS lines and 14 % of its stall samples wait for instructions: 11.00 -> 10.60 ms per C3-shaped sweep */
+#endif
 #ifndef ARGMIN_MIN_CTAS
 #define ARGMIN_MIN_CTAS 5 /* 48 registers: 12.48 instead of 13.11 ms per C3-shaped sweep of 100 M points (6: the same) */
 #endif
@@ -1245,7 +1256,8 @@ select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__
   __syncthreads();
 
   // ---- phase 1 (striped): squared distance of every sampled point to the target of its cell ------------------
-#pragma unroll
+  constexpr int P1_UNROLL = ARGMIN_P1_UNROLL;
+#pragma unroll P1_UNROLL
   for (int j = 0; j < SWP_ITEMS; ++j) {
     const u32 p = j * SWP_THREADS + tid;
     const u64 i = base + p;
