@@ -181,6 +181,19 @@ def test_coarse_spacing_candidate_level_root(port_oracle):
         assert_same(*run_both(port_oracle, xyz, sampling, "ACCURATE", bmin, bmax, spacing, 50, 1))
 
 
+@pytest.mark.parametrize("sampling", ["GRID_CENTER", "JITTERED"])
+def test_cells_that_span_many_tiles(port_oracle, sampling):
+    """Coarse spacing on a dense cloud: a selection cell holds tens of thousands of points, i.e. it spans many
+    2 048-point tiles of select_argmin_kernel; argmin_carry_kernel has to walk back over tiles without a cell head."""
+    _torch_cuda()
+    xyz = make_cloud("uniform", 1_200_000, 21, side_m=50.0)
+    xyz[500_000:500_600] = xyz[499_999]  # ties: equal distances inside one cell, the first one wins
+    bmin, bmax, _ = setup_case(xyz)
+    spacing = np.float32((bmax[0] - bmin[0]) / 18.0)  # JITTERED needs a 16 x 16 x 16 grid at least
+    for tiling in TILINGS:
+        assert_same(*run_both(port_oracle, xyz, sampling, tiling, bmin, bmax, spacing, 30_000, 8))
+
+
 def test_error_codes_match_reference_exceptions(port_oracle):
     """JITTERED throws for grids below 16 cells per axis (Sampling.h:632-635); FAST's scatter throws
     when a batch has fewer points than indexing threads (threading/Parallel.h:181-186)."""
