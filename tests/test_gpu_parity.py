@@ -189,7 +189,9 @@ def test_cells_that_span_many_tiles(port_oracle, sampling):
     xyz = make_cloud("uniform", 1_200_000, 21, side_m=50.0)
     xyz[500_000:500_600] = xyz[499_999]  # ties: equal distances inside one cell, the first one wins
     bmin, bmax, _ = setup_case(xyz)
-    spacing = np.float32((bmax[0] - bmin[0]) / 18.0)  # JITTERED needs a 16 x 16 x 16 grid at least
+    # GRID_CENTER: 3 cells per axis, 44 000 points per cell = 20 tiles; JITTERED needs a 16 x 16 x 16 grid at least
+    # (300 points per cell: nearly every tile starts inside a cell)
+    spacing = np.float32((bmax[0] - bmin[0]) / (3.0 if sampling == "GRID_CENTER" else 18.0))
     for tiling in TILINGS:
         assert_same(*run_both(port_oracle, xyz, sampling, tiling, bmin, bmax, spacing, 30_000, 8))
 
