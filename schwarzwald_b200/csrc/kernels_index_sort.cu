@@ -949,49 +949,51 @@ segment_finish_kernel(u64* __restrict__ keys, u32* __restrict__ ids, u32 n, u32*
     for (u32 j = tid; j < valid; j += FIN_THREADS) {
       const u32 tag = s_tag[1 + j];
       if (!(tag & s_tag[2 + j] & FIN_HEAD))
-        finish_scan_run<LOW_BITS>(j, tag, s_tag, s_src, steps, moved, unsorted_long, long_elements, base, stats, long_runs);
+        finish_scan_run<LOW_BITS>(j, tag, s_tag, s_src, steps, moved, unsorted_long, long_elements, base, stats,
+                                  long_runs);
     }
   } else {
 #pragma unroll 1
-  for (u32 w0 = warp * FIN_STRIDE; w0 < valid; w0 += (FIN_THREADS / 32) * FIN_STRIDE) {
-    const u32 j = w0 + lane;
-    const u32 tag = s_tag[1 + j]; // elements behind the last valid one carry FIN_HEAD
-    const u32 lo = tag & LOW_MASK;
-    const u32 heads = __ballot_sync(0xffffffffu, (tag & FIN_HEAD) != 0);
-    const u32 hb = heads & le, ha = heads & ~le;
-    const bool live = j < valid;
-    const int l_lane = 31 - __clz(hb); // -1: the run starts before the window
-    const int r_lane = ha ? __ffs(ha) - 1 : 32;
-    // runs of this window that the shuffle path can rank
-    const bool mine = live && hb != 0 && l_lane < FIN_STRIDE;
-    const bool fast = mine && ha != 0;
-    // elements nobody else scans: runs that leave the window at its end, or entered it more than 8 lanes ago (the
-    // previous window could not see their end either); in the first window every run that comes from the left
-    const bool slow = live && ((mine && ha == 0) || (hb == 0 && (lane >= 32 - FIN_STRIDE || w0 == 0)));
-    const int len = fast ? r_lane - l_lane : 1;
-    const int maxlen = __reduce_max_sync(0xffffffffu, len);
-    // (low bits, lane) as one number: an element precedes another iff its number is smaller (ties: earlier lane)
-    const u32 val = (lo << 5) | lane;
-    u32 rank = 0;
-    for (int d = 1; d < maxlen; ++d) {
-      int partner = (int)lane + d;
-      if (partner >= r_lane)
-        partner -= len;
-      const u32 v = __shfl_sync(0xffffffffu, val, d < len ? partner : (int)lane);
-      rank += v < val ? 1u : 0u;
-    }
-    if (fast) {
-      steps += (u32)len - 1u;
-      const u32 l = w0 + (u32)l_lane;
-      const u32 p = l + rank;
-      if (l < FIN_TILE && p != j) { // runs that start behind this tile belong to the next one
-        s_src[p] = (unsigned short)j;
-        ++moved;
+    for (u32 w0 = warp * FIN_STRIDE; w0 < valid; w0 += (FIN_THREADS / 32) * FIN_STRIDE) {
+      const u32 j = w0 + lane;
+      const u32 tag = s_tag[1 + j]; // elements behind the last valid one carry FIN_HEAD
+      const u32 lo = tag & LOW_MASK;
+      const u32 heads = __ballot_sync(0xffffffffu, (tag & FIN_HEAD) != 0);
+      const u32 hb = heads & le, ha = heads & ~le;
+      const bool live = j < valid;
+      const int l_lane = 31 - __clz(hb); // -1: the run starts before the window
+      const int r_lane = ha ? __ffs(ha) - 1 : 32;
+      // runs of this window that the shuffle path can rank
+      const bool mine = live && hb != 0 && l_lane < FIN_STRIDE;
+      const bool fast = mine && ha != 0;
+      // elements nobody else scans: runs that leave the window at its end, or entered it more than 8 lanes ago (the
+      // previous window could not see their end either); in the first window every run that comes from the left
+      const bool slow = live && ((mine && ha == 0) || (hb == 0 && (lane >= 32 - FIN_STRIDE || w0 == 0)));
+      const int len = fast ? r_lane - l_lane : 1;
+      const int maxlen = __reduce_max_sync(0xffffffffu, len);
+      // (low bits, lane) as one number: an element precedes another iff its number is smaller (ties: earlier lane)
+      const u32 val = (lo << 5) | lane;
+      u32 rank = 0;
+      for (int d = 1; d < maxlen; ++d) {
+        int partner = (int)lane + d;
+        if (partner >= r_lane)
+          partner -= len;
+        const u32 v = __shfl_sync(0xffffffffu, val, d < len ? partner : (int)lane);
+        rank += v < val ? 1u : 0u;
       }
+      if (fast) {
+        steps += (u32)len - 1u;
+        const u32 l = w0 + (u32)l_lane;
+        const u32 p = l + rank;
+        if (l < FIN_TILE && p != j) { // runs that start behind this tile belong to the next one
+          s_src[p] = (unsigned short)j;
+          ++moved;
+        }
+      }
+      if (slow)
+        finish_scan_run<LOW_BITS>(j, tag, s_tag, s_src, steps, moved, unsorted_long, long_elements, base, stats,
+                                  long_runs);
     }
-    if (slow)
-      finish_scan_run<LOW_BITS>(j, tag, s_tag, s_src, steps, moved, unsorted_long, long_elements, base, stats, long_runs);
-  }
   }
   __syncthreads();
 
