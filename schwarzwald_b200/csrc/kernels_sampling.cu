@@ -1083,10 +1083,15 @@ jitter_node_setup(const double mn[3], const double mx[3], const SwArgminArgs& a,
 #define JIT_ROW 64
 #define JIT_TABLE_WORDS (3 * 3 * JIT_ROW) /* [size class 16 / 32 / 64][row][entry] */
 
-__device__ __forceinline__ void
-jitter_stage_tables(int node_level, u32* s_perm)
+// All 16 possible start indices, laid out the way the kernel wants them; filled once per device by
+// jitter_build_tables_kernel.  (Staging straight from the __constant__ tables cost 14 % of select_argmin_kernel's stall
+// samples: 576 constant loads per block, every lane at another address, plus the index divisions.)
+__device__ u32 g_jit_staged[16][JIT_TABLE_WORDS];
+
+__global__ void __launch_bounds__(256)
+jitter_build_tables_kernel()
 {
-  const u32 start_index = (3u * (u32)(node_level + 1)) % 16u;
+  const u32 start_index = blockIdx.x;
   for (u32 e = threadIdx.x; e < JIT_TABLE_WORDS; e += blockDim.x) {
     const u32 cls = e / (3 * JIT_ROW), row = (e / JIT_ROW) % 3, i = e % JIT_ROW;
     const u32 t = (start_index + row) % 16u;
@@ -1097,8 +1102,16 @@ jitter_stage_tables(int node_level, u32* s_perm)
       v = i < 32 ? PERMUTATIONS_32[t][i] : 0u;
     else
       v = PERMUTATIONS_64[t][i];
-    s_perm[e] = v;
+    g_jit_staged[start_index][e] = v;
   }
+}
+
+__device__ __forceinline__ void
+jitter_stage_tables(int node_level, u32* s_perm)
+{
+  const u32* __restrict__ src = g_jit_staged[(3u * (u32)(node_level + 1)) % 16u];
+  for (u32 e = threadIdx.x; e < JIT_TABLE_WORDS; e += blockDim.x)
+    s_perm[e] = src[e];
 }
 
 __device__ __forceinline__ void
@@ -1466,6 +1479,18 @@ launch_select_argmin(const SwArgminArgs& a, u64* status, u32* ticket, cudaStream
 {
   const size_t tiles = sweep_tiles(a.count);
   (void)ticket;
+  if (a.sampling == SW_JITTERED) { // the staged permutation tables exist once per device
+    static bool built[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !built[dev]) {
+      // once per device and process: wait for it, handles on other streams of this device rely on the flag
+      jitter_build_tables_kernel<<<16, 256, 0, stream>>>();
+      cudaStreamSynchronize(stream);
+      if (dev >= 0 && dev < 64)
+        built[dev] = true;
+    }
+  }
   cudaMemsetAsync(status, 0, tiles * sizeof(ArgminDesc), stream); // the "first cell of the tile" descriptors
   argmin_nodes_kernel<<<(a.n_nodes + 255) / 256, 256, 0, stream>>>(a);
   select_argmin_kernel<<<(u32)tiles, SWP_THREADS, 0, stream>>>(a, status, ticket);
