@@ -230,11 +230,20 @@ __device__ __forceinline__ void
 load_keys_blocked(const u64* __restrict__ in_key, u64 base, u64 count, u64* s_k, u64* s_prev, u64 k[BLK_ITEMS], u64& prev)
 {
   const u32 tid = threadIdx.x;
+  if (base + SW_SWEEP_TILE <= count) { // all tiles but the last: no bounds tests
+    const u64* __restrict__ kp = in_key + base;
 #pragma unroll
-  for (int j = 0; j < BLK_ITEMS; ++j) {
-    const u32 p = j * SWP_THREADS + tid;
-    const u64 i = base + p;
-    s_k[BLK_PAD(p)] = (i < count) ? (in_key[i] & SW_KEY_MASK) : ~0ull;
+    for (int j = 0; j < BLK_ITEMS; ++j) {
+      const u32 p = j * SWP_THREADS + tid;
+      s_k[BLK_PAD(p)] = kp[p] & SW_KEY_MASK;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < BLK_ITEMS; ++j) {
+      const u32 p = j * SWP_THREADS + tid;
+      const u64 i = base + p;
+      s_k[BLK_PAD(p)] = (i < count) ? (in_key[i] & SW_KEY_MASK) : ~0ull;
+    }
   }
   if (tid == 0)
     *s_prev = base ? (in_key[base - 1] & SW_KEY_MASK) : 0ull;
@@ -574,10 +583,19 @@ level_scatter_kernel(SwLevelArgs a)
 
   // ---- load: keys and ids, coalesced, transposed to the blocked layout ----------------------------------
   if (a.in_idx) {
+    const u32* __restrict__ ip = a.in_idx + base;
+    if (tile_valid == SW_SWEEP_TILE) {
 #pragma unroll
-    for (int j = 0; j < BLK_ITEMS; ++j) {
-      const u32 p = j * SWP_THREADS + tid;
-      s_i[BLK_PAD(p)] = (p < tile_valid) ? a.in_idx[base + p] : 0u;
+      for (int j = 0; j < BLK_ITEMS; ++j) {
+        const u32 p = j * SWP_THREADS + tid;
+        s_i[BLK_PAD(p)] = ip[p];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < BLK_ITEMS; ++j) {
+        const u32 p = j * SWP_THREADS + tid;
+        s_i[BLK_PAD(p)] = (p < tile_valid) ? ip[p] : 0u;
+      }
     }
   }
   u64 k[BLK_ITEMS];
@@ -1198,7 +1216,7 @@ struct ArgminDesc
 #define ARGMIN_P1_UNROLL 4 /* elements of the distance phase whose loads are in flight together; fully unrolled (8) the kernel has 7 400 SASS lines and 14 % of its stall samples wait for instructions: 11.00 -> 10.60 ms per C3-shaped sweep */
 #endif
 #ifndef ARGMIN_MIN_CTAS
-#define ARGMIN_MIN_CTAS 5 /* 48 registers: 12.48 instead of 13.11 ms per C3-shaped sweep of 100 M points (6: the same) */
+#define ARGMIN_MIN_CTAS 6 /* 40 registers.  4 -> 5 blocks per SM: 13.11 -> 12.48 ms per C3-shaped sweep of 100 M points; 5 -> 6 gave nothing while the kernel waited on the look-back, 10.30 -> 10.17 ms without it */
 #endif
 __global__ void __launch_bounds__(SWP_THREADS, ARGMIN_MIN_CTAS)
 select_argmin_kernel(SwArgminArgs a, u64* __restrict__ status, u32* __restrict__ ticket)
