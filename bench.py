@@ -697,7 +697,7 @@ def main():
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": captured_traffic(n_sorted), "algorithmic_bytes_per_launch": 24 * n_sorted,
                 "whole_step": {"algorithmic_bytes": int(bytes_all),
-                               "model": "SURVEY 8(d): index 36 + sort 8 + 24 per pass + gather 2 x 24 (strategies that "
+                               "model": "SURVEY 8(d): index 36 + sort 8 + 8 passes x 24 (the model's pass count, whatever ran: see 'sort') + gather 2 x 24 (strategies that "
                                         "read positions) + per level (12 + 24 pos) r + 12 (r - s) + 4 s, all GPUs",
                                "achieved": bytes_all / (ms_per_step * 1e-3) / 1e9,
                                "frac": bytes_all / (ms_per_step * 1e-3) / 1e9 / (peak * world),
